@@ -1,0 +1,1188 @@
+// Bandwidth-bound kernels of the attack path: 128-bit vectorised, channel-innermost (NHWC) so that a
+// warp touches contiguous bytes, per-channel reductions done warp/block-first and flushed with a
+// handful of global atomics per block.  Grids are sized in multiples of the SM count.
+#include "sfk_common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+using bf16 = __nv_bfloat16;
+
+inline unsigned grid_for(long work_items, int per_sm_blocks = 8) {
+  long blocks = (work_items + kBlock - 1) / kBlock;
+  long cap = static_cast<long>(sfk_num_sms()) * per_sm_blocks;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+// flush per-thread channel-vector accumulators (thread owns channels [cv*8, cv*8+8)) to global[n][C]
+__device__ __forceinline__ void flush_channel_acc(float* sacc, const float* acc, int cv, int C, float* gdst) {
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&sacc[cv * 8 + i], acc[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(gdst + i, sacc[i]);
+}
+
+// ============================================================================================
+// first-layer conv (Cin = 3)
+__global__ void conv_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                   bf16* __restrict__ out, int N, int H, int W, int Cout, int relu) {
+  extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;  // k = c*9 + ky*3 + kx
+    sw[i] = w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long total = static_cast<long>(N) * H * W * groups;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    long p = idx / groups;
+    const int wq = p % W;
+    p /= W;
+    const int hq = p % H;
+    const int n = p / H;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = sw[27 * Cout + g * 8 + i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* xp = x + (static_cast<long>(n) * 3 + c) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ih = hq + ky - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iw = wq + kx - 1;
+          if (iw < 0 || iw >= W) continue;
+          const float xv = __ldg(xp + static_cast<long>(ih) * W + iw);
+          const float* wp = sw + (c * 9 + ky * 3 + kx) * Cout + g * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
+        }
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    stg8(out + ((static_cast<long>(n) * H + hq) * W + wq) * Cout + g * 8, pack8(acc));
+  }
+}
+
+__global__ void conv_c3_bwd_kernel(const bf16* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int N,
+                                   int H, int W, int Cout, int LP /* lanes per pixel, power of 2 <= 8 */) {
+  extern __shared__ float sw[];  // [9][Cout][3]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    const int c = i % 3, co = (i / 3) % Cout, k = i / (3 * Cout);
+    sw[i] = w[co * 27 + c * 9 + k];
+  }
+  __syncthreads();
+  const int vecs = Cout / 8;
+  const long total = static_cast<long>(N) * H * W * LP;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  const long rounds = (total + stride - 1) / stride;
+  for (long rr = 0; rr < rounds; ++rr) {
+    const long idx = rr * stride + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    const bool active = idx < total;
+    const int sub = idx % LP;
+    long p = idx / LP;
+    const int wq = p % W;
+    p /= W;
+    const int hq = p % H;
+    const int n = p / H;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (active) {
+      for (int ky = 0; ky < 3; ++ky) {
+        const int oh = hq - ky + 1;
+        if (oh < 0 || oh >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ow = wq - kx + 1;
+          if (ow < 0 || ow >= W) continue;
+          const bf16* gp = g + ((static_cast<long>(n) * H + oh) * W + ow) * Cout;
+          const float* wp = sw + (ky * 3 + kx) * Cout * 3;
+          for (int v = sub; v < vecs; v += LP) {
+            float gv[8];
+            unpack8(ldg8(gp + v * 8), gv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float* w3 = wp + (v * 8 + i) * 3;
+              a0 = fmaf(gv[i], w3[0], a0);
+              a1 = fmaf(gv[i], w3[1], a1);
+              a2 = fmaf(gv[i], w3[2], a2);
+            }
+          }
+        }
+      }
+    }
+    for (int o = LP >> 1; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (active && sub == 0) {
+      const long hw = static_cast<long>(H) * W;
+      float* o = gx + static_cast<long>(n) * 3 * hw + static_cast<long>(hq) * W + wq;
+      o[0] = a0;
+      o[hw] = a1;
+      o[2 * hw] = a2;
+    }
+  }
+}
+
+// ============================================================================================
+// pools
+__global__ void avgpool_affine_kernel(const float* __restrict__ x, float* __restrict__ y, long planes, int H, int W, int k,
+                                      float a, float b) {
+  const int Ho = H / k, Wo = W / k;
+  const long total = planes * Ho * Wo;
+  const float inv = a / static_cast<float>(k * k);
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int j = idx % Wo;
+    long p = idx / Wo;
+    const int i = p % Ho;
+    const long pl = p / Ho;
+    const float* xp = x + (pl * H + static_cast<long>(i) * k) * W + static_cast<long>(j) * k;
+    float s = 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) s += __ldg(xp + static_cast<long>(dy) * W + dx);
+    y[idx] = s * inv + b;
+  }
+}
+
+__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, vecs = C / 8;
+  const long total = static_cast<long>(N) * Ho * Wo * vecs;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    long p = idx / vecs;
+    const int j = p % Wo;
+    p /= Wo;
+    const int i = p % Ho;
+    const int n = p / Ho;
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int dy = 0; dy < 2; ++dy) {
+      const int h = 2 * i + dy;
+      if (h >= H) continue;
+      for (int dx = 0; dx < 2; ++dx) {
+        const int w = 2 * j + dx;
+        if (w >= W) continue;
+        float t[8];
+        unpack8(ldg8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8), t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], t[q]);
+      }
+    }
+    stg8(y + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8, pack8(m));
+  }
+}
+
+// One thread per pooling window x 8 channels: routes gy to the FIRST maximum in row-major window order
+// (torch's tie-break; ties are common in bf16), adds the optional feature-tap gradient, applies the ReLU mask.
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy, bf16* __restrict__ gx,
+                                    const bf16* __restrict__ tap_ref, float tap_coef, int relu_mask, int N, int H, int W, int C) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, vecs = C / 8;
+  const long total = static_cast<long>(N) * Ho * Wo * vecs;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    long p = idx / vecs;
+    const int j = p % Wo;
+    p /= Wo;
+    const int i = p % Ho;
+    const int n = p / Ho;
+    float xin[4][8];
+    bool inb[4];
+    float m[8];
+    int am[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      m[q] = -INFINITY;
+      am[q] = -1;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int h = 2 * i + (s >> 1), w = 2 * j + (s & 1);
+      inb[s] = (h < H) && (w < W);
+      if (inb[s]) {
+        unpack8(ldg8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8), xin[s]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (xin[s][q] > m[q]) {
+            m[q] = xin[s][q];
+            am[q] = s;
+          }
+        }
+      }
+    }
+    float g[8];
+    unpack8(ldg8(gy + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8), g);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (!inb[s]) continue;
+      const int h = 2 * i + (s >> 1), w = 2 * j + (s & 1);
+      const long off = ((static_cast<long>(n) * H + h) * W + w) * C + v * 8;
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = (am[q] == s) ? g[q] : 0.f;
+      if (tap_ref) {
+        float r[8];
+        unpack8(ldg8(tap_ref + off), r);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] += tap_coef * (xin[s][q] - r[q]);
+      }
+      if (relu_mask) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = xin[s][q] > 0.f ? o[q] : 0.f;
+      }
+      stg8(gx + off, pack8(o));
+    }
+  }
+}
+
+__global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  // block = (n, channel-vector group); threads stride over HW
+  const int n = blockIdx.y, vecs = C / 8;
+  const int v = blockIdx.x;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    float t[8];
+    unpack8(ldg8(x + (static_cast<long>(n) * HW + p) * C + v * 8), t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += t[q];
+  }
+  __shared__ float red[8][kBlock / 32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float s = warp_sum(acc[q]);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+    for (int k = 0; k < blockDim.x / 32; ++k) s += red[threadIdx.x][k];
+    y[static_cast<long>(n) * C + v * 8 + threadIdx.x] = s / static_cast<float>(HW);
+  }
+  (void)vecs;
+}
+
+__global__ void gap_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gy, bf16* __restrict__ gx, int N, int HW, int C) {
+  const int vecs = C / 8;
+  const long total = static_cast<long>(N) * HW * vecs;
+  const float inv = 1.f / static_cast<float>(HW);
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    const long p = idx / vecs;
+    const int n = p / HW;
+    float t[8], o[8];
+    unpack8(ldg8(x + p * C + v * 8), t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = t[q] > 0.f ? gy[static_cast<long>(n) * C + v * 8 + q] * inv : 0.f;
+    stg8(gx + p * C + v * 8, pack8(o));
+  }
+}
+
+// ============================================================================================
+// losses
+__global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restrict__ ref, bf16* __restrict__ g, float* __restrict__ loss,
+                               float coef_loss, float coef_grad, int accumulate, int relu_mask, long per_sample) {
+  const int n = blockIdx.y;
+  const long vecs = per_sample / 8;
+  const long base = static_cast<long>(n) * per_sample;
+  float lsum = 0.f;
+  for (long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; v < vecs; v += static_cast<long>(gridDim.x) * blockDim.x) {
+    float a[8], r[8];
+    unpack8(ldg8(f + base + v * 8), a);
+    unpack8(ldg8(ref + base + v * 8), r);
+    float o[8];
+    if (g && accumulate) unpack8(ldg8(g + base + v * 8), o);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float d = a[q] - r[q];
+      lsum += d * d;
+      float gq = coef_grad * d;
+      if (relu_mask && !(a[q] > 0.f)) gq = 0.f;
+      o[q] = (g && accumulate) ? o[q] + gq : gq;
+    }
+    if (g) stg8(g + base + v * 8, pack8(o));
+  }
+  lsum = warp_sum(lsum);
+  __shared__ float red[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float s = 0.f;
+    for (int k = 0; k < blockDim.x / 32; ++k) s += red[k];
+    atomicAdd(loss + n, coef_loss * s);
+  }
+}
+
+__global__ void image_loss_grad_kernel(const float* __restrict__ img, const float* __restrict__ ref, const float* __restrict__ gpool,
+                                       float* __restrict__ g, float* __restrict__ loss, float coef_loss, float coef_grad, int S, int k) {
+  const int n = blockIdx.y;
+  const long per = 3L * S * S;
+  const int Sp = S / k;
+  const float invk2 = 1.f / static_cast<float>(k * k);
+  float lsum = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int w = i % S;
+    long p = i / S;
+    const int h = p % S;
+    const int c = p / S;
+    const long off = static_cast<long>(n) * per + i;
+    const float d = img[off] - ref[off];
+    lsum += d * d;
+    float gv = coef_grad * d;
+    if (gpool) gv += invk2 * __ldg(gpool + ((static_cast<long>(n) * 3 + c) * Sp + h / k) * Sp + w / k);
+    g[off] = gv;
+  }
+  lsum = warp_sum(lsum);
+  __shared__ float red[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float s = 0.f;
+    for (int q = 0; q < blockDim.x / 32; ++q) s += red[q];
+    atomicAdd(loss + n, coef_loss * s);
+  }
+}
+
+// ============================================================================================
+// style space
+__global__ void style_affine_fwd_kernel(const float* __restrict__ w, const float* __restrict__ A, const float* __restrict__ bias,
+                                        const int* __restrict__ row_widx, float* __restrict__ s, int N, int L, int D, int SD, float scale) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < SD; r += warps) {
+    const int l = row_widx[r];
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(A + static_cast<long>(r) * D + k), __ldg(w + (static_cast<long>(n) * L + l) * D + k), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s[static_cast<long>(n) * SD + r] = bias[r] + scale * acc;
+    }
+  }
+}
+
+__global__ void style_affine_bwd_kernel(const float* __restrict__ gs, const float* __restrict__ A, const int* __restrict__ layer_row_start,
+                                        const int* __restrict__ layer_widx, int n_layers, float* __restrict__ gw, int N, int L, int D, int SD,
+                                        float scale) {
+  const long total = static_cast<long>(N) * L * D;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int k = idx % D;
+    const int l = (idx / D) % L;
+    const int n = idx / (static_cast<long>(D) * L);
+    float acc = 0.f;
+    for (int ly = 0; ly < n_layers; ++ly) {
+      if (layer_widx[ly] != l) continue;
+      for (int r = layer_row_start[ly]; r < layer_row_start[ly + 1]; ++r)
+        acc = fmaf(__ldg(gs + static_cast<long>(n) * SD + r), __ldg(A + static_cast<long>(r) * D + k), acc);
+    }
+    gw[idx] = scale * acc;
+  }
+}
+
+__global__ void demod_fwd_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ Q, float* __restrict__ d, int N, int Cin, int Cout) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = N * Cout;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < total; r += warps) {
+    const int j = r % Cout, n = r / Cout;
+    float acc = 0.f;
+    for (int i = lane; i < Cin; i += 32) {
+      const float sv = __ldg(s + static_cast<long>(n) * s_stride + i);
+      acc = fmaf(sv * sv, __ldg(Q + static_cast<long>(j) * Cin + i), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) d[r] = rsqrtf(acc + 1e-8f);
+  }
+}
+
+__global__ void demod_bwd_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ Q, const float* __restrict__ d,
+                                 const float* __restrict__ gdacc, float* __restrict__ gs, int gs_stride, int N, int Cin, int Cout) {
+  const int total = N * Cin;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx % Cin, n = idx / Cin;
+    float acc = 0.f;
+    for (int j = 0; j < Cout; ++j) {
+      const float dj = d[n * Cout + j];
+      acc = fmaf(gdacc[n * Cout + j] * dj * dj, __ldg(Q + static_cast<long>(j) * Cin + i), acc);
+    }
+    gs[static_cast<long>(n) * gs_stride + i] -= __ldg(s + static_cast<long>(n) * s_stride + i) * acc;
+  }
+}
+
+__global__ void modulate_weights_kernel(const float* __restrict__ wbase, const float* __restrict__ s, int s_stride, bf16* __restrict__ wmod,
+                                        int N, long rows /* taps*cout */, int Cin) {
+  const int vecs = Cin / 8;
+  const long total = static_cast<long>(N) * rows * vecs;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    const long r = (idx / vecs) % rows;
+    const int n = idx / (vecs * rows);
+    const float4* wp = reinterpret_cast<const float4*>(wbase + r * Cin + v * 8);
+    const float4* sp = reinterpret_cast<const float4*>(s + static_cast<long>(n) * s_stride + v * 8);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
+    stg8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, pack8(o));
+  }
+}
+
+// ============================================================================================
+// blur (upfirdn2d [1,3,3,1], pad (1,1)) over the phase-planar transposed-conv output, fused with
+// demod, noise, bias, leaky-relu
+__device__ __forceinline__ float blur_w(int t) { return (t == 0 || t == 3) ? 0.25f : 0.75f; }
+
+__global__ void blur_act_fwd_kernel(const bf16* __restrict__ T, bf16* __restrict__ out, const float* __restrict__ d, const float* __restrict__ noise,
+                                    float noise_w, const float* __restrict__ bias, int H, int W, int C) {
+  const int n = blockIdx.y;
+  const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1;
+  const long total = static_cast<long>(Ho) * Wo * vecs;
+  const bf16* Tn = T + static_cast<long>(n) * 4 * Hp * Wp * C;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    long p = idx / vecs;
+    const int pw = p % Wo;
+    const int po = p / Wo;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int q = po + t - 1;
+      if (q < 0 || q > 2 * H) continue;
+      const float wt = blur_w(t);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = pw + u - 1;
+        if (r < 0 || r > 2 * W) continue;
+        const float wgt = wt * blur_w(u);
+        const int plane = (q & 1) * 2 + (r & 1);
+        float tv[8];
+        unpack8(ldg8(Tn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + v * 8), tv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, tv[i], acc[i]);
+      }
+    }
+    const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(po) * Wo + pw) : 0.f;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = v * 8 + i;
+      o[i] = lrelu_fwd(acc[i] * d[static_cast<long>(n) * C + c] + nz + bias[c]);
+    }
+    stg8(out + ((static_cast<long>(n) * Ho + po) * Wo + pw) * C + v * 8, pack8(o));
+  }
+}
+
+// thread = one gT position (q,r) in [0,2H]x[0,2W] x 8 channels.  gz = d*slope(out)*gout is recomputed at the
+// 16 contributing output pixels; the thread also owns output pixel (q,r) for the demod reduction.
+__global__ void blur_act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ gout, bf16* __restrict__ gT, const float* __restrict__ d,
+                                    const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
+                                    int H, int W, int C) {
+  extern __shared__ float sacc[];
+  const int n = blockIdx.y;
+  const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1;
+  const int Hq = 2 * H + 2, Wq = 2 * W + 2;   // cover every (plane, m, n) slot so unused slots are written as zero
+  const long total = static_cast<long>(Hq) * Wq * vecs;
+  const bf16* on = out + static_cast<long>(n) * Ho * Wo * C;
+  const bf16* gn = gout + static_cast<long>(n) * Ho * Wo * C;
+  bf16* gTn = gT + static_cast<long>(n) * 4 * Hp * Wp * C;
+  const int cv = threadIdx.x % vecs;  // constant across the grid-stride loop (total threads % vecs == 0)
+  float dv[8], bv[8], racc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dv[i] = d[static_cast<long>(n) * C + cv * 8 + i];
+    bv[i] = bias[cv * 8 + i];
+    racc[i] = 0.f;
+  }
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    long p = idx / vecs;
+    const int r = p % Wq;
+    const int q = p / Wq;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (q <= 2 * H && r <= 2 * W) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int o = q - t + 1;
+        if (o < 0 || o >= Ho) continue;
+        const float wt = blur_w(t);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pw = r - u + 1;
+          if (pw < 0 || pw >= Wo) continue;
+          const float wgt = wt * blur_w(u);
+          const long off = (static_cast<long>(o) * Wo + pw) * C + cv * 8;
+          float ov[8], gv[8];
+          unpack8(ldg8(on + off), ov);
+          unpack8(ldg8(gn + off), gv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt * lrelu_slope(ov[i]), gv[i], acc[i]);
+        }
+      }
+      if (q < Ho && r < Wo) {
+        const long off = (static_cast<long>(q) * Wo + r) * C + cv * 8;
+        float ov[8], gv[8];
+        unpack8(ldg8(on + off), ov);
+        unpack8(ldg8(gn + off), gv);
+        const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(q) * Wo + r) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) racc[i] = fmaf(gv[i] * lrelu_slope(ov[i]), lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= dv[i];
+    const int plane = (q & 1) * 2 + (r & 1);
+    stg8(gTn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + cv * 8, pack8(acc));
+  }
+  flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
+}
+
+__global__ void act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ gout, bf16* __restrict__ gz, const float* __restrict__ d,
+                               const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc, int HW, int C) {
+  extern __shared__ float sacc[];
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const long total = static_cast<long>(HW) * vecs;
+  const long base = static_cast<long>(n) * HW * C;
+  const int cv = threadIdx.x % vecs;
+  float dv[8], bv[8], racc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dv[i] = d[static_cast<long>(n) * C + cv * 8 + i];
+    bv[i] = bias[cv * 8 + i];
+    racc[i] = 0.f;
+  }
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = idx / vecs;
+    const long off = base + p * C + cv * 8;
+    float ov[8], gv[8], o[8];
+    unpack8(ldg8(out + off), ov);
+    unpack8(ldg8(gout + off), gv);
+    const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gy = gv[i] * lrelu_slope(ov[i]);
+      racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
+      o[i] = gy * dv[i];
+    }
+    stg8(gz + off, pack8(o));
+  }
+  flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
+}
+
+// ============================================================================================
+// ToRGB (1x1 modulated conv to 3 channels, no demod) + skip upsample
+__device__ __forceinline__ float skip_up_sample(const float* __restrict__ sk, int hs, int ws, int o, int p) {
+  // upfirdn2d(skip, k*4, up=2, pad=(2,1)): even o -> (o/2-1: 1/4, o/2: 3/4); odd o -> ((o-1)/2: 3/4, (o+1)/2: 1/4)
+  int i0, i1, j0, j1;
+  float a0, a1, b0, b1;
+  if ((o & 1) == 0) { i0 = o / 2 - 1; i1 = o / 2; a0 = 0.25f; a1 = 0.75f; } else { i0 = (o - 1) / 2; i1 = (o + 1) / 2; a0 = 0.75f; a1 = 0.25f; }
+  if ((p & 1) == 0) { j0 = p / 2 - 1; j1 = p / 2; b0 = 0.25f; b1 = 0.75f; } else { j0 = (p - 1) / 2; j1 = (p + 1) / 2; b0 = 0.75f; b1 = 0.25f; }
+  float r = 0.f;
+  const bool vi0 = i0 >= 0 && i0 < hs, vi1 = i1 >= 0 && i1 < hs, vj0 = j0 >= 0 && j0 < ws, vj1 = j1 >= 0 && j1 < ws;
+  if (vi0 && vj0) r += a0 * b0 * __ldg(sk + static_cast<long>(i0) * ws + j0);
+  if (vi0 && vj1) r += a0 * b1 * __ldg(sk + static_cast<long>(i0) * ws + j1);
+  if (vi1 && vj0) r += a1 * b0 * __ldg(sk + static_cast<long>(i1) * ws + j0);
+  if (vi1 && vj1) r += a1 * b1 * __ldg(sk + static_cast<long>(i1) * ws + j1);
+  return r;
+}
+
+// LP lanes cooperate on one pixel (LP = min(32, C/8)), each lane owns channel vectors lane, lane+LP, ...
+__global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
+                                 const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ rgb, int H, int W, int C, int LP) {
+  extern __shared__ float swm[];  // [3][C] modulated weights of this sample
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) swm[i] = wrgb[i] * s[static_cast<long>(n) * s_stride + (i % C)];
+  __syncthreads();
+  const int vecs = C / 8;
+  const long HW = static_cast<long>(H) * W;
+  const long total = HW * LP;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  const long rounds = (total + stride - 1) / stride;
+  for (long rr = 0; rr < rounds; ++rr) {
+    const long idx = rr * stride + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+    const bool active = idx < total;
+    const int sub = idx % LP;
+    const long p = idx / LP;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (active) {
+      const bf16* xp = x + (static_cast<long>(n) * HW + p) * C;
+      for (int v = sub; v < vecs; v += LP) {
+        float xv[8];
+        unpack8(ldg8(xp + v * 8), xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = v * 8 + i;
+          a0 = fmaf(xv[i], swm[c], a0);
+          a1 = fmaf(xv[i], swm[C + c], a1);
+          a2 = fmaf(xv[i], swm[2 * C + c], a2);
+        }
+      }
+    }
+    for (int o = LP >> 1; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (active && sub == 0) {
+      const int h = p / W, w = p % W;
+      float r0 = a0 + bias[0], r1 = a1 + bias[1], r2 = a2 + bias[2];
+      if (skip) {
+        const int hs = H / 2, ws = W / 2;
+        const float* sk = skip + static_cast<long>(n) * 3 * hs * ws;
+        r0 += skip_up_sample(sk, hs, ws, h, w);
+        r1 += skip_up_sample(sk + static_cast<long>(hs) * ws, hs, ws, h, w);
+        r2 += skip_up_sample(sk + 2L * hs * ws, hs, ws, h, w);
+      }
+      float* o = rgb + static_cast<long>(n) * 3 * HW + p;
+      o[0] = r0;
+      o[HW] = r1;
+      o[2 * HW] = r2;
+    }
+  }
+}
+
+__global__ void torgb_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
+                                 const float* __restrict__ grgb, bf16* __restrict__ gx, float* __restrict__ gs, int gs_stride, int HW, int C) {
+  extern __shared__ float sm[];  // [3][C] weights, then [C] accumulators
+  float* sw = sm;
+  float* sacc = sm + 3 * C;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = wrgb[i];
+  __syncthreads();
+  const int vecs = C / 8;
+  const int cv = threadIdx.x % vecs;
+  float sv[8], racc[8], w0[8], w1[8], w2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sv[i] = s[static_cast<long>(n) * s_stride + cv * 8 + i];
+    racc[i] = 0.f;
+    w0[i] = sw[cv * 8 + i];
+    w1[i] = sw[C + cv * 8 + i];
+    w2[i] = sw[2 * C + cv * 8 + i];
+  }
+  const long total = static_cast<long>(HW) * vecs;
+  const float* g0 = grgb + static_cast<long>(n) * 3 * HW;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = idx / vecs;
+    const float ga = __ldg(g0 + p), gb = __ldg(g0 + HW + p), gc = __ldg(g0 + 2L * HW + p);
+    const long off = (static_cast<long>(n) * HW + p) * C + cv * 8;
+    float xv[8], o[8];
+    unpack8(ldg8(x + off), xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gt = w0[i] * ga + w1[i] * gb + w2[i] * gc;
+      racc[i] = fmaf(xv[i], gt, racc[i]);
+      o[i] = sv[i] * gt;
+    }
+    stg8(gx + off, pack8(o));
+  }
+  flush_channel_acc(sacc, racc, cv, C, gs + static_cast<long>(n) * gs_stride);
+}
+
+__global__ void rgb_down_kernel(const float* __restrict__ g, float* __restrict__ gs, long planes, int H, int W) {
+  // gskip[i][j] = sum_{t,u} g[2i+t-1][2j+u-1] k'[t] k'[u]
+  const int hs = H / 2, ws = W / 2;
+  const long total = planes * hs * ws;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int j = idx % ws;
+    long p = idx / ws;
+    const int i = p % hs;
+    const long pl = p / hs;
+    const float* gp = g + pl * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = 2 * i + t - 1;
+      if (o < 0 || o >= H) continue;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = 2 * j + u - 1;
+        if (q < 0 || q >= W) continue;
+        acc = fmaf(blur_w(t) * blur_w(u), __ldg(gp + static_cast<long>(o) * W + q), acc);
+      }
+    }
+    gs[idx] = acc;
+  }
+}
+
+// ============================================================================================
+// small dense helpers
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias, float* __restrict__ y,
+                                  int N, int In, int Out) {
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; o < Out; o += warps) {
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = lane; k < In; k += 32) acc = fmaf(__ldg(Wt + static_cast<long>(o) * In + k), __ldg(x + static_cast<long>(n) * In + k), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) y[static_cast<long>(n) * Out + o] = acc + (bias ? bias[o] : 0.f);
+    }
+  }
+}
+
+__global__ void linear_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx, int N, int In, int Out) {
+  const int total = N * In;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx % In, n = idx / In;
+    float acc = 0.f;
+    for (int o = 0; o < Out; ++o) acc = fmaf(__ldg(gy + static_cast<long>(n) * Out + o), __ldg(Wt + static_cast<long>(o) * In + i), acc);
+    gx[idx] = acc;
+  }
+}
+
+__global__ void fuse_spatial_fwd_kernel(const float* sa, const float* sb, const float* al, const float* be, const float* c, float* s, int N, int D) {
+  const long total = static_cast<long>(N) * D;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int r = idx % D;
+    const float a = sa[idx], b = sb[idx];
+    const float q = 1.f / (1.f + __expf(-(al[r] * a + be[r] * b + c[r])));
+    s[idx] = q * a + (1.f - q) * b;
+  }
+}
+
+__global__ void fuse_spatial_bwd_kernel(const float* sa, const float* sb, const float* al, const float* be, const float* c, const float* gs,
+                                        float* gsa, float* gsb, int N, int D) {
+  const long total = static_cast<long>(N) * D;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int r = idx % D;
+    const float a = sa[idx], b = sb[idx], g = gs[idx];
+    const float q = 1.f / (1.f + __expf(-(al[r] * a + be[r] * b + c[r])));
+    const float gq = g * (a - b) * q * (1.f - q);
+    gsa[idx] = g * q + gq * al[r];
+    gsb[idx] = g * (1.f - q) + gq * be[r];
+  }
+}
+
+__global__ void axpby_kernel(const float* x, const float* y, float* out, float a, float b, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = a * x[i] + (y ? b * y[i] : 0.f);
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int N, int C, int H, int W) {
+  const long total = static_cast<long>(N) * H * W * C;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int c = idx % C;
+    long p = idx / C;
+    const int w = p % W;
+    p /= W;
+    const int h = p % H;
+    const int n = p / H;
+    y[idx] = __float2bfloat16(x[((static_cast<long>(n) * C + c) * H + h) * W + w]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W) {
+  const long total = static_cast<long>(N) * H * W * C;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int w = idx % W;
+    long p = idx / W;
+    const int h = p % H;
+    p /= H;
+    const int c = p % C;
+    const int n = p / C;
+    y[idx] = __bfloat162float(x[((static_cast<long>(n) * H + h) * W + w) * C + c]);
+  }
+}
+
+// ============================================================================================
+// perturbation updates
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
+
+__device__ __forceinline__ void block_add(float v, float* dst) {
+  v = warp_sum(v);
+  __shared__ float red[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0 && dst) {
+    float s = 0.f;
+    for (int q = 0; q < blockDim.x / 32; ++q) s += red[q];
+    atomicAdd(dst, s);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float pooled_grad(const float* __restrict__ gpool, int n, long i, int S, int k) {
+  const int Sp = S / k;
+  const int w = i % S;
+  long p = i / S;
+  const int h = p % S;
+  const int c = p / S;
+  return __ldg(gpool + ((static_cast<long>(n) * 3 + c) * Sp + h / k) * Sp + w / k);
+}
+
+__global__ void update_linf_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ gpool, float alpha, float eps,
+                                   float dir, float lo, float hi, float* __restrict__ stats, int S, int k) {
+  const int n = blockIdx.y;
+  const long per = 3L * S * S;
+  float dsum = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long off = static_cast<long>(n) * per + i;
+    const float g = pooled_grad(gpool, n, i, S, k);
+    const float c0 = x0[off];
+    float v = x[off] + dir * alpha * sgn(g);
+    const float dl = fminf(fmaxf(v - c0, -eps), eps);
+    v = fminf(fmaxf(c0 + dl, lo), hi);
+    x[off] = v;
+    dsum += fabsf(v - c0);
+  }
+  block_add(dsum, stats ? stats + n : nullptr);
+}
+
+__global__ void update_patch_kernel(float* __restrict__ x, const float* __restrict__ x0, float* __restrict__ patch, const float* __restrict__ mask,
+                                    const float* __restrict__ gpool, float lr, float dir, int use_sign, const float* __restrict__ lo,
+                                    const float* __restrict__ hi, float gscale, float* __restrict__ stats, int S, int k) {
+  const int n = blockIdx.y;
+  const long per = 3L * S * S;
+  float dsum = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long off = static_cast<long>(n) * per + i;
+    const float g = gscale * pooled_grad(gpool, n, i, S, k);
+    const float pv = patch[off] + dir * lr * (use_sign ? sgn(g) : g);
+    patch[off] = pv;
+    const float m = mask[off], c0 = x0[off];
+    float v = (1.f - m) * c0 + m * pv;
+    v = fminf(fmaxf(v, lo[n]), hi[n]);
+    x[off] = v;
+    dsum += fabsf(v - c0);
+  }
+  block_add(dsum, stats ? stats + n : nullptr);
+}
+
+__global__ void update_adam_kernel(float* __restrict__ x, const float* __restrict__ gpool, float* __restrict__ m, float* __restrict__ v, float lr,
+                                   float b1, float b2, float eps, float bc1, float bc2, float gscale, int S, int k) {
+  const int n = blockIdx.y;
+  const long per = 3L * S * S;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long off = static_cast<long>(n) * per + i;
+    const float g = gscale * pooled_grad(gpool, n, i, S, k);
+    const float mm = b1 * m[off] + (1.f - b1) * g;
+    const float vv = b2 * v[off] + (1.f - b2) * g * g;
+    m[off] = mm;
+    v[off] = vv;
+    x[off] -= lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+  }
+}
+
+__global__ void update_l2_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ gpool, float* __restrict__ norms,
+                                 float* __restrict__ dn, float alpha, float eps, float dir, float lo, float hi, int phase, int S, int k) {
+  const int n = blockIdx.y;
+  const long per = 3L * S * S;
+  float acc = 0.f;
+  const float gn = phase == 1 ? fmaxf(sqrtf(norms[n]), 1e-12f) : 1.f;
+  const float sc = phase == 2 ? fminf(eps / fmaxf(sqrtf(dn[n]), 1e-12f), 1.f) : 1.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long off = static_cast<long>(n) * per + i;
+    if (phase == 0) {
+      const float g = pooled_grad(gpool, n, i, S, k);
+      acc += g * g;
+    } else if (phase == 1) {
+      const float g = pooled_grad(gpool, n, i, S, k);
+      const float v = x[off] + dir * alpha * g / gn;
+      x[off] = v;
+      const float dl = v - x0[off];
+      acc += dl * dl;
+    } else {
+      const float c0 = x0[off];
+      x[off] = fminf(fmaxf(c0 + (x[off] - c0) * sc, lo), hi);
+    }
+  }
+  if (phase == 0) block_add(acc, norms + n);
+  if (phase == 1) block_add(acc, dn + n);
+}
+
+__global__ void minmax_kernel(const float* __restrict__ x, float* __restrict__ lo, float* __restrict__ hi, long per) {
+  const int n = blockIdx.x;
+  float mn = INFINITY, mx = -INFINITY;
+  for (long i = threadIdx.x; i < per; i += blockDim.x) {
+    const float v = x[static_cast<long>(n) * per + i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ float smn[32], smx[32];
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < blockDim.x / 32; ++q) {
+      mn = fminf(mn, smn[q]);
+      mx = fmaxf(mx, smx[q]);
+    }
+    lo[n] = mn;
+    hi[n] = mx;
+  }
+}
+
+inline cudaStream_t S_(sfk_stream_t s) { return static_cast<cudaStream_t>(s); }
+inline unsigned per_sample_blocks(long items, int n) {
+  long b = (items + kBlock - 1) / kBlock;
+  long cap = (static_cast<long>(sfk_num_sms()) * 8 + n - 1) / n;
+  if (cap < 1) cap = 1;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int sfk_conv_c3_fwd(const float* x, const float* w, const float* bias, void* out, int n, int h, int w_, int cout, int relu, sfk_stream_t s) {
+  SFK_REQUIRE(x && w && out, SFK_E_ARG, "conv_c3_fwd: null");
+  SFK_REQUIRE(cout % 8 == 0 && cout <= 512, SFK_E_SHAPE, "conv_c3_fwd: cout must be a multiple of 8, <= 512");
+  const size_t smem = static_cast<size_t>(28 * cout) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  conv_c3_fwd_kernel<<<grid_for(static_cast<long>(n) * h * w_ * (cout / 8)), kBlock, smem, S_(s)>>>(x, w, bias, static_cast<bf16*>(out), n, h, w_, cout, relu);
+  return sfk_check_launch("conv_c3_fwd");
+}
+
+int sfk_conv_c3_bwd(const void* g, const float* w, float* gx, int n, int h, int w_, int cout, sfk_stream_t s) {
+  SFK_REQUIRE(g && w && gx, SFK_E_ARG, "conv_c3_bwd: null");
+  SFK_REQUIRE(cout % 8 == 0 && cout <= 512, SFK_E_SHAPE, "conv_c3_bwd: cout must be a multiple of 8, <= 512");
+  int lp = 1;
+  while (lp < 8 && lp * 2 <= cout / 8) lp *= 2;
+  const size_t smem = static_cast<size_t>(27 * cout) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  conv_c3_bwd_kernel<<<grid_for(static_cast<long>(n) * h * w_ * lp), kBlock, smem, S_(s)>>>(static_cast<const bf16*>(g), w, gx, n, h, w_, cout, lp);
+  return sfk_check_launch("conv_c3_bwd");
+}
+
+int sfk_avgpool_affine_fwd(const float* x, float* y, int n_planes, int h, int w, int k, float a, float b, sfk_stream_t s) {
+  SFK_REQUIRE(x && y && k >= 1 && h % k == 0 && w % k == 0, SFK_E_ARG, "avgpool_affine: bad args");
+  avgpool_affine_kernel<<<grid_for(static_cast<long>(n_planes) * (h / k) * (w / k)), kBlock, 0, S_(s)>>>(x, y, n_planes, h, w, k, a, b);
+  return sfk_check_launch("avgpool_affine");
+}
+
+int sfk_maxpool2_fwd(const void* x, void* y, int n, int h, int w, int c, sfk_stream_t s) {
+  SFK_REQUIRE(x && y && c % 8 == 0, SFK_E_ARG, "maxpool2_fwd: bad args");
+  maxpool2_fwd_kernel<<<grid_for(static_cast<long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), kBlock, 0, S_(s)>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(y), n, h, w, c);
+  return sfk_check_launch("maxpool2_fwd");
+}
+
+int sfk_maxpool2_bwd(const void* x, const void* y, const void* gy, void* gx, const void* tap_ref, float tap_coef, int relu_mask, int n, int h,
+                     int w, int c, sfk_stream_t s) {
+  (void)y;
+  SFK_REQUIRE(x && gy && gx && c % 8 == 0, SFK_E_ARG, "maxpool2_bwd: bad args");
+  maxpool2_bwd_kernel<<<grid_for(static_cast<long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), kBlock, 0, S_(s)>>>(
+      static_cast<const bf16*>(x), static_cast<const bf16*>(gy), static_cast<bf16*>(gx), static_cast<const bf16*>(tap_ref), tap_coef, relu_mask,
+      n, h, w, c);
+  return sfk_check_launch("maxpool2_bwd");
+}
+
+int sfk_gap_fwd(const void* x, float* y, int n, int hw, int c, sfk_stream_t s) {
+  SFK_REQUIRE(x && y && c % 8 == 0, SFK_E_ARG, "gap_fwd: bad args");
+  gap_fwd_kernel<<<dim3(c / 8, n), kBlock, 0, S_(s)>>>(static_cast<const bf16*>(x), y, hw, c);
+  return sfk_check_launch("gap_fwd");
+}
+
+int sfk_gap_bwd(const void* x, const float* gy, void* gx, int n, int hw, int c, sfk_stream_t s) {
+  SFK_REQUIRE(x && gy && gx && c % 8 == 0, SFK_E_ARG, "gap_bwd: bad args");
+  gap_bwd_kernel<<<grid_for(static_cast<long>(n) * hw * (c / 8)), kBlock, 0, S_(s)>>>(static_cast<const bf16*>(x), gy, static_cast<bf16*>(gx), n, hw, c);
+  return sfk_check_launch("gap_bwd");
+}
+
+int sfk_mse_tap(const void* f, const void* ref, void* g, float* loss, float coef_loss, float coef_grad, int accumulate, int relu_mask, int n,
+                long per_sample, sfk_stream_t s) {
+  SFK_REQUIRE(f && ref && per_sample % 8 == 0, SFK_E_ARG, "mse_tap: bad args");
+  mse_tap_kernel<<<dim3(per_sample_blocks(per_sample / 8, n), n), kBlock, 0, S_(s)>>>(static_cast<const bf16*>(f), static_cast<const bf16*>(ref),
+                                                                                      static_cast<bf16*>(g), loss, coef_loss, coef_grad, accumulate,
+                                                                                      relu_mask, per_sample);
+  return sfk_check_launch("mse_tap");
+}
+
+int sfk_image_loss_grad(const float* img, const float* ref, const float* gpool, float* g, float* loss, float coef_loss, float coef_grad, int n,
+                        int size, int k, sfk_stream_t s) {
+  SFK_REQUIRE(img && ref && g && size % k == 0, SFK_E_ARG, "image_loss_grad: bad args");
+  image_loss_grad_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(s)>>>(img, ref, gpool, g, loss, coef_loss, coef_grad, size, k);
+  return sfk_check_launch("image_loss_grad");
+}
+
+int sfk_style_affine_fwd(const float* w, const float* A, const float* bias, const int32_t* row_widx, float* sdst, int n, int n_latent,
+                         int style_dim, int s_dim, float scale, sfk_stream_t st) {
+  SFK_REQUIRE(w && A && bias && row_widx && sdst, SFK_E_ARG, "style_affine_fwd: null");
+  style_affine_fwd_kernel<<<grid_for(static_cast<long>(s_dim) * 32), kBlock, 0, S_(st)>>>(w, A, bias, row_widx, sdst, n, n_latent, style_dim, s_dim, scale);
+  return sfk_check_launch("style_affine_fwd");
+}
+
+int sfk_style_affine_bwd(const float* gs, const float* A, const int32_t* layer_row_start, const int32_t* layer_widx, int n_layers, float* gw, int n,
+                         int n_latent, int style_dim, int s_dim, float scale, sfk_stream_t st) {
+  SFK_REQUIRE(gs && A && layer_row_start && layer_widx && gw, SFK_E_ARG, "style_affine_bwd: null");
+  style_affine_bwd_kernel<<<grid_for(static_cast<long>(n) * n_latent * style_dim), kBlock, 0, S_(st)>>>(gs, A, layer_row_start, layer_widx, n_layers, gw,
+                                                                                                        n, n_latent, style_dim, s_dim, scale);
+  return sfk_check_launch("style_affine_bwd");
+}
+
+int sfk_demod_fwd(const float* sv, int s_stride, const float* Q, float* d, int n, int cin, int cout, sfk_stream_t st) {
+  SFK_REQUIRE(sv && Q && d, SFK_E_ARG, "demod_fwd: null");
+  demod_fwd_kernel<<<grid_for(static_cast<long>(n) * cout * 32), kBlock, 0, S_(st)>>>(sv, s_stride, Q, d, n, cin, cout);
+  return sfk_check_launch("demod_fwd");
+}
+
+int sfk_demod_bwd(const float* sv, int s_stride, const float* Q, const float* d, const float* gdacc, float* gs, int gs_stride, int n, int cin,
+                  int cout, sfk_stream_t st) {
+  SFK_REQUIRE(sv && Q && d && gdacc && gs, SFK_E_ARG, "demod_bwd: null");
+  demod_bwd_kernel<<<grid_for(static_cast<long>(n) * cin), kBlock, 0, S_(st)>>>(sv, s_stride, Q, d, gdacc, gs, gs_stride, n, cin, cout);
+  return sfk_check_launch("demod_bwd");
+}
+
+int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void* wmod, int n, int taps, int cout, int cin, sfk_stream_t st) {
+  SFK_REQUIRE(wbase && sv && wmod && cin % 8 == 0 && s_stride % 4 == 0, SFK_E_ARG, "modulate_weights: bad args");
+  SFK_REQUIRE(sfk_aligned16(wbase) && sfk_aligned16(sv) && sfk_aligned16(wmod), SFK_E_ALIGN, "modulate_weights: alignment");
+  const long rows = static_cast<long>(taps) * cout;
+  modulate_weights_kernel<<<grid_for(static_cast<long>(n) * rows * (cin / 8)), kBlock, 0, S_(st)>>>(wbase, sv, s_stride, static_cast<bf16*>(wmod), n, rows, cin);
+  return sfk_check_launch("modulate_weights");
+}
+
+int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias, int n, int h, int w, int c,
+                     sfk_stream_t st) {
+  SFK_REQUIRE(T && out && d && bias && c % 8 == 0, SFK_E_ARG, "blur_act_fwd: bad args");
+  blur_act_fwd_kernel<<<dim3(per_sample_blocks(4L * h * w * (c / 8), n), n), kBlock, 0, S_(st)>>>(static_cast<const bf16*>(T), static_cast<bf16*>(out), d,
+                                                                                                  noise, noise_w, bias, h, w, c);
+  return sfk_check_launch("blur_act_fwd");
+}
+
+int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d, const float* noise, float noise_w, const float* bias,
+                     float* gdacc, int n, int h, int w, int c, sfk_stream_t st) {
+  SFK_REQUIRE(out && gout && gT && d && bias && gdacc && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "blur_act_bwd: bad args");
+  blur_act_bwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(2 * h + 2) * (2 * w + 2) * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
+      static_cast<const bf16*>(out), static_cast<const bf16*>(gout), static_cast<bf16*>(gT), d, noise, noise_w, bias, gdacc, h, w, c);
+  return sfk_check_launch("blur_act_bwd");
+}
+
+int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w, const float* bias, float* gdacc,
+                int n, int h, int w, int c, sfk_stream_t st) {
+  SFK_REQUIRE(out && gout && gz && d && bias && gdacc && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "act_bwd: bad args");
+  act_bwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
+      static_cast<const bf16*>(out), static_cast<const bf16*>(gout), static_cast<bf16*>(gz), d, noise, noise_w, bias, gdacc, h * w, c);
+  return sfk_check_launch("act_bwd");
+}
+
+int sfk_torgb_fwd(const void* x, const float* wrgb, const float* sv, int s_stride, const float* bias, const float* skip, float* rgb, int n, int h,
+                  int w, int c, sfk_stream_t st) {
+  SFK_REQUIRE(x && wrgb && sv && bias && rgb && c % 8 == 0, SFK_E_ARG, "torgb_fwd: bad args");
+  int lp = 1;
+  while (lp < 32 && lp * 2 <= c / 8) lp *= 2;
+  torgb_fwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * lp, n), n), kBlock, 3 * c * sizeof(float), S_(st)>>>(
+      static_cast<const bf16*>(x), wrgb, sv, s_stride, bias, skip, rgb, h, w, c, lp);
+  return sfk_check_launch("torgb_fwd");
+}
+
+int sfk_torgb_bwd(const void* x, const float* wrgb, const float* sv, int s_stride, const float* grgb, void* gx, float* gs, int gs_stride, int n,
+                  int h, int w, int c, sfk_stream_t st) {
+  SFK_REQUIRE(x && wrgb && sv && grgb && gx && gs && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "torgb_bwd: bad args");
+  torgb_bwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, 4 * c * sizeof(float), S_(st)>>>(
+      static_cast<const bf16*>(x), wrgb, sv, s_stride, grgb, static_cast<bf16*>(gx), gs, gs_stride, h * w, c);
+  return sfk_check_launch("torgb_bwd");
+}
+
+int sfk_rgb_down(const float* g, float* gskip, int planes, int h, int w, sfk_stream_t st) {
+  SFK_REQUIRE(g && gskip && h % 2 == 0 && w % 2 == 0, SFK_E_ARG, "rgb_down: bad args");
+  rgb_down_kernel<<<grid_for(static_cast<long>(planes) * (h / 2) * (w / 2)), kBlock, 0, S_(st)>>>(g, gskip, planes, h, w);
+  return sfk_check_launch("rgb_down");
+}
+
+int sfk_linear_fwd(const float* x, const float* W, const float* bias, float* y, int n, int in, int out, sfk_stream_t st) {
+  SFK_REQUIRE(x && W && y, SFK_E_ARG, "linear_fwd: null");
+  linear_fwd_kernel<<<grid_for(static_cast<long>(out) * 32), kBlock, 0, S_(st)>>>(x, W, bias, y, n, in, out);
+  return sfk_check_launch("linear_fwd");
+}
+
+int sfk_linear_bwd(const float* gy, const float* W, float* gx, int n, int in, int out, sfk_stream_t st) {
+  SFK_REQUIRE(gy && W && gx, SFK_E_ARG, "linear_bwd: null");
+  linear_bwd_kernel<<<grid_for(static_cast<long>(n) * in), kBlock, 0, S_(st)>>>(gy, W, gx, n, in, out);
+  return sfk_check_launch("linear_bwd");
+}
+
+int sfk_fuse_spatial_fwd(const float* sa, const float* sb, const float* al, const float* be, const float* c, float* s, int n, int dim, sfk_stream_t st) {
+  SFK_REQUIRE(sa && sb && al && be && c && s, SFK_E_ARG, "fuse_spatial_fwd: null");
+  fuse_spatial_fwd_kernel<<<grid_for(static_cast<long>(n) * dim), kBlock, 0, S_(st)>>>(sa, sb, al, be, c, s, n, dim);
+  return sfk_check_launch("fuse_spatial_fwd");
+}
+
+int sfk_fuse_spatial_bwd(const float* sa, const float* sb, const float* al, const float* be, const float* c, const float* gs, float* gsa, float* gsb,
+                         int n, int dim, sfk_stream_t st) {
+  SFK_REQUIRE(sa && sb && al && be && c && gs && gsa && gsb, SFK_E_ARG, "fuse_spatial_bwd: null");
+  fuse_spatial_bwd_kernel<<<grid_for(static_cast<long>(n) * dim), kBlock, 0, S_(st)>>>(sa, sb, al, be, c, gs, gsa, gsb, n, dim);
+  return sfk_check_launch("fuse_spatial_bwd");
+}
+
+int sfk_axpby(const float* x, const float* y, float* out, float a, float b, long n, sfk_stream_t st) {
+  SFK_REQUIRE(x && out, SFK_E_ARG, "axpby: null");
+  axpby_kernel<<<grid_for(n), kBlock, 0, S_(st)>>>(x, y, out, a, b, n);
+  return sfk_check_launch("axpby");
+}
+
+int sfk_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, sfk_stream_t st) {
+  SFK_REQUIRE(x && y, SFK_E_ARG, "nchw_to_nhwc: null");
+  nchw_to_nhwc_kernel<<<grid_for(static_cast<long>(n) * c * h * w), kBlock, 0, S_(st)>>>(x, static_cast<bf16*>(y), n, c, h, w);
+  return sfk_check_launch("nchw_to_nhwc");
+}
+
+int sfk_nhwc_bf16_to_nchw(const void* x, float* y, int n, int c, int h, int w, sfk_stream_t st) {
+  SFK_REQUIRE(x && y, SFK_E_ARG, "nhwc_to_nchw: null");
+  nhwc_to_nchw_kernel<<<grid_for(static_cast<long>(n) * c * h * w), kBlock, 0, S_(st)>>>(static_cast<const bf16*>(x), y, n, c, h, w);
+  return sfk_check_launch("nhwc_to_nchw");
+}
+
+int sfk_attack_update_linf(float* x, const float* x0, const float* gpool, float alpha, float eps, float dir, float lo, float hi, float* stats,
+                           int n, int size, int k, sfk_stream_t st) {
+  SFK_REQUIRE(x && x0 && gpool && size % k == 0, SFK_E_ARG, "attack_update_linf: bad args");
+  update_linf_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, x0, gpool, alpha, eps, dir, lo, hi, stats, size, k);
+  return sfk_check_launch("attack_update_linf");
+}
+
+int sfk_attack_update_patch(float* x, const float* x0, float* patch, const float* mask, const float* gpool, float lr, float dir, int use_sign,
+                            const float* lo, const float* hi, float gscale, float* stats, int n, int size, int k, sfk_stream_t st) {
+  SFK_REQUIRE(x && x0 && patch && mask && gpool && lo && hi && size % k == 0, SFK_E_ARG, "attack_update_patch: bad args");
+  update_patch_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, x0, patch, mask, gpool, lr, dir, use_sign, lo, hi, gscale,
+                                                                                             stats, size, k);
+  return sfk_check_launch("attack_update_patch");
+}
+
+int sfk_attack_update_adam(float* x, const float* gpool, float* m, float* v, float lr, float b1, float b2, float eps, int t, float gscale, int n,
+                           int size, int k, sfk_stream_t st) {
+  SFK_REQUIRE(x && gpool && m && v && t >= 1 && size % k == 0, SFK_E_ARG, "attack_update_adam: bad args");
+  const float bc1 = 1.f - powf(b1, static_cast<float>(t)), bc2 = 1.f - powf(b2, static_cast<float>(t));
+  update_adam_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, gpool, m, v, lr, b1, b2, eps, bc1, bc2, gscale, size, k);
+  return sfk_check_launch("attack_update_adam");
+}
+
+int sfk_attack_update_l2(float* x, const float* x0, const float* gpool, float* norms, float* dn, float alpha, float eps, float dir, float lo,
+                         float hi, int phase, int n, int size, int k, sfk_stream_t st) {
+  SFK_REQUIRE(x && x0 && gpool && norms && dn && phase >= 0 && phase <= 2 && size % k == 0, SFK_E_ARG, "attack_update_l2: bad args");
+  update_l2_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, x0, gpool, norms, dn, alpha, eps, dir, lo, hi, phase, size, k);
+  return sfk_check_launch("attack_update_l2");
+}
+
+int sfk_minmax_per_sample(const float* x, float* lo, float* hi, int n, long per_sample, sfk_stream_t st) {
+  SFK_REQUIRE(x && lo && hi, SFK_E_ARG, "minmax: null");
+  minmax_kernel<<<n, 1024, 0, S_(st)>>>(x, lo, hi, per_sample);
+  return sfk_check_launch("minmax");
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// Implicit-GEMM convolution for sm_100a: TMA (cp.async.bulk.tensor) -> 128B/64B/32B-swizzled smem ->
+// tcgen05.mma (one issuing thread, fp32 accumulators in TMEM) -> tcgen05.ld epilogue.
+//
+// GEMM view (see include/sfk.h): M = 128 output positions (a TH x TW patch of one image),
+// N = block_n output channels per accumulator, K = taps x Cin walked in k-steps of KC channels.
+// Because the activation tensor is NHWC, the box {KC, TW, TH, 1, 1} of a 5-D tensor map lands in
+// shared memory as 128 rows x (KC*2) bytes -- exactly the K-major swizzled operand layout
+// tcgen05.mma wants -- and the spatial shift (dy,dx) of a filter tap is just a coordinate offset;
+// out-of-bounds rows are zero-filled by TMA, which implements the conv padding for free.
+//
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM alloc/dealloc,
+// warps4-7 = epilogue (TMEM lanes 32*(warp%4)..).  Two CTAs fit per SM so one CTA's epilogue
+// overlaps the other's main loop.
+#include <cuda.h>
+
+#include "sfk_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr long long kTimeoutCycles = 400000000LL;  // ~0.2 s: a hung pipeline flags an error instead of hanging the GPU
+
+struct KTap {
+  int dy, dx, plane, acc, brow, first;
+};
+
+struct __align__(64) IgemmKArgs {
+  CUtensorMap mapA;
+  CUtensorMap mapB;
+  int n_img, out_h, out_w, out_c;
+  int TH, TW, tiles_h, tiles_w;
+  int KC, num_cblk, block_n, num_acc, num_taps, stages;
+  int b_per_sample;
+  int a_stage_bytes, b_stage_bytes;
+  int layout_type;  // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
+  int sbo_bytes;
+  int tmem_cols;
+  int flags;
+  float noise_w;
+  __nv_bfloat16* out;
+  const float* dscale;
+  const float* bias;
+  const float* noise;
+  const __nv_bfloat16* xin;
+  const float* colscale;
+  float* gs;
+  int* err;
+  KTap taps[SFK_MAX_TAPS];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: returns false (and raises *err) if the barrier never flips.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kTimeoutCycles || (err && *reinterpret_cast<volatile int*>(err) != 0)) {
+      if (err) atomicExch(err, 1);
+      return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFFu);         // start address, bits [0,14)
+  d |= static_cast<uint64_t>(1u) << 16;                      // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // stride byte offset between 8-row groups, bits [32,46)
+  d |= static_cast<uint64_t>(1u) << 46;                      // descriptor version = 1 on sm_100
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;        // swizzle mode, bits [61,64)
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Sum each of 16 per-lane values over the 32 lanes with 16 shuffles; afterwards lane l holds the total
+// of column  8*b0 + 4*b1 + 2*b2 + b3  (b_i = bit i of l).
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 1 << step;
+    const int half = 8 >> step;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < half) {
+        const float keep = upper ? v[i + half] : v[i];
+        const float send = upper ? v[i] : v[i + half];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+__device__ __forceinline__ int colsum16_column(int lane) {
+  return 8 * (lane & 1) + 4 * ((lane >> 1) & 1) + 2 * ((lane >> 2) & 1) + ((lane >> 3) & 1);
+}
+
+// The epilogue arithmetic for one output position and 16 consecutive channels.  Shared by the
+// tensor-core kernel and the CUDA-core cross-check kernel so both define the same operator.
+template <typename Args>
+__device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h, int w, int col0, bool valid, float* v,
+                                           float* gsdot /* 16 products for the style-gradient reduction */) {
+  const int flags = a.flags;
+  const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
+  const long off = pix * a.out_c + col0;
+  const long vec = static_cast<long>(n) * a.out_c + col0;
+  if (flags & SFK_EP_DSCALE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= __ldg(a.dscale + vec + i);
+  }
+  if ((flags & SFK_EP_NOISE) && valid) {
+    const float nz = a.noise_w * __ldg(a.noise + static_cast<long>(h) * a.out_w + w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += nz;
+  }
+  if (flags & SFK_EP_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + col0 + i);
+  }
+  if (flags & SFK_EP_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (flags & SFK_EP_LRELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = lrelu_fwd(v[i]);
+  }
+  if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {
+    float x[16];
+    if (valid) {
+      unpack8(ldg8(a.xin + off), x);
+      unpack8(ldg8(a.xin + off + 8), x + 8);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = 0.f;
+    }
+    if (flags & SFK_EP_GSDOT) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) gsdot[i] = x[i] * v[i];
+    }
+    if (flags & SFK_EP_XMASK) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
+    }
+  }
+  if (flags & SFK_EP_COLSCALE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= __ldg(a.colscale + vec + i);
+  }
+  if (valid) {
+    if (flags & SFK_EP_ACCUM) {
+      float o[16];
+      unpack8(ldg8(a.out + off), o);
+      unpack8(ldg8(a.out + off + 8), o + 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += o[i];
+    }
+    stg8(a.out + off, pack8(v));
+    stg8(a.out + off + 8, pack8(v + 8));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) igemm_tc_kernel(const __grid_constant__ IgemmKArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float gs_acc[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + a.stages * a.a_stage_bytes;
+
+  // tile coordinates
+  const int bx = blockIdx.x;
+  const int tw_i = bx % a.tiles_w;
+  const int th_i = (bx / a.tiles_w) % a.tiles_h;
+  const int n = bx / (a.tiles_w * a.tiles_h);
+  const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
+  const int n0 = blockIdx.y * a.block_n;
+  const int num_k = a.num_cblk * a.num_taps;
+
+  if (threadIdx.x < 256) gs_acc[threadIdx.x] = 0.f;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(static_cast<uint32_t>(a.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = static_cast<uint32_t>(128 * a.KC * 2 + a.block_n * a.KC * 2);
+      int ks = 0;
+      bool ok = true;
+      for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
+        for (int t = 0; t < a.num_taps; ++t, ++ks) {
+          const int stage = ks % a.stages;
+          const uint32_t phase = (ks / a.stages) & 1;
+          if (!mbar_wait(&empty_bar[stage], phase ^ 1, a.err)) {
+            ok = false;
+            break;
+          }
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          const KTap& tp = a.taps[t];
+          tma_load_5d(smem_a + stage * a.a_stage_bytes, &a.mapA, &full_bar[stage], cb * a.KC, w0 + tp.dx, h0 + tp.dy,
+                      tp.plane, n);
+          tma_load_3d(smem_b + stage * a.b_stage_bytes, &a.mapB, &full_bar[stage], cb * a.KC, tp.brow + n0,
+                      a.b_per_sample ? n : 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a.block_n >> 3) << 17) |
+                             (static_cast<uint32_t>(128 >> 4) << 24);
+      const int kslices = a.KC / 16;
+      int ks = 0;
+      bool ok = true;
+      for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
+        for (int t = 0; t < a.num_taps; ++t, ++ks) {
+          const int stage = ks % a.stages;
+          const uint32_t phase = (ks / a.stages) & 1;
+          if (!mbar_wait(&full_bar[stage], phase, a.err)) {
+            ok = false;
+            break;
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const KTap& tp = a.taps[t];
+          const uint64_t adesc = make_smem_desc(smem_a + stage * a.a_stage_bytes, a.sbo_bytes, a.layout_type);
+          const uint64_t bdesc = make_smem_desc(smem_b + stage * a.b_stage_bytes, a.sbo_bytes, a.layout_type);
+          const uint32_t tmem_c = tmem_base + static_cast<uint32_t>(tp.acc * a.block_n);
+          for (int k = 0; k < kslices; ++k) {
+            const uint32_t accum = (cb == 0 && tp.first && k == 0) ? 0u : 1u;
+            // advancing K by 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(tmem_c, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accum);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        }
+      }
+      umma_commit(&tmem_full_bar);  // accumulators complete
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const bool ok = mbar_wait(&tmem_full_bar, 0, a.err);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int th = row / a.TW, tw = row % a.TW;
+    const int h = h0 + th, w = w0 + tw;
+    const bool valid = ok && (h < a.out_h) && (w < a.out_w);
+    const int chunks = a.block_n / 16;
+    const int mycol = colsum16_column(lane);
+    for (int acc = 0; acc < a.num_acc; ++acc) {
+      for (int c = 0; c < chunks; ++c) {
+        float v[16], gsd[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * a.block_n + c * 16);
+        tmem_ld16(taddr, v);
+        epilogue16(a, n, acc, h, w, n0 + c * 16, valid, v, gsd);
+        if (a.flags & SFK_EP_GSDOT) {
+          const float tot = warp_colsum16(gsd, lane);
+          if (lane < 16) atomicAdd(&gs_acc[c * 16 + mycol], tot);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if ((a.flags & SFK_EP_GSDOT) && threadIdx.x < a.block_n) {
+    atomicAdd(a.gs + static_cast<long>(n) * a.out_c + n0 + threadIdx.x, gs_acc[threadIdx.x]);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(static_cast<uint32_t>(a.tmem_cols))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core cross-check with the identical contract (one thread = one position x 16 channels).
+struct RefArgs {
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* B;
+  int n_img, a_h, a_w, a_c, a_planes, b_rows, b_per_sample;
+  int out_h, out_w, out_c, num_acc, block_n, num_taps, flags;
+  float noise_w;
+  __nv_bfloat16* out;
+  const float* dscale;
+  const float* bias;
+  const float* noise;
+  const __nv_bfloat16* xin;
+  const float* colscale;
+  float* gs;
+  KTap taps[SFK_MAX_TAPS];
+};
+
+__global__ void igemm_ref_kernel(const __grid_constant__ RefArgs a) {
+  const int chunks_per_pos = a.out_c / 16;
+  const long total = static_cast<long>(a.n_img) * a.num_acc * a.out_h * a.out_w * chunks_per_pos;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ch = idx % chunks_per_pos;
+    long r = idx / chunks_per_pos;
+    const int w = r % a.out_w;
+    r /= a.out_w;
+    const int h = r % a.out_h;
+    r /= a.out_h;
+    const int acc = r % a.num_acc;
+    const int n = r / a.num_acc;
+    const int col0 = ch * 16;
+    const int nblk = col0 / a.block_n;            // which weight-row block this channel group lives in
+    const int cin_blk = col0 - nblk * a.block_n;  // offset inside it
+    float v[16], gsd[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    for (int t = 0; t < a.num_taps; ++t) {
+      const KTap& tp = a.taps[t];
+      if (tp.acc != acc) continue;
+      const int ih = h + tp.dy, iw = w + tp.dx;
+      if (ih < 0 || ih >= a.a_h || iw < 0 || iw >= a.a_w) continue;
+      const __nv_bfloat16* ap = a.A + ((((static_cast<long>(n) * a.a_planes + tp.plane) * a.a_h + ih) * a.a_w + iw) * a.a_c);
+      const long brow0 = static_cast<long>(a.b_per_sample ? n : 0) * a.b_rows + tp.brow + nblk * a.block_n + cin_blk;
+      for (int k = 0; k < a.a_c; ++k) {
+        const float av = __bfloat162float(ap[k]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const long br = brow0 + i;
+          const float bv = (tp.brow + nblk * a.block_n + cin_blk + i < a.b_rows) ? __bfloat162float(a.B[br * a.a_c + k]) : 0.f;
+          v[i] += av * bv;
+        }
+      }
+    }
+    epilogue16(a, n, acc, h, w, col0, true, v, gsd);
+    if (a.flags & SFK_EP_GSDOT) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) atomicAdd(a.gs + static_cast<long>(n) * a.out_c + col0 + i, gsd[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int validate(const sfk_igemm_desc* d) {
+  SFK_REQUIRE(d != nullptr, SFK_E_ARG, "igemm: null descriptor");
+  SFK_REQUIRE(d->a && d->b && d->out, SFK_E_ARG, "igemm: null operand");
+  SFK_REQUIRE(sfk_aligned16(d->a) && sfk_aligned16(d->b) && sfk_aligned16(d->out), SFK_E_ALIGN, "igemm: operands must be 16B aligned");
+  SFK_REQUIRE(d->a_c >= 16 && d->a_c % 16 == 0, SFK_E_SHAPE, "igemm: Cin must be a multiple of 16");
+  SFK_REQUIRE(d->block_n >= 16 && d->block_n % 16 == 0 && d->block_n <= 256, SFK_E_SHAPE, "igemm: block_n must be 16..256, multiple of 16");
+  SFK_REQUIRE(d->num_acc >= 1 && d->num_acc * d->block_n <= 512, SFK_E_SHAPE, "igemm: num_acc*block_n must fit 512 TMEM columns");
+  SFK_REQUIRE(d->out_c % d->block_n == 0, SFK_E_SHAPE, "igemm: out_c must be a multiple of block_n");
+  SFK_REQUIRE(d->num_taps >= 1 && d->num_taps <= SFK_MAX_TAPS, SFK_E_SHAPE, "igemm: bad tap count");
+  SFK_REQUIRE(d->n_img >= 1 && d->out_h >= 1 && d->out_w >= 1 && d->a_h >= 1 && d->a_w >= 1 && d->a_planes >= 1, SFK_E_SHAPE, "igemm: bad dims");
+  SFK_REQUIRE(d->b_samples == 1 || d->b_samples == d->n_img, SFK_E_SHAPE, "igemm: b_samples must be 1 or n_img");
+  for (int t = 0; t < d->num_taps; ++t) {
+    SFK_REQUIRE(d->taps[t].acc >= 0 && d->taps[t].acc < d->num_acc, SFK_E_SHAPE, "igemm: tap accumulator out of range");
+    SFK_REQUIRE(d->taps[t].plane >= 0 && d->taps[t].plane < d->a_planes, SFK_E_SHAPE, "igemm: tap plane out of range");
+    SFK_REQUIRE(d->taps[t].brow >= 0 && d->taps[t].brow + d->out_c <= d->b_rows, SFK_E_SHAPE, "igemm: tap weight rows out of range");
+  }
+  if (d->flags & SFK_EP_DSCALE) SFK_REQUIRE(d->dscale, SFK_E_ARG, "igemm: dscale missing");
+  if (d->flags & SFK_EP_BIAS) SFK_REQUIRE(d->bias, SFK_E_ARG, "igemm: bias missing");
+  if (d->flags & SFK_EP_NOISE) SFK_REQUIRE(d->noise, SFK_E_ARG, "igemm: noise missing");
+  if (d->flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) SFK_REQUIRE(d->xin && sfk_aligned16(d->xin), SFK_E_ARG, "igemm: xin missing");
+  if (d->flags & SFK_EP_GSDOT) SFK_REQUIRE(d->gs, SFK_E_ARG, "igemm: gs missing");
+  if (d->flags & SFK_EP_COLSCALE) SFK_REQUIRE(d->colscale, SFK_E_ARG, "igemm: colscale missing");
+  return 0;
+}
+
+void fill_taps(const sfk_igemm_desc* d, KTap* taps) {
+  bool seen[32] = {false};
+  for (int t = 0; t < d->num_taps; ++t) {
+    taps[t].dy = d->taps[t].dy;
+    taps[t].dx = d->taps[t].dx;
+    taps[t].plane = d->taps[t].plane;
+    taps[t].acc = d->taps[t].acc;
+    taps[t].brow = d->taps[t].brow;
+    taps[t].first = seen[d->taps[t].acc] ? 0 : 1;
+    seen[d->taps[t].acc] = true;
+  }
+}
+
+}  // namespace
+
+extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode_fn();
+  SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+
+  IgemmKArgs k;
+  memset(&k, 0, sizeof(k));
+  const int KC = (d->a_c % 64 == 0) ? 64 : (d->a_c % 32 == 0 ? 32 : 16);
+  k.KC = KC;
+  k.num_cblk = d->a_c / KC;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  k.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
+  k.sbo_bytes = 8 * KC * 2;
+  k.TW = d->out_w > 8 ? 16 : (d->out_w > 4 ? 8 : 4);
+  k.TH = 128 / k.TW;
+  k.tiles_w = (d->out_w + k.TW - 1) / k.TW;
+  k.tiles_h = (d->out_h + k.TH - 1) / k.TH;
+  k.n_img = d->n_img;
+  k.out_h = d->out_h;
+  k.out_w = d->out_w;
+  k.out_c = d->out_c;
+  k.block_n = d->block_n;
+  k.num_acc = d->num_acc;
+  k.num_taps = d->num_taps;
+  k.b_per_sample = d->b_samples > 1 ? 1 : 0;
+  k.a_stage_bytes = 128 * KC * 2;
+  k.b_stage_bytes = ((d->block_n * KC * 2 + 1023) / 1024) * 1024;
+  const int cols = d->num_acc * d->block_n;
+  k.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  k.flags = d->flags;
+  k.noise_w = d->noise_w;
+  k.out = static_cast<__nv_bfloat16*>(d->out);
+  k.dscale = d->dscale;
+  k.bias = d->bias;
+  k.noise = d->noise;
+  k.xin = static_cast<const __nv_bfloat16*>(d->xin);
+  k.colscale = d->colscale;
+  k.gs = d->gs;
+  k.err = d->err;
+  fill_taps(d, k.taps);
+  const int num_k = k.num_cblk * k.num_taps;
+  int stages = d->stages;
+  if (stages <= 0) {
+    const int budget = 100 * 1024;  // two CTAs per SM
+    stages = budget / (k.a_stage_bytes + k.b_stage_bytes);
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > num_k) stages = num_k;
+  if (stages < 1) stages = 1;
+  k.stages = stages;
+
+  // A: [n][planes][h][w][c] bf16, box {KC, TW, TH, 1, 1}
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_w, (cuuint64_t)d->a_h, (cuuint64_t)d->a_planes, (cuuint64_t)d->n_img};
+    cuuint64_t strides[4] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->a_w * d->a_c * 2, (cuuint64_t)d->a_h * d->a_w * d->a_c * 2,
+                             (cuuint64_t)d->a_planes * d->a_h * d->a_w * d->a_c * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)k.TW, (cuuint32_t)k.TH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&k.mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(A) failed");
+  }
+  // B: [samples][rows][c] bf16, box {KC, block_n, 1}
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->a_c, (cuuint64_t)d->b_rows, (cuuint64_t)d->b_samples};
+    cuuint64_t strides[2] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->b_rows * d->a_c * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)d->block_n, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&k.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->b), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(B) failed");
+  }
+  const size_t smem = static_cast<size_t>(stages) * (k.a_stage_bytes + k.b_stage_bytes) + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    smem_set = 200 * 1024;
+  }
+  dim3 grid(static_cast<unsigned>(k.tiles_w * k.tiles_h * d->n_img), static_cast<unsigned>(d->out_c / d->block_n));
+  igemm_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(k);
+  return sfk_check_launch("igemm_tc_kernel");
+}
+
+extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  RefArgs r;
+  memset(&r, 0, sizeof(r));
+  r.A = static_cast<const __nv_bfloat16*>(d->a);
+  r.B = static_cast<const __nv_bfloat16*>(d->b);
+  r.n_img = d->n_img; r.a_h = d->a_h; r.a_w = d->a_w; r.a_c = d->a_c; r.a_planes = d->a_planes;
+  r.b_rows = d->b_rows; r.b_per_sample = d->b_samples > 1 ? 1 : 0;
+  r.out_h = d->out_h; r.out_w = d->out_w; r.out_c = d->out_c; r.num_acc = d->num_acc; r.block_n = d->block_n;
+  r.num_taps = d->num_taps; r.flags = d->flags; r.noise_w = d->noise_w;
+  r.out = static_cast<__nv_bfloat16*>(d->out);
+  r.dscale = d->dscale; r.bias = d->bias; r.noise = d->noise;
+  r.xin = static_cast<const __nv_bfloat16*>(d->xin); r.colscale = d->colscale; r.gs = d->gs;
+  fill_taps(d, r.taps);
+  const long total = static_cast<long>(d->n_img) * d->num_acc * d->out_h * d->out_w * (d->out_c / 16);
+  long blocks = (total + 127) / 128;
+  if (blocks > 65535L * 16) blocks = 65535L * 16;
+  igemm_ref_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(r);
+  return sfk_check_launch("igemm_ref_kernel");
+}

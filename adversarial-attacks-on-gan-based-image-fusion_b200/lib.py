@@ -1,0 +1,328 @@
+"""ctypes binding of libsfattack.so (the C ABI declared in include/sfk.h).
+
+No libtorch linkage: tensors cross the boundary as raw device pointers (``tensor.data_ptr()``) plus
+sizes, launches go to torch's current CUDA stream.  There is NO fallback: if the library is missing
+or a call returns non-zero, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libsfattack.so")
+
+SFK_MAX_TAPS = 16
+EP_DSCALE, EP_NOISE, EP_BIAS, EP_RELU, EP_LRELU, EP_XMASK, EP_GSDOT, EP_COLSCALE, EP_ACCUM = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256)
+
+
+class SfkTap(C.Structure):
+    _fields_ = [("dy", C.c_int32), ("dx", C.c_int32), ("plane", C.c_int32), ("acc", C.c_int32), ("brow", C.c_int32)]
+
+
+class SfkIgemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p),
+        ("n_img", C.c_int32), ("a_h", C.c_int32), ("a_w", C.c_int32), ("a_c", C.c_int32), ("a_planes", C.c_int32),
+        ("b", C.c_void_p),
+        ("b_samples", C.c_int32), ("b_rows", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_h", C.c_int32), ("out_w", C.c_int32), ("out_c", C.c_int32),
+        ("num_acc", C.c_int32), ("block_n", C.c_int32),
+        ("num_taps", C.c_int32),
+        ("taps", SfkTap * SFK_MAX_TAPS),
+        ("flags", C.c_int32),
+        ("dscale", C.c_void_p), ("bias", C.c_void_p), ("noise", C.c_void_p),
+        ("noise_w", C.c_float),
+        ("xin", C.c_void_p), ("colscale", C.c_void_p), ("gs", C.c_void_p),
+        ("err", C.c_void_p),
+        ("stages", C.c_int32),
+    ]
+
+
+# every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
+EXPORTS = [
+    "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
+    "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
+    "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
+    "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd",
+    "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
+    "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_update_patch",
+    "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample",
+]
+
+_lib = None
+
+
+class SfkError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; raise loudly if it has not been built (no CPU / eager fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SfkError(f"{LIB_PATH} not found: run `python __graft_entry__.py build` (the CUDA library is mandatory)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.sfk_last_error_string.restype = C.c_char_p
+        _lib.sfk_version.restype = C.c_int
+    return _lib
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "sfk: tensors must be contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _chk(rc: int, what: str):
+    if rc != 0:
+        raise SfkError(f"{what} failed rc={rc}: {load().sfk_last_error_string().decode()}")
+
+
+def _f(v) -> C.c_float:
+    return C.c_float(float(v))
+
+
+# ------------------------------------------------------------------------------------------------
+def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out, out_h, out_w, out_c, num_acc, block_n,
+                    taps: Sequence[tuple], flags=0, dscale=None, bias=None, noise=None, noise_w=0.0, xin=None,
+                    colscale=None, gs=None, err=None, stages=0) -> SfkIgemmDesc:
+    d = SfkIgemmDesc()
+    d.a, d.n_img, d.a_h, d.a_w, d.a_c, d.a_planes = _p(a), n_img, a_h, a_w, a_c, a_planes
+    d.b, d.b_samples, d.b_rows = _p(b), b_samples, b_rows
+    d.out, d.out_h, d.out_w, d.out_c = _p(out), out_h, out_w, out_c
+    d.num_acc, d.block_n, d.num_taps = num_acc, block_n, len(taps)
+    assert len(taps) <= SFK_MAX_TAPS
+    for i, (dy, dx, plane, acc, brow) in enumerate(taps):
+        d.taps[i] = SfkTap(dy, dx, plane, acc, brow)
+    d.flags = flags
+    d.dscale, d.bias, d.noise, d.noise_w = _p(dscale), _p(bias), _p(noise), float(noise_w)
+    d.xin, d.colscale, d.gs, d.err, d.stages = _p(xin), _p(colscale), _p(gs), _p(err), stages
+    # keep the tensors alive as long as the descriptor
+    d._keep = (a, b, out, dscale, bias, noise, xin, colscale, gs, err)
+    return d
+
+
+def igemm(desc: SfkIgemmDesc, ref: bool = False):
+    fn = load().sfk_igemm_ref if ref else load().sfk_igemm
+    _chk(fn(C.byref(desc), _stream()), "sfk_igemm_ref" if ref else "sfk_igemm")
+
+
+def conv3x3_taps(cout: int):
+    """forward 3x3, pad 1: tap (ky,kx) reads x[h+ky-1][w+kx-1]; weight rows (ky*3+kx)*cout."""
+    return [(ky - 1, kx - 1, 0, 0, (ky * 3 + kx) * cout) for ky in range(3) for kx in range(3)]
+
+
+def conv3x3_dgrad_taps(cin: int):
+    """data gradient of the same conv: gx[p] = sum_k gz[p-(k-1)] W[k]^T; weight rows are Wt[k][cin][cout]."""
+    return [(1 - ky, 1 - kx, 0, 0, (ky * 3 + kx) * cin) for ky in range(3) for kx in range(3)]
+
+
+def tconv_taps(cout: int):
+    """stride-2 transposed 3x3 conv as 4 phase accumulators (tests/test_kernel_math.py): phase a=(ky==1), b=(kx==1);
+    reads x[m-ky//2][n-kx//2]."""
+    return [(-(ky // 2), -(kx // 2), 0, (1 if ky == 1 else 0) * 2 + (1 if kx == 1 else 0), (ky * 3 + kx) * cout)
+            for ky in range(3) for kx in range(3)]
+
+
+def tconv_dgrad_taps(cin: int):
+    """transpose of the above: gx~[i] = sum_k gT[2i+k] W[k]^T, gT read from phase plane (ky%2, kx%2) at shift k//2."""
+    return [(ky // 2, kx // 2, (ky % 2) * 2 + (kx % 2), 0, (ky * 3 + kx) * cin) for ky in range(3) for kx in range(3)]
+
+
+def pick_block_n(cout: int, num_acc: int = 1) -> int:
+    bn = min(cout, 128 if num_acc > 1 else 128)
+    while num_acc * bn > 512:
+        bn //= 2
+    return bn
+
+
+# ------------------------------------------------------------------------------------------------
+def conv_c3_fwd(x, w, bias, out, relu=True):
+    n, _, h, wd = x.shape
+    _chk(load().sfk_conv_c3_fwd(_p(x), _p(w), _p(bias), _p(out), n, h, wd, w.shape[0], int(relu), _stream()), "conv_c3_fwd")
+
+
+def conv_c3_bwd(g, w, gx):
+    n, _, h, wd = gx.shape
+    _chk(load().sfk_conv_c3_bwd(_p(g), _p(w), _p(gx), n, h, wd, w.shape[0], _stream()), "conv_c3_bwd")
+
+
+def avgpool_affine_fwd(x, y, k, a=1.0, b=0.0):
+    planes = x.shape[0] * x.shape[1]
+    _chk(load().sfk_avgpool_affine_fwd(_p(x), _p(y), planes, x.shape[2], x.shape[3], k, _f(a), _f(b), _stream()), "avgpool")
+
+
+def maxpool2_fwd(x, y):
+    n, h, w, c = x.shape
+    _chk(load().sfk_maxpool2_fwd(_p(x), _p(y), n, h, w, c, _stream()), "maxpool2_fwd")
+
+
+def maxpool2_bwd(x, gy, gx, tap_ref=None, tap_coef=0.0, relu_mask=True):
+    n, h, w, c = x.shape
+    _chk(load().sfk_maxpool2_bwd(_p(x), C.c_void_p(0), _p(gy), _p(gx), _p(tap_ref), _f(tap_coef), int(relu_mask), n, h, w, c,
+                                 _stream()), "maxpool2_bwd")
+
+
+def gap_fwd(x, y):
+    n, h, w, c = x.shape
+    _chk(load().sfk_gap_fwd(_p(x), _p(y), n, h * w, c, _stream()), "gap_fwd")
+
+
+def gap_bwd(x, gy, gx):
+    n, h, w, c = x.shape
+    _chk(load().sfk_gap_bwd(_p(x), _p(gy), _p(gx), n, h * w, c, _stream()), "gap_bwd")
+
+
+def mse_tap(f, ref, g, loss, coef_loss, coef_grad, accumulate=False, relu_mask=False):
+    n = f.shape[0]
+    per = f.numel() // n
+    _chk(load().sfk_mse_tap(_p(f), _p(ref), _p(g), _p(loss), _f(coef_loss), _f(coef_grad), int(accumulate), int(relu_mask), n,
+                            C.c_long(per), _stream()), "mse_tap")
+
+
+def image_loss_grad(img, ref, gpool, g, loss, coef_loss, coef_grad, k):
+    n, _, s, _ = img.shape
+    _chk(load().sfk_image_loss_grad(_p(img), _p(ref), _p(gpool), _p(g), _p(loss), _f(coef_loss), _f(coef_grad), n, s, k, _stream()),
+         "image_loss_grad")
+
+
+def style_affine_fwd(w, A, bias, row_widx, s, scale):
+    n, L, D = w.shape
+    _chk(load().sfk_style_affine_fwd(_p(w), _p(A), _p(bias), _p(row_widx), _p(s), n, L, D, A.shape[0], _f(scale), _stream()),
+         "style_affine_fwd")
+
+
+def style_affine_bwd(gs, A, layer_row_start, layer_widx, gw, scale):
+    n, L, D = gw.shape
+    _chk(load().sfk_style_affine_bwd(_p(gs), _p(A), _p(layer_row_start), _p(layer_widx), layer_widx.numel(), _p(gw), n, L, D,
+                                     A.shape[0], _f(scale), _stream()), "style_affine_bwd")
+
+
+def _sub(t: torch.Tensor, off: int) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr() + off * t.element_size())
+
+
+def demod_fwd(s, s_off, Q, d):
+    n, sd = s.shape
+    cout, cin = Q.shape
+    _chk(load().sfk_demod_fwd(_sub(s, s_off), sd, _p(Q), _p(d), n, cin, cout, _stream()), "demod_fwd")
+
+
+def demod_bwd(s, s_off, Q, d, gdacc, gs):
+    n, sd = s.shape
+    cout, cin = Q.shape
+    _chk(load().sfk_demod_bwd(_sub(s, s_off), sd, _p(Q), _p(d), _p(gdacc), _sub(gs, s_off), gs.shape[1], n, cin, cout, _stream()),
+         "demod_bwd")
+
+
+def modulate_weights(wbase, s, s_off, wmod):
+    n, sd = s.shape
+    taps, cout, cin = wbase.shape
+    _chk(load().sfk_modulate_weights(_p(wbase), _sub(s, s_off), sd, _p(wmod), n, taps, cout, cin, _stream()), "modulate_weights")
+
+
+def blur_act_fwd(T, out, d, noise, noise_w, bias):
+    n, ho, wo, c = out.shape
+    _chk(load().sfk_blur_act_fwd(_p(T), _p(out), _p(d), _p(noise), _f(noise_w), _p(bias), n, ho // 2, wo // 2, c, _stream()),
+         "blur_act_fwd")
+
+
+def blur_act_bwd(out, gout, gT, d, noise, noise_w, bias, gdacc):
+    n, ho, wo, c = out.shape
+    _chk(load().sfk_blur_act_bwd(_p(out), _p(gout), _p(gT), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc), n, ho // 2, wo // 2,
+                                 c, _stream()), "blur_act_bwd")
+
+
+def act_bwd(out, gout, gz, d, noise, noise_w, bias, gdacc):
+    n, h, w, c = out.shape
+    _chk(load().sfk_act_bwd(_p(out), _p(gout), _p(gz), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc), n, h, w, c, _stream()),
+         "act_bwd")
+
+
+def torgb_fwd(x, wrgb, s, s_off, bias, skip, rgb):
+    n, h, w, c = x.shape
+    _chk(load().sfk_torgb_fwd(_p(x), _p(wrgb), _sub(s, s_off), s.shape[1], _p(bias), _p(skip), _p(rgb), n, h, w, c, _stream()),
+         "torgb_fwd")
+
+
+def torgb_bwd(x, wrgb, s, s_off, grgb, gx, gs):
+    n, h, w, c = x.shape
+    _chk(load().sfk_torgb_bwd(_p(x), _p(wrgb), _sub(s, s_off), s.shape[1], _p(grgb), _p(gx), _sub(gs, s_off), gs.shape[1], n, h, w,
+                              c, _stream()), "torgb_bwd")
+
+
+def rgb_down(g, gskip):
+    n, c, h, w = g.shape
+    _chk(load().sfk_rgb_down(_p(g), _p(gskip), n * c, h, w, _stream()), "rgb_down")
+
+
+def linear_fwd(x, W, bias, y):
+    _chk(load().sfk_linear_fwd(_p(x), _p(W), _p(bias), _p(y), x.shape[0], W.shape[1], W.shape[0], _stream()), "linear_fwd")
+
+
+def linear_bwd(gy, W, gx):
+    _chk(load().sfk_linear_bwd(_p(gy), _p(W), _p(gx), gy.shape[0], W.shape[1], W.shape[0], _stream()), "linear_bwd")
+
+
+def fuse_spatial_fwd(sa, sb, al, be, c, s):
+    _chk(load().sfk_fuse_spatial_fwd(_p(sa), _p(sb), _p(al), _p(be), _p(c), _p(s), sa.shape[0], sa.shape[1], _stream()), "fuse_fwd")
+
+
+def fuse_spatial_bwd(sa, sb, al, be, c, gs, gsa, gsb):
+    _chk(load().sfk_fuse_spatial_bwd(_p(sa), _p(sb), _p(al), _p(be), _p(c), _p(gs), _p(gsa), _p(gsb), sa.shape[0], sa.shape[1],
+                                     _stream()), "fuse_bwd")
+
+
+def axpby(x, y, out, a, b=0.0):
+    _chk(load().sfk_axpby(_p(x), _p(y), _p(out), _f(a), _f(b), C.c_long(x.numel()), _stream()), "axpby")
+
+
+def nchw_to_nhwc_bf16(x, y):
+    n, c, h, w = x.shape
+    _chk(load().sfk_nchw_to_nhwc_bf16(_p(x), _p(y), n, c, h, w, _stream()), "nchw_to_nhwc")
+
+
+def nhwc_bf16_to_nchw(x, y):
+    n, h, w, c = x.shape
+    _chk(load().sfk_nhwc_bf16_to_nchw(_p(x), _p(y), n, c, h, w, _stream()), "nhwc_to_nchw")
+
+
+def attack_update_linf(x, x0, gpool, alpha, eps, direction, lo, hi, stats, k):
+    n, _, s, _ = x.shape
+    _chk(load().sfk_attack_update_linf(_p(x), _p(x0), _p(gpool), _f(alpha), _f(eps), _f(direction), _f(lo), _f(hi), _p(stats), n, s, k,
+                                       _stream()), "attack_update_linf")
+
+
+def attack_update_patch(x, x0, patch, mask, gpool, lr, direction, use_sign, lo, hi, gscale, stats, k):
+    n, _, s, _ = x.shape
+    _chk(load().sfk_attack_update_patch(_p(x), _p(x0), _p(patch), _p(mask), _p(gpool), _f(lr), _f(direction), int(use_sign), _p(lo),
+                                        _p(hi), _f(gscale), _p(stats), n, s, k, _stream()), "attack_update_patch")
+
+
+def attack_update_adam(x, gpool, m, v, lr, t, gscale, k, b1=0.9, b2=0.999, eps=1e-8):
+    n, _, s, _ = x.shape
+    _chk(load().sfk_attack_update_adam(_p(x), _p(gpool), _p(m), _p(v), _f(lr), _f(b1), _f(b2), _f(eps), int(t), _f(gscale), n, s, k,
+                                       _stream()), "attack_update_adam")
+
+
+def attack_update_l2(x, x0, gpool, norms, dn, alpha, eps, direction, lo, hi, phase, k):
+    n, _, s, _ = x.shape
+    _chk(load().sfk_attack_update_l2(_p(x), _p(x0), _p(gpool), _p(norms), _p(dn), _f(alpha), _f(eps), _f(direction), _f(lo), _f(hi),
+                                     int(phase), n, s, k, _stream()), "attack_update_l2")
+
+
+def minmax_per_sample(x, lo, hi):
+    n = x.shape[0]
+    _chk(load().sfk_minmax_per_sample(_p(x), _p(lo), _p(hi), n, C.c_long(x.numel() // n), _stream()), "minmax")

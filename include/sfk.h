@@ -1,0 +1,197 @@
+/* sfk.h -- C ABI of libsfattack.so: hand-written sm_100a kernels for the attack hot path.
+ *
+ * The reference (Wu-sm/Adversarial-Attacks-on-GAN-based-Image-Fusion) has NO native interface: its
+ * hot loops call PyTorch modules.  Each entry point below therefore cites the reference
+ * Python call it stands under.  All pointers are DEVICE pointers owned by the caller, 16-byte aligned;
+ * nothing here allocates, synchronises or touches the default stream; every call enqueues on `stream`.
+ * Return: 0 ok, >0 cudaError_t, <0 argument error (SFK_E_*).
+ *
+ * Layouts:  activations NHWC bf16 [N][H][W][C];  images NCHW fp32 [N][3][H][W];
+ *           phase-planar (stride-2 transposed conv intermediates) [N][4][H+1][W+1][C] bf16 with
+ *           plane p=2a+b holding T[2m+a][2n+b];  per-sample vectors fp32 [N][C];
+ *           conv weights bf16 [S][taps][Cout][Cin] (S=1 shared, S=N per-sample modulated).
+ */
+#ifndef SFK_H
+#define SFK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sfk_stream_t; /* cudaStream_t */
+
+#define SFK_E_ARG (-1)
+#define SFK_E_SHAPE (-2)
+#define SFK_E_DRIVER (-3)
+#define SFK_E_ALIGN (-4)
+
+int sfk_version(void);
+const char* sfk_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
+ * One description covers every dense contraction on the path:
+ *   VGG / encoder conv3x3+bias+ReLU fwd and dgrad     (code/vgg.py:45-63 and its autograd)
+ *   StyleGAN2 ModulatedConv2d fwd and dgrad            (decoder(...) call, attack_main2.py:619-621)
+ *   stride-2 transposed conv as 4 phase accumulators   (same call, upsample=True layers)
+ * GEMM view: M = output positions (tile = TH x TW = 128), N = block_n output channels per
+ * accumulator, K = taps x Cin.  A k-step loads the activation box shifted by (dy,dx) from plane
+ * `plane` and the weight rows [brow + n0, +block_n) and accumulates into accumulator `acc`. */
+#define SFK_MAX_TAPS 16
+typedef struct {
+  int32_t dy, dx;    /* input shift */
+  int32_t plane;     /* input phase plane (0 for plain NHWC) */
+  int32_t acc;       /* accumulator (output plane) */
+  int32_t brow;      /* first weight row of this tap: tap_index * Cout */
+} sfk_tap;
+
+enum {
+  SFK_EP_DSCALE = 1,     /* acc *= dscale[n][col]               (demodulation) */
+  SFK_EP_NOISE = 2,      /* acc += noise_w * noise[h][w]        (NoiseInjection) */
+  SFK_EP_BIAS = 4,       /* acc += bias[col] */
+  SFK_EP_RELU = 8,
+  SFK_EP_LRELU = 16,     /* leaky_relu(.,0.2)*sqrt(2)           (FusedLeakyReLU) */
+  SFK_EP_XMASK = 32,     /* acc *= (xin > 0)                    (ReLU backward, fused into dgrad) */
+  SFK_EP_GSDOT = 64,     /* gs[n][col] += sum_hw xin*acc        (style gradient, fused into dgrad) */
+  SFK_EP_COLSCALE = 128, /* acc *= colscale[n][col]             (gx = s * gx~) */
+  SFK_EP_ACCUM = 256     /* out += acc                          (second consumer of an activation) */
+};
+
+typedef struct {
+  /* A operand: activations */
+  const void* a;             /* bf16 */
+  int32_t n_img, a_h, a_w, a_c, a_planes; /* A tensor dims: [n_img][a_planes][a_h][a_w][a_c] */
+  /* B operand: weights [b_samples][b_rows][a_c] bf16, K(=a_c)-major */
+  const void* b;
+  int32_t b_samples, b_rows;
+  /* iteration space / output: [n_img][num_acc][out_h][out_w][out_c] bf16 */
+  void* out;
+  int32_t out_h, out_w, out_c;
+  int32_t num_acc, block_n;  /* num_acc*block_n <= 512, block_n % 16 == 0, block_n <= 256 */
+  int32_t num_taps;
+  sfk_tap taps[SFK_MAX_TAPS];
+  /* epilogue */
+  int32_t flags;
+  const float* dscale;       /* [n_img][out_c] */
+  const float* bias;         /* [out_c] */
+  const float* noise;        /* [out_h][out_w] */
+  float noise_w;
+  const void* xin;           /* bf16 [n_img][out_h][out_w][out_c] */
+  const float* colscale;     /* [n_img][out_c] */
+  float* gs;                 /* [n_img][out_c] */
+  int32_t* err;              /* device int, set non-zero on an internal timeout */
+  int32_t stages;            /* 0 = auto */
+} sfk_igemm_desc;
+
+int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);
+/* Same contract on CUDA cores with plain loops: the on-device cross-check of the tensor-core path. */
+int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * First-layer 3x3 conv (Cin = 3, K = 27: bandwidth-bound, CUDA cores).  code/vgg.py:45 (conv1_1). */
+int sfk_conv_c3_fwd(const float* x /*[N][3][H][W]*/, const float* w /*[Cout][3][3][3]*/, const float* bias,
+                    void* out /*bf16 NHWC*/, int n, int h, int w_, int cout, int relu, sfk_stream_t s);
+/* dL/dx of the same conv; g is already the PRE-activation gradient. */
+int sfk_conv_c3_bwd(const void* g /*bf16 NHWC*/, const float* w, float* gx /*[N][3][H][W]*/,
+                    int n, int h, int w_, int cout, sfk_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pools.  F.avg_pool2d(img, k, k) (attack_main2.py:590-591,619-624) fused with y = a*pool(x)+b;
+ * nn.MaxPool2d(2,2[,ceil_mode]) (code/vgg.py:14,18,24). */
+int sfk_avgpool_affine_fwd(const float* x, float* y, int n_planes, int h, int w, int k, float a, float b, sfk_stream_t s);
+int sfk_maxpool2_fwd(const void* x, void* y, int n, int h, int w, int c, sfk_stream_t s); /* out = ceil(h/2) */
+/* gx = route(gy) [+ tap_coef*(x - tap_ref)] ; if relu_mask: gx *= (x > 0).  x = pool input (post-ReLU). */
+int sfk_maxpool2_bwd(const void* x, const void* y, const void* gy, void* gx, const void* tap_ref, float tap_coef,
+                     int relu_mask, int n, int h, int w, int c, sfk_stream_t s);
+int sfk_gap_fwd(const void* x, float* y, int n, int hw, int c, sfk_stream_t s);       /* mean over H*W */
+int sfk_gap_bwd(const void* x, const float* gy, void* gx, int n, int hw, int c, sfk_stream_t s); /* with ReLU mask */
+
+/* ---------------------------------------------------------------------------------------------
+ * MSE feature loss taps (nn.MSELoss(reduction='mean') per sample, attack_main2.py:605,626-645).
+ *   loss[n] += coef_loss * sum((f-ref)^2);  g (=|+=) coef_grad*(f-ref) [* (f>0)] */
+int sfk_mse_tap(const void* f, const void* ref, void* g, float* loss, float coef_loss, float coef_grad,
+                int accumulate, int relu_mask, int n, long per_sample, sfk_stream_t s);
+/* image term + avg-pool backward of the VGG input gradient:
+ *   g[n][c][h][w] = coef_grad*(img-ref) + gpool[n][c][h/k][w/k]/k^2 ; loss[n] += coef_loss*sum((img-ref)^2) */
+int sfk_image_loss_grad(const float* img, const float* ref, const float* gpool, float* g, float* loss,
+                        float coef_loss, float coef_grad, int n, int size, int k, sfk_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * StyleGAN2 synthesis pieces (un-vendored stylefusion.sf_stylegan2). */
+/* s[n][r] = bias[r] + scale * dot(w[n][row_widx[r]][:], A[r][:]) */
+int sfk_style_affine_fwd(const float* w, const float* A, const float* bias, const int32_t* row_widx, float* s,
+                         int n, int n_latent, int style_dim, int s_dim, float scale, sfk_stream_t st);
+/* gw[n][l][k] = scale * sum_{r: row_widx[r]==l} gs[n][r]*A[r][k]   (rows of one layer are contiguous) */
+int sfk_style_affine_bwd(const float* gs, const float* A, const int32_t* layer_row_start, const int32_t* layer_widx,
+                         int n_layers, float* gw, int n, int n_latent, int style_dim, int s_dim, float scale,
+                         sfk_stream_t st);
+/* d[n][j] = rsqrt(sum_i s[n][i]^2 Q[j][i] + 1e-8) */
+int sfk_demod_fwd(const float* s, int s_stride, const float* Q, float* d, int n, int cin, int cout, sfk_stream_t st);
+/* gs[n][i] -= s[n][i] * sum_j gdacc[n][j] d[n][j]^2 Q[j][i] */
+int sfk_demod_bwd(const float* s, int s_stride, const float* Q, const float* d, const float* gdacc, float* gs,
+                  int gs_stride, int n, int cin, int cout, sfk_stream_t st);
+/* wmod[n][t][j][i] = bf16(wbase[t][j][i] * s[n][i])    (wbase already carries 1/sqrt(cin*k*k)) */
+int sfk_modulate_weights(const float* wbase, const float* s, int s_stride, void* wmod, int n, int taps, int cout,
+                         int cin, sfk_stream_t st);
+/* upfirdn2d([1,3,3,1] blur, pad (1,1)) of the phase-planar transposed-conv output, fused with
+ * demod * . + noise + bias, leaky_relu*sqrt2.  T: [n][4][h+1][w+1][c] -> out [n][2h][2w][c]. */
+int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias,
+                     int n, int h, int w, int c, sfk_stream_t st);
+/* backward of the above: gT (phase-planar) = blur^T(d * act'(out) * gout); gdacc[n][c] += sum gy*y */
+int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d, const float* noise, float noise_w,
+                     const float* bias, float* gdacc, int n, int h, int w, int c, sfk_stream_t st);
+/* backward of FusedLeakyReLU+noise+demod for non-upsampling layers: gz = d*act'(out)*gout (in place ok) */
+int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w,
+                const float* bias, float* gdacc, int n, int h, int w, int c, sfk_stream_t st);
+/* ToRGB: rgb[n][c][h][w] = sum_i wrgb[c][i] s[n][i] x[n][h][w][i] + bias[c] + upsample2(skip) */
+int sfk_torgb_fwd(const void* x, const float* wrgb, const float* s, int s_stride, const float* bias, const float* skip,
+                  float* rgb, int n, int h, int w, int c, sfk_stream_t st);
+/* gx[n][h][w][i] = s[n][i]*sum_c wrgb[c][i] grgb[n][c][h][w];  gs[n][i] += sum_hw x*gx~ */
+int sfk_torgb_bwd(const void* x, const float* wrgb, const float* s, int s_stride, const float* grgb, void* gx,
+                  float* gs, int gs_stride, int n, int h, int w, int c, sfk_stream_t st);
+/* transpose of the skip upsample: gskip = upfirdn2d(g, k*4, down=2, pad=(1,2)); planes = n*3 */
+int sfk_rgb_down(const float* g, float* gskip, int planes, int h, int w, sfk_stream_t st);
+
+/* ---------------------------------------------------------------------------------------------
+ * small dense helpers (encoder head, fusion) */
+int sfk_linear_fwd(const float* x, const float* W, const float* bias, float* y, int n, int in, int out, sfk_stream_t st);
+int sfk_linear_bwd(const float* gy, const float* W, float* gx, int n, int in, int out, sfk_stream_t st);
+/* spatial pair fusion stand-in: q = sigmoid(al*sa + be*sb + c); s = q*sa + (1-q)*sb */
+int sfk_fuse_spatial_fwd(const float* sa, const float* sb, const float* al, const float* be, const float* c,
+                         float* s, int n, int dim, sfk_stream_t st);
+int sfk_fuse_spatial_bwd(const float* sa, const float* sb, const float* al, const float* be, const float* c,
+                         const float* gs, float* gsa, float* gsb, int n, int dim, sfk_stream_t st);
+int sfk_axpby(const float* x, const float* y, float* out, float a, float b, long n, sfk_stream_t st);
+
+/* layout converters for the NCHW fp32 API surface */
+int sfk_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, sfk_stream_t st);
+int sfk_nhwc_bf16_to_nchw(const void* x, float* y, int n, int c, int h, int w, sfk_stream_t st);
+
+/* ---------------------------------------------------------------------------------------------
+ * Perturbation update (code/attack/interpolation.py:92-94 PGD step; adversarial_patch.py:131-138;
+ * attack_main2.py:413-433 mask apply; attack_main2.py:606 Adam).  gpool is the gradient w.r.t. the
+ * k x k box-pooled input; the full-resolution gradient is gscale*gpool[h/k][w/k].
+ *   mode 0 linf : x = clamp(x0 + clamp(x + dir*alpha*sign(g) - x0, -eps, eps), lo, hi)
+ *   mode 1 l2   : two-phase, see sfk_attack_update_l2
+ *   mode 2 patch: patch += dir*lr*(sign?sign(g):g); x = clamp((1-m)*x0 + m*patch, lo[n], hi[n])
+ *   mode 3 adam : torch.optim.Adam step on x (m, v state), no projection
+ * stats[n] += sum |x_new - x0| (a cheap on-device progress metric reduced with warp shuffles). */
+int sfk_attack_update_linf(float* x, const float* x0, const float* gpool, float alpha, float eps, float dir,
+                           float lo, float hi, float* stats, int n, int size, int k, sfk_stream_t st);
+int sfk_attack_update_patch(float* x, const float* x0, float* patch, const float* mask, const float* gpool,
+                            float lr, float dir, int use_sign, const float* lo, const float* hi, float gscale,
+                            float* stats, int n, int size, int k, sfk_stream_t st);
+int sfk_attack_update_adam(float* x, const float* gpool, float* m, float* v, float lr, float b1, float b2,
+                           float eps, int t, float gscale, int n, int size, int k, sfk_stream_t st);
+/* l2: norms[n] = sum g^2 (phase 0); x' = x + dir*alpha*g/|g|, dn[n] = sum (x'-x0)^2 (phase 1);
+ *     x = clamp(x0 + (x'-x0)*min(1, eps/|d|), lo, hi) (phase 2) */
+int sfk_attack_update_l2(float* x, const float* x0, const float* gpool, float* norms, float* dn, float alpha,
+                         float eps, float dir, float lo, float hi, int phase, int n, int size, int k, sfk_stream_t st);
+int sfk_minmax_per_sample(const float* x, float* lo, float* hi, int n, long per_sample, sfk_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
