@@ -1,0 +1,88 @@
+"""The iterative attack loops on top of AttackEngine (one shard of independent pairs).
+
+Update rules and where they come from in the reference:
+  linf  (FGSM / PGD)  code/attack/interpolation.py:71-96 (random start :74-76, step :92, projection :93, clamp :94)
+  patch               code/attack/patch/adversarial_patch.py:106,131-138 ; mask apply code/attack/attack_main2.py:413-433
+  adam                code/attack/attack_main2.py:606,614-653 (torch.optim.Adam on the pixels)
+  l2                  not in the reference: normalised step, projection onto the eps ball
+Every step is one fused update kernel (sign/step/projection/clamp/mask + a warp-shuffle reduction); the loss of every
+iteration stays in a device buffer and is copied out once after the loop (the reference formats it on the host every
+iteration: adversarial_patch.py:141-156).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib
+from .engine import AttackEngine, LossCfg
+
+
+@dataclass
+class AttackCfg:
+    kind: str = "linf"            # linf | l2 | patch | adam
+    steps: int = 10
+    eps: float = 8.0 / 255.0
+    alpha: float = 2.0 / 255.0
+    random_start: bool = True
+    targeted: bool = False
+    patch_sign: bool = False
+    lr: float = 1.0
+
+
+def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: AttackCfg, start_noise: Optional[torch.Tensor] = None,
+               target: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, mask: Optional[torch.Tensor] = None,
+               patch0: Optional[torch.Tensor] = None, compute_final: bool = True, record: Optional[list] = None):
+    """xa, xb: (B,3,S,S) in [0,1] on the engine's device.  Returns dict(x_adv, fused_adv, fused_ref, losses, [patch])."""
+    B, dev = eng.B, eng.dev
+    direction = -1.0 if cfg.targeted else 1.0
+    eng.set_inputs(xa, xb)
+    eng.compute_reference(target if cfg.targeted else None)
+    k = eng.k_in
+    gscale = 2.0 / (k * k)
+    losses = torch.zeros(cfg.steps, B, device=dev)
+    if cfg.kind == "patch":
+        patch = patch0.to(dev).clone().contiguous()
+        mask = mask.to(dev).expand_as(eng.x).contiguous()
+        lo = torch.empty(2 * B, device=dev)
+        hi = torch.empty(2 * B, device=dev)
+        lib.minmax_per_sample(eng.x0, lo, hi)
+        # adv_x = (1-mask)*img + mask*patch, clamped to the clean range (adversarial_patch.py:106,137-138): a zero-step update
+        zero_g = torch.zeros_like(eng.g_xin)
+        lib.attack_update_patch(eng.x, eng.x0, patch, mask, zero_g, 0.0, direction, False, lo, hi, gscale, None, k)
+    elif cfg.random_start and start_noise is not None and cfg.kind in ("linf", "l2"):
+        eng.x.copy_(torch.clamp(eng.x0 + cfg.eps * start_noise.reshape(eng.x0.shape).to(dev), 0.0, 1.0))   # interpolation.py:74-76
+    if cfg.kind == "adam":
+        m = torch.zeros_like(eng.x)
+        v = torch.zeros_like(eng.x)
+    if cfg.kind == "l2":
+        norms = torch.zeros(2 * B, device=dev)
+        dn = torch.zeros(2 * B, device=dev)
+    for it in range(cfg.steps):
+        loss, g = eng.forward_backward()
+        losses[it].copy_(loss)
+        if record is not None:      # diagnostics only (forces clones; never used by the benchmark)
+            record.append(dict(loss=loss.clone(), grad=eng.full_res_grad(), x=eng.x.clone(), img=eng.syn.image.clone()))
+        if cfg.kind == "linf":
+            lib.attack_update_linf(eng.x, eng.x0, g, cfg.alpha, cfg.eps, direction, 0.0, 1.0, eng.stats, k)
+        elif cfg.kind == "l2":
+            norms.zero_()
+            dn.zero_()
+            for ph in range(3):
+                lib.attack_update_l2(eng.x, eng.x0, g, norms, dn, cfg.alpha, cfg.eps, direction, 0.0, 1.0, ph, k)
+        elif cfg.kind == "patch":
+            lib.attack_update_patch(eng.x, eng.x0, patch, mask, g, cfg.lr, direction, cfg.patch_sign, lo, hi, gscale, eng.stats, k)
+        elif cfg.kind == "adam":
+            # Adam minimises; ascent (untargeted) flips the gradient sign
+            lib.attack_update_adam(eng.x, g, m, v, cfg.lr, it + 1, -direction * gscale, k)
+        else:
+            raise ValueError(cfg.kind)
+    out = dict(x_adv=eng.x.clone(), fused_ref=eng.ref_img.clone(), losses=losses)
+    if compute_final:
+        out["fused_adv"] = eng.fused_forward().clone()
+    if cfg.kind == "patch":
+        out["patch"] = patch
+    eng.check()
+    return out

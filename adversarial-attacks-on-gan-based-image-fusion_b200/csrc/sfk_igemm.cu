@@ -37,6 +37,7 @@ struct __align__(64) IgemmKArgs {
   int sbo_bytes;
   int tmem_cols;
   int flags;
+  int vec_stride;
   float noise_w;
   __nv_bfloat16* out;
   const float* dscale;
@@ -161,6 +162,7 @@ __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h,
   const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
   const long off = pix * a.out_c + col0;
   const long vec = static_cast<long>(n) * a.out_c + col0;
+  const long svec = static_cast<long>(n) * a.vec_stride + col0;  // colscale / gs rows may live inside a wider [n][s_dim] array
   if (flags & SFK_EP_DSCALE) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= __ldg(a.dscale + vec + i);
@@ -202,7 +204,7 @@ __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h,
   }
   if (flags & SFK_EP_COLSCALE) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= __ldg(a.colscale + vec + i);
+    for (int i = 0; i < 16; ++i) v[i] *= __ldg(a.colscale + svec + i);
   }
   if (valid) {
     if (flags & SFK_EP_ACCUM) {
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc_kernel(const __grid_cons
   }
   __syncthreads();
   if ((a.flags & SFK_EP_GSDOT) && threadIdx.x < a.block_n) {
-    atomicAdd(a.gs + static_cast<long>(n) * a.out_c + n0 + threadIdx.x, gs_acc[threadIdx.x]);
+    atomicAdd(a.gs + static_cast<long>(n) * a.vec_stride + n0 + threadIdx.x, gs_acc[threadIdx.x]);
   }
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -362,6 +364,7 @@ struct RefArgs {
   const __nv_bfloat16* B;
   int n_img, a_h, a_w, a_c, a_planes, b_rows, b_per_sample;
   int out_h, out_w, out_c, num_acc, block_n, num_taps, flags;
+  int vec_stride;
   float noise_w;
   __nv_bfloat16* out;
   const float* dscale;
@@ -412,7 +415,7 @@ __global__ void igemm_ref_kernel(const __grid_constant__ RefArgs a) {
     epilogue16(a, n, acc, h, w, col0, true, v, gsd);
     if (a.flags & SFK_EP_GSDOT) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) atomicAdd(a.gs + static_cast<long>(n) * a.out_c + col0 + i, gsd[i]);
+      for (int i = 0; i < 16; ++i) atomicAdd(a.gs + static_cast<long>(n) * a.vec_stride + col0 + i, gsd[i]);
     }
   }
 }
@@ -507,6 +510,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   const int cols = d->num_acc * d->block_n;
   k.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   k.flags = d->flags;
+  k.vec_stride = d->vec_stride > 0 ? d->vec_stride : d->out_c;
   k.noise_w = d->noise_w;
   k.out = static_cast<__nv_bfloat16*>(d->out);
   k.dscale = d->dscale;
@@ -572,6 +576,7 @@ extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
   r.b_rows = d->b_rows; r.b_per_sample = d->b_samples > 1 ? 1 : 0;
   r.out_h = d->out_h; r.out_w = d->out_w; r.out_c = d->out_c; r.num_acc = d->num_acc; r.block_n = d->block_n;
   r.num_taps = d->num_taps; r.flags = d->flags; r.noise_w = d->noise_w;
+  r.vec_stride = d->vec_stride > 0 ? d->vec_stride : d->out_c;
   r.out = static_cast<__nv_bfloat16*>(d->out);
   r.dscale = d->dscale; r.bias = d->bias; r.noise = d->noise;
   r.xin = static_cast<const __nv_bfloat16*>(d->xin); r.colscale = d->colscale; r.gs = d->gs;

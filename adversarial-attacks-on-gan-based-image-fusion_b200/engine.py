@@ -1,0 +1,506 @@
+"""The attack hot path as explicit forward/backward kernel schedules over pre-allocated HBM buffers.
+
+Nothing here computes: every arithmetic step is a launch into libsfattack.so (lib.py).  torch is used
+for device memory and streams only.  Three schedules:
+
+  ConvStack        3x3 conv + bias + ReLU / 2x2 max-pool chains: the reference's VGG feature extractor
+                   (code/vgg.py:44-64) and the encoder stand-in.
+  SynthesisEngine  StyleGAN2 config-f synthesis from StyleSpace vectors, forward and data/style backward
+                   (the `decoder([w], input_is_latent=True, ...)` call, code/attack/attack_main2.py:619-621).
+  AttackEngine     encoder -> pair fusion -> synthesis -> VGG/pixel loss -> backward -> perturbation update
+                   for a batch of independent image pairs (the loops of attack_main2.py:614-653 and
+                   attack/patch/adversarial_patch.py:111-158, re-posed on the fused output as north_star asks).
+
+Layouts: activations NHWC bf16, images NCHW fp32, style vectors fp32.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib
+from .params import EncSpec, GenSpec, VGG_CONVS
+
+BF16 = torch.bfloat16
+
+
+def _empty(shape, dev, dtype=BF16):
+    return torch.empty(shape, device=dev, dtype=dtype)
+
+
+def _zeros(shape, dev, dtype=torch.float32):
+    return torch.zeros(shape, device=dev, dtype=dtype)
+
+
+# =================================================================================================
+@dataclass
+class StackLayer:
+    kind: str            # "c3" | "conv" | "pool"
+    cin: int = 0
+    cout: int = 0
+    tap: int = -1        # index into the tap list, -1 = not a tap
+    h: int = 0           # output spatial size (filled by ConvStack)
+    w: int = 0
+
+
+def vgg_layers(width_div: int = 1) -> List[StackLayer]:
+    """conv1_1[tap0] conv1_2[tap1] pool1 conv2_1 conv2_2 pool2[tap2, named "conv3_2" by the reference]
+    conv3_1 conv3_2 conv3_3 pool3(ceil) conv4_1 conv4_2[tap3]   (code/vgg.py:44-64)."""
+    c = lambda v: v // width_div
+    return [StackLayer("c3", 3, c(64), tap=0), StackLayer("conv", c(64), c(64), tap=1), StackLayer("pool"),
+            StackLayer("conv", c(64), c(128)), StackLayer("conv", c(128), c(128)), StackLayer("pool", tap=2),
+            StackLayer("conv", c(128), c(256)), StackLayer("conv", c(256), c(256)), StackLayer("conv", c(256), c(256)),
+            StackLayer("pool"), StackLayer("conv", c(256), c(512)), StackLayer("conv", c(512), c(512), tap=3)]
+
+
+def encoder_layers(spec: EncSpec) -> List[StackLayer]:
+    L: List[StackLayer] = []
+    cin = 3
+    for i, co in enumerate(spec.widths):
+        L.append(StackLayer("c3" if i == 0 else "conv", cin, co))
+        if i < len(spec.widths) - 1:
+            L.append(StackLayer("pool"))
+        cin = co
+    return L
+
+
+class ConvStack:
+    def __init__(self, layers: List[StackLayer], weights: Sequence[Tuple[torch.Tensor, torch.Tensor]], n: int, res: int,
+                 device, err: torch.Tensor):
+        self.layers, self.n, self.res, self.dev, self.err = layers, n, res, device, err
+        self.w_f32, self.bias, self.w_fwd, self.w_bwd = {}, {}, {}, {}
+        h = w = res
+        c = 3
+        wi = 0
+        self.out: List[torch.Tensor] = []
+        self.g: List[torch.Tensor] = []
+        for i, l in enumerate(layers):
+            if l.kind == "pool":
+                h, w = (h + 1) // 2, (w + 1) // 2
+                l.cin = l.cout = c
+            else:
+                W, b = weights[wi]
+                wi += 1
+                assert W.shape[0] == l.cout and W.shape[1] == l.cin, (W.shape, l)
+                self.bias[i] = b.to(device=device, dtype=torch.float32).contiguous()
+                if l.kind == "c3":
+                    self.w_f32[i] = W.to(device=device, dtype=torch.float32).contiguous()
+                else:
+                    Wd = W.to(device=device, dtype=torch.float32)
+                    self.w_fwd[i] = Wd.permute(2, 3, 0, 1).reshape(9 * l.cout, l.cin).to(BF16).contiguous()   # [tap][cout][cin]
+                    self.w_bwd[i] = Wd.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(BF16).contiguous()   # [tap][cin][cout]
+                c = l.cout
+            l.h, l.w = h, w
+            self.out.append(_empty((n, h, w, c), device))
+            self.g.append(_empty((n, h, w, c), device))
+        self.g_in = _empty((n, 3, res, res), device, torch.float32)
+        self.taps = [i for i, l in enumerate(layers) if l.tap >= 0]
+        self._fwd_desc, self._bwd_desc = {}, {}
+        self._build_descs()
+
+    def _build_descs(self):
+        n = self.n
+        for i, l in enumerate(self.layers):
+            if l.kind != "conv":
+                continue
+            prev = self.layers[i - 1]
+            self._fwd_desc[i] = lib.make_igemm_desc(
+                self.out[i - 1], n, prev.h, prev.w, l.cin, 1, self.w_fwd[i], 1, 9 * l.cout, self.out[i], l.h, l.w, l.cout, 1,
+                lib.pick_block_n(l.cout), lib.conv3x3_taps(l.cout), flags=lib.EP_BIAS | lib.EP_RELU, bias=self.bias[i], err=self.err)
+            flags = lib.EP_XMASK if prev.kind != "pool" else 0
+            self._bwd_desc[i] = lib.make_igemm_desc(
+                self.g[i], n, l.h, l.w, l.cout, 1, self.w_bwd[i], 1, 9 * l.cin, self.g[i - 1], prev.h, prev.w, l.cin, 1,
+                lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=flags,
+                xin=self.out[i - 1] if flags else None, err=self.err)
+
+    def forward(self, x: torch.Tensor):
+        """x: (n,3,res,res) fp32 NCHW."""
+        for i, l in enumerate(self.layers):
+            if l.kind == "c3":
+                lib.conv_c3_fwd(x, self.w_f32[i], self.bias[i], self.out[i], relu=True)
+            elif l.kind == "conv":
+                lib.igemm(self._fwd_desc[i])
+            else:
+                lib.maxpool2_fwd(self.out[i - 1], self.out[i])
+        return self.out[-1]
+
+    def tap_outputs(self) -> List[torch.Tensor]:
+        return [self.out[i] for i in self.taps]
+
+    def _tap_coefs(self, i: int, coef: float):
+        per = self.out[i].numel() // self.n
+        return coef / per, 2.0 * coef / per
+
+    def backward(self, tap_refs: Optional[Sequence[torch.Tensor]] = None, tap_coef: float = 0.0,
+                 loss: Optional[torch.Tensor] = None, top_grad_ready: bool = False) -> torch.Tensor:
+        """Back-propagate sum_taps coef*MSE(tap, ref) (and/or a gradient already stored, masked, in g[-1])
+        down to the stack input.  Returns g_in (n,3,res,res) fp32 (owned by the stack)."""
+        L = self.layers
+        last = len(L) - 1
+
+        def tap_at(i):
+            return tap_refs is not None and L[i].tap >= 0
+
+        if not top_grad_ready:
+            assert tap_at(last)
+            cl, cg = self._tap_coefs(last, tap_coef)
+            lib.mse_tap(self.out[last], tap_refs[L[last].tap], self.g[last], loss, cl, cg, accumulate=False,
+                        relu_mask=L[last].kind != "pool")
+        for i in range(last, -1, -1):
+            l = L[i]
+            if l.kind == "conv":
+                lib.igemm(self._bwd_desc[i])
+                if tap_at(i - 1):
+                    cl, cg = self._tap_coefs(i - 1, tap_coef)
+                    lib.mse_tap(self.out[i - 1], tap_refs[L[i - 1].tap], self.g[i - 1], loss, cl, cg, accumulate=True,
+                                relu_mask=L[i - 1].kind != "pool")
+            elif l.kind == "pool":
+                if tap_at(i - 1):
+                    cl, cg = self._tap_coefs(i - 1, tap_coef)
+                    lib.mse_tap(self.out[i - 1], tap_refs[L[i - 1].tap], None, loss, cl, 0.0)   # loss value only
+                    lib.maxpool2_bwd(self.out[i - 1], self.g[i], self.g[i - 1], tap_ref=tap_refs[L[i - 1].tap], tap_coef=cg,
+                                     relu_mask=True)
+                else:
+                    lib.maxpool2_bwd(self.out[i - 1], self.g[i], self.g[i - 1], relu_mask=True)
+            else:  # c3
+                lib.conv_c3_bwd(self.g[i], self.w_f32[i], self.g_in)
+        return self.g_in
+
+    @property
+    def launches_fwd(self):
+        return len(self.layers)
+
+
+# =================================================================================================
+class SynthesisEngine:
+    """StyleGAN2 synthesis from a concatenated StyleSpace vector s (B, s_dim)."""
+
+    def __init__(self, spec: GenSpec, P: Dict[str, torch.Tensor], batch: int, device, err: torch.Tensor):
+        self.spec, self.B, self.dev, self.err = spec, batch, device, err
+        B = batch
+        f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
+        self.layers = spec.layers
+        self.A_all = f32(torch.cat([P[f"{l.name}.conv.modulation.weight"] for l in spec.layers], 0))
+        self.b_all = f32(torch.cat([P[f"{l.name}.conv.modulation.bias"] for l in spec.layers], 0))
+        self.row_widx = torch.cat([torch.full((l.cin,), l.w_idx, dtype=torch.int32) for l in spec.layers]).to(device)
+        self.layer_row_start = torch.tensor([l.s_off for l in spec.layers] + [spec.s_dim], dtype=torch.int32, device=device)
+        self.layer_widx = torch.tensor([l.w_idx for l in spec.layers], dtype=torch.int32, device=device)
+        self.aff_scale = 1.0 / math.sqrt(spec.style_dim)
+        c0 = spec.channels[4]
+        const = P["input.input"][0].permute(1, 2, 0).contiguous()                      # (4,4,C)
+        self.const = const[None].repeat(B, 1, 1, 1).to(device=device, dtype=BF16).contiguous()
+        self.L: List[dict] = []
+        max_w = 0
+        max_T = 0
+        for l in spec.layers:
+            e = dict(l=l)
+            if l.kind == "rgb":
+                e["wrgb"] = f32(P[f"{l.name}.conv.weight"][0, :, :, 0, 0] / math.sqrt(l.cin))   # (3,cin), carries 1/sqrt(cin)
+                e["bias"] = f32(P[f"{l.name}.bias"].reshape(3))
+                e["rgb"] = _empty((B, 3, l.res, l.res), device, torch.float32)
+                e["grgb"] = _empty((B, 3, l.res, l.res), device, torch.float32)
+            else:
+                W = P[f"{l.name}.conv.weight"][0].to(torch.float32)                              # (cout,cin,3,3)
+                scale = 1.0 / math.sqrt(l.cin * 9)
+                Ws = (W * scale).to(device)
+                e["wbase"] = Ws.permute(2, 3, 0, 1).reshape(9, l.cout, l.cin).contiguous()        # fp32 [tap][cout][cin]
+                e["wT"] = Ws.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(BF16).contiguous()  # bf16 [tap][cin][cout], shared
+                e["Q"] = (Ws * Ws).sum((2, 3)).contiguous()                                       # (cout,cin)
+                e["bias"] = f32(P[f"{l.name}.activate.bias"])
+                e["noise"] = f32(P[f"noises.noise_{l.noise_idx}"][0, 0])
+                e["noise_w"] = float(P[f"{l.name}.noise.weight"].reshape(-1)[0])
+                e["d"] = _empty((B, l.cout), device, torch.float32)
+                e["gdacc"] = _zeros((B, l.cout), device)
+                e["out"] = _empty((B, l.res, l.res, l.cout), device)
+                e["gout"] = _empty((B, l.res, l.res, l.cout), device)
+                max_w = max(max_w, 9 * l.cout * l.cin)
+                if l.kind == "up":
+                    hp = l.res // 2 + 1
+                    max_T = max(max_T, 4 * hp * hp * l.cout)
+            self.L.append(e)
+        self.wmod = _empty((B * max_w,), device)
+        self.T = _empty((B * max(max_T, 8),), device)
+        self.gx_scratch = _empty((B, 4, 4, c0), device)
+        self.s = _empty((B, spec.s_dim), device, torch.float32)
+        self.gs = _zeros((B, spec.s_dim), device)
+        self._gd_all = [e["gdacc"] for e in self.L if "gdacc" in e]
+        self._build_descs()
+
+    # ---------------------------------------------------------------------------------------
+    def _build_descs(self):
+        B, sd = self.B, self.spec.s_dim
+        x, xh = self.const, 4
+        prev_conv = None
+        for e in self.L:
+            l = e["l"]
+            if l.kind == "rgb":
+                e["x"] = x
+                continue
+            e["x"] = x
+            if l.kind == "conv":
+                wmod = self.wmod[: B * 9 * l.cout * l.cin].view(B, 9 * l.cout, l.cin)
+                e["wmod"] = wmod
+                e["fwd"] = lib.make_igemm_desc(
+                    x, B, l.res, l.res, l.cin, 1, wmod, B, 9 * l.cout, e["out"], l.res, l.res, l.cout, 1, lib.pick_block_n(l.cout),
+                    lib.conv3x3_taps(l.cout), flags=lib.EP_DSCALE | lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU, dscale=e["d"],
+                    bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err)
+                gx_dst = prev_conv["gout"] if prev_conv is not None else self.gx_scratch
+                e["bwd"] = lib.make_igemm_desc(
+                    e["gout"], B, l.res, l.res, l.cout, 1, e["wT"], 1, 9 * l.cin, gx_dst, l.res, l.res, l.cin, 1,
+                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=x,
+                    colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
+            else:  # up
+                h = l.res // 2
+                wmod = self.wmod[: B * 9 * l.cout * l.cin].view(B, 9 * l.cout, l.cin)
+                e["wmod"] = wmod
+                T = self.T[: B * 4 * (h + 1) * (h + 1) * l.cout].view(B, 4, h + 1, h + 1, l.cout)
+                e["T"] = T
+                e["fwd"] = lib.make_igemm_desc(x, B, h, h, l.cin, 1, wmod, B, 9 * l.cout, T, h + 1, h + 1, l.cout, 4,
+                                               lib.pick_block_n(l.cout, 4), lib.tconv_taps(l.cout), err=self.err)
+                # data gradient accumulates into the gradient buffer of the previous resolution's conv
+                e["bwd"] = lib.make_igemm_desc(
+                    T, B, h + 1, h + 1, l.cout, 4, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1, lib.pick_block_n(l.cin),
+                    lib.tconv_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM, xin=x, colscale=self.s,
+                    gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
+            x = e["out"]
+            prev_conv = e
+
+    # ---------------------------------------------------------------------------------------
+    def styles_from_wplus(self, wplus: torch.Tensor, s_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        s_out = self.s if s_out is None else s_out
+        lib.style_affine_fwd(wplus, self.A_all, self.b_all, self.row_widx, s_out, self.aff_scale)
+        return s_out
+
+    def wplus_grad_from_styles(self, gs: torch.Tensor, gw: torch.Tensor) -> torch.Tensor:
+        lib.style_affine_bwd(gs, self.A_all, self.layer_row_start, self.layer_widx, gw, self.aff_scale)
+        return gw
+
+    def forward(self, s: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """s (B, s_dim) fp32 (default: self.s).  Returns the image buffer (B,3,size,size) fp32."""
+        if s is not None and s.data_ptr() != self.s.data_ptr():
+            self.s.copy_(s)
+        s = self.s
+        skip = None
+        for e in self.L:
+            l = e["l"]
+            if l.kind == "rgb":
+                lib.torgb_fwd(e["x"], e["wrgb"], s, l.s_off, e["bias"], skip, e["rgb"])
+                skip = e["rgb"]
+                continue
+            lib.demod_fwd(s, l.s_off, e["Q"], e["d"])
+            lib.modulate_weights(e["wbase"], s, l.s_off, e["wmod"])
+            lib.igemm(e["fwd"])
+            if l.kind == "up":
+                lib.blur_act_fwd(e["T"], e["out"], e["d"], e["noise"], e["noise_w"], e["bias"])
+        return skip
+
+    @property
+    def image(self) -> torch.Tensor:
+        return self.L[-1]["rgb"]
+
+    def backward(self, g_img: torch.Tensor) -> torch.Tensor:
+        """g_img (B,3,size,size) fp32 -> gs (B, s_dim) fp32 (owned).  Must follow forward() with the same s.
+
+        Layer list is [conv1, rgb1, (up, conv, rgb) per resolution].  Every conv output feeds ToRGB and (except at the
+        top) the next up-conv: ToRGB's backward is the first writer of the conv's gradient buffer, the up-conv's data
+        gradient accumulates into it (SFK_EP_ACCUM)."""
+        s = self.s
+        self.gs.zero_()
+        for g in self._gd_all:
+            g.zero_()
+        L = self.L
+        nb = (len(L) - 2) // 3
+
+        def conv_backward(e):
+            l = e["l"]
+            lib.act_bwd(e["out"], e["gout"], e["gout"], e["d"], e["noise"], e["noise_w"], e["bias"], e["gdacc"])
+            lib.igemm(e["bwd"])                       # -> gradient of the producer of x, + fused style gradient
+            lib.demod_bwd(s, l.s_off, e["Q"], e["d"], e["gdacc"], self.gs)
+
+        conv, rgb = (L[3 + 3 * (nb - 1)], L[4 + 3 * (nb - 1)]) if nb > 0 else (L[0], L[1])
+        grgb = g_img
+        lib.torgb_bwd(conv["out"], rgb["wrgb"], s, rgb["l"].s_off, grgb, conv["gout"], self.gs)
+        for k in range(nb - 1, -1, -1):
+            up, conv = L[2 + 3 * k], L[3 + 3 * k]
+            below_conv, below_rgb = (L[3 + 3 * (k - 1)], L[4 + 3 * (k - 1)]) if k > 0 else (L[0], L[1])
+            conv_backward(conv)                        # writes up["gout"]
+            lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
+            lib.rgb_down(grgb, below_rgb["grgb"])
+            grgb = below_rgb["grgb"]
+            lib.torgb_bwd(below_conv["out"], below_rgb["wrgb"], s, below_rgb["l"].s_off, grgb, below_conv["gout"], self.gs)
+            lib.igemm(up["bwd"])                       # accumulates into below_conv["gout"]
+            lib.demod_bwd(s, up["l"].s_off, up["Q"], up["d"], up["gdacc"], self.gs)
+        conv_backward(L[0])
+        return self.gs
+
+
+# =================================================================================================
+@dataclass
+class LossCfg:
+    c_pix: float = 1.0
+    c_feat: float = 1.0
+    c_reg: float = 0.0
+
+
+class AttackEngine:
+    """One data-parallel shard of the attack: B independent pairs resident in HBM."""
+
+    def __init__(self, gspec: GenSpec, GP, espec: EncSpec, EP, vgg_sd, FP=None, fusion: str = "arithmetic", batch: int = 1,
+                 device="cuda:0", loss: Optional[LossCfg] = None, vgg_res: int = 256, vgg_width_div: int = 1):
+        lib.load()
+        self.dev = torch.device(device)
+        self.gspec, self.espec, self.fusion, self.B = gspec, espec, fusion, batch
+        self.loss_cfg = loss or LossCfg()
+        B, dev = batch, self.dev
+        S, R = gspec.size, espec.in_res
+        self.S, self.R, self.k_in = S, R, S // R
+        self.vgg_res, self.k_vgg = vgg_res, S // vgg_res
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        # encoder
+        enc_w = [(EP[f"convs.{i}.weight"], EP[f"convs.{i}.bias"]) for i in range(len(espec.widths))]
+        self.enc = ConvStack(encoder_layers(espec), enc_w, 2 * B, R, dev, self.err)
+        self.head_w = f32(EP["head.weight"])
+        self.head_b = f32(EP["head.bias"] + EP["latent_avg"].reshape(-1))     # get_latents adds latent_avg (attack_main2.py:137-146)
+        cl = espec.widths[-1]
+        LD = espec.n_latent * espec.style_dim
+        self.feat = _empty((2 * B, cl), dev, torch.float32)
+        self.gfeat = _empty((2 * B, cl), dev, torch.float32)
+        self.codes = _empty((2 * B, espec.n_latent, espec.style_dim), dev, torch.float32)
+        self.gcodes = _empty((2 * B, espec.n_latent, espec.style_dim), dev, torch.float32)
+        self.w = _empty((B, espec.n_latent, espec.style_dim), dev, torch.float32)
+        self.gw = _empty((B, espec.n_latent, espec.style_dim), dev, torch.float32)
+        # synthesis
+        self.syn = SynthesisEngine(gspec, GP, B, dev, self.err)
+        if fusion == "spatial":
+            self.FP = {k: f32(v) for k, v in FP.items()}
+            self.s_all = _empty((2 * B, gspec.s_dim), dev, torch.float32)
+            self.gs_all = _empty((2 * B, gspec.s_dim), dev, torch.float32)
+        # loss network
+        from .params import VGG_EXECUTED
+        vals = list(vgg_sd.values())
+        vgg_w = [(vals[2 * i], vals[2 * i + 1]) for i in range(VGG_EXECUTED)]
+        self.vgg = ConvStack(vgg_layers(vgg_width_div), vgg_w, B, vgg_res, dev, self.err)
+        self.vgg_in = _empty((B, 3, vgg_res, vgg_res), dev, torch.float32)
+        self.ref_img = _empty((B, 3, S, S), dev, torch.float32)
+        self.ref_feats = [torch.empty_like(t) for t in self.vgg.tap_outputs()]
+        self.g_img = _empty((B, 3, S, S), dev, torch.float32)
+        self.loss = _zeros((B,), dev)
+        if self.loss_cfg.c_reg != 0.0:
+            self.vgg_reg = ConvStack(vgg_layers(vgg_width_div), vgg_w, 2 * B, R, dev, self.err)
+            self.reg_refs = [torch.empty_like(t) for t in self.vgg_reg.tap_outputs()]
+            self.reg_loss = _zeros((2 * B,), dev)
+        # attack state
+        self.x = _empty((2 * B, 3, S, S), dev, torch.float32)
+        self.x0 = _empty((2 * B, 3, S, S), dev, torch.float32)
+        self.xin = _empty((2 * B, 3, R, R), dev, torch.float32)
+        self.g_xin = _empty((2 * B, 3, R, R), dev, torch.float32)
+        self.stats = _zeros((2 * B,), dev)
+
+    # ---------------------------------------------------------------------------------------
+    def set_inputs(self, xa: torch.Tensor, xb: torch.Tensor):
+        B = self.B
+        self.x0[:B].copy_(xa)
+        self.x0[B:].copy_(xb)
+        self.x.copy_(self.x0)
+
+    def _encode(self):
+        lib.avgpool_affine_fwd(self.x, self.xin, self.k_in, 2.0, -1.0)
+        top = self.enc.forward(self.xin)
+        lib.gap_fwd(top, self.feat)
+        lib.linear_fwd(self.feat, self.head_w, self.head_b, self.codes.view(2 * self.B, -1))
+
+    def _fuse(self):
+        B = self.B
+        if self.fusion == "arithmetic":
+            lib.axpby(self.codes[:B], self.codes[B:], self.w, 0.5, 0.5)       # interpolation.py:661
+            self.syn.styles_from_wplus(self.w)
+        else:
+            self.syn.styles_from_wplus(self.codes, self.s_all)
+            lib.fuse_spatial_fwd(self.s_all[:B], self.s_all[B:], self.FP["alpha"], self.FP["beta"], self.FP["c"], self.syn.s)
+
+    def fused_forward(self) -> torch.Tensor:
+        """current x -> fused image (B,3,S,S) fp32 (buffer owned by the synthesis engine)."""
+        self._encode()
+        self._fuse()
+        return self.syn.forward()
+
+    def _vgg_forward_on_image(self, img):
+        lib.avgpool_affine_fwd(img, self.vgg_in, self.k_vgg, 1.0, 0.0)
+        self.vgg.forward(self.vgg_in)
+
+    def compute_reference(self, target: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """Reference = fusion of the clean pair (untargeted) or of `target` (targeted)."""
+        B = self.B
+        keep = self.x.clone()
+        if target is not None:
+            self.x[:B].copy_(target[0])
+            self.x[B:].copy_(target[1])
+        else:
+            self.x.copy_(self.x0)
+        img = self.fused_forward()
+        self.ref_img.copy_(img)
+        self._vgg_forward_on_image(img)
+        for r, t in zip(self.ref_feats, self.vgg.tap_outputs()):
+            r.copy_(t)
+        if self.loss_cfg.c_reg != 0.0:
+            self.x.copy_(self.x0)
+            lib.avgpool_affine_fwd(self.x, self.xin, self.k_in, 2.0, -1.0)
+            self.vgg_reg.forward(self.xin)
+            for r, t in zip(self.reg_refs, self.vgg_reg.tap_outputs()):
+                r.copy_(t)
+        self.x.copy_(keep)
+
+    def forward_backward(self):
+        """loss (B,) and the gradient w.r.t. the pooled, [-1,1]-mapped inputs g_xin (2B,3,R,R);
+        d loss / d x(full res, [0,1]) = (2/k^2) * g_xin[h/k][w/k]."""
+        B, cfg = self.B, self.loss_cfg
+        S = self.S
+        img = self.fused_forward()
+        self.loss.zero_()
+        # loss + its gradient w.r.t. the fused image
+        self._vgg_forward_on_image(img)
+        g_vin = self.vgg.backward(self.ref_feats, cfg.c_feat, self.loss) if cfg.c_feat != 0.0 else None
+        per = 3 * S * S
+        lib.image_loss_grad(img, self.ref_img, g_vin, self.g_img, self.loss, cfg.c_pix / per, 2.0 * cfg.c_pix / per, self.k_vgg)
+        # synthesis backward -> style gradient
+        gs = self.syn.backward(self.g_img)
+        # fusion backward -> latent gradients of both inputs
+        if self.fusion == "arithmetic":
+            self.syn.wplus_grad_from_styles(gs, self.gw)
+            lib.axpby(self.gw, None, self.gcodes[:B], 0.5)
+            lib.axpby(self.gw, None, self.gcodes[B:], 0.5)
+        else:
+            lib.fuse_spatial_bwd(self.s_all[:B], self.s_all[B:], self.FP["alpha"], self.FP["beta"], self.FP["c"], gs,
+                                 self.gs_all[:B], self.gs_all[B:])
+            self.syn.wplus_grad_from_styles(self.gs_all, self.gcodes)
+        # encoder backward
+        lib.linear_bwd(self.gcodes.view(2 * B, -1), self.head_w, self.gfeat)
+        lib.gap_bwd(self.enc.out[-1], self.gfeat, self.enc.g[-1])
+        g_xin = self.enc.backward(top_grad_ready=True)
+        if cfg.c_reg != 0.0:
+            # perceptual regulariser on the adversarial inputs themselves (config 5): L -= c_reg * sum_taps MSE
+            self.reg_loss.zero_()
+            self.vgg_reg.forward(self.xin)
+            g_reg = self.vgg_reg.backward(self.reg_refs, -cfg.c_reg, self.reg_loss)
+            lib.axpby(g_xin, g_reg, self.g_xin, 1.0, 1.0)
+            lib.axpby(self.reg_loss[:B], self.reg_loss[B:], self.reg_loss[:B], 1.0, 1.0)
+            lib.axpby(self.loss, self.reg_loss[:B], self.loss, 1.0, 1.0)
+        else:
+            self.g_xin.copy_(g_xin)
+        return self.loss, self.g_xin
+
+    def full_res_grad(self) -> torch.Tensor:
+        """d loss / d x at full resolution (2B,3,S,S) -- diagnostic / parity helper (not used by the loop)."""
+        k = self.k_in
+        g = self.g_xin.repeat_interleave(k, 2).repeat_interleave(k, 3) if k > 1 else self.g_xin.clone()
+        return g * (2.0 / (k * k))
+
+    # ---------------------------------------------------------------------------------------
+    def check(self):
+        torch.cuda.synchronize(self.dev)
+        if int(self.err.item()) != 0:
+            raise lib.SfkError("a tensor-core kernel reported an internal pipeline timeout")

@@ -39,6 +39,7 @@ class SfkIgemmDesc(C.Structure):
         ("dscale", C.c_void_p), ("bias", C.c_void_p), ("noise", C.c_void_p),
         ("noise_w", C.c_float),
         ("xin", C.c_void_p), ("colscale", C.c_void_p), ("gs", C.c_void_p),
+        ("vec_stride", C.c_int32),
         ("err", C.c_void_p),
         ("stages", C.c_int32),
     ]
@@ -85,7 +86,13 @@ def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+LAUNCHES = 0          # kernels of libsfattack launched since last reset (every entry point launches exactly one)
+_PROFILE = None       # when a list: igemm() appends (start_event, end_event, flops)
+
+
 def _chk(rc: int, what: str):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         raise SfkError(f"{what} failed rc={rc}: {load().sfk_last_error_string().decode()}")
 
@@ -97,7 +104,7 @@ def _f(v) -> C.c_float:
 # ------------------------------------------------------------------------------------------------
 def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out, out_h, out_w, out_c, num_acc, block_n,
                     taps: Sequence[tuple], flags=0, dscale=None, bias=None, noise=None, noise_w=0.0, xin=None,
-                    colscale=None, gs=None, err=None, stages=0) -> SfkIgemmDesc:
+                    colscale=None, gs=None, err=None, stages=0, vec_stride=0, vec_off=0) -> SfkIgemmDesc:
     d = SfkIgemmDesc()
     d.a, d.n_img, d.a_h, d.a_w, d.a_c, d.a_planes = _p(a), n_img, a_h, a_w, a_c, a_planes
     d.b, d.b_samples, d.b_rows = _p(b), b_samples, b_rows
@@ -108,15 +115,42 @@ def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out
         d.taps[i] = SfkTap(dy, dx, plane, acc, brow)
     d.flags = flags
     d.dscale, d.bias, d.noise, d.noise_w = _p(dscale), _p(bias), _p(noise), float(noise_w)
-    d.xin, d.colscale, d.gs, d.err, d.stages = _p(xin), _p(colscale), _p(gs), _p(err), stages
+    d.xin, d.err, d.stages, d.vec_stride = _p(xin), _p(err), stages, vec_stride
+    d.colscale = _sub(colscale, vec_off) if colscale is not None else C.c_void_p(0)
+    d.gs = _sub(gs, vec_off) if gs is not None else C.c_void_p(0)
     # keep the tensors alive as long as the descriptor
     d._keep = (a, b, out, dscale, bias, noise, xin, colscale, gs, err)
     return d
 
 
+def igemm_flops(d: SfkIgemmDesc) -> float:
+    """algorithmic FLOPs of one launch: every tap is an (out_c x a_c) MAC block per output position"""
+    return 2.0 * d.n_img * d.out_h * d.out_w * d.num_taps * d.out_c * d.a_c
+
+
 def igemm(desc: SfkIgemmDesc, ref: bool = False):
     fn = load().sfk_igemm_ref if ref else load().sfk_igemm
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _chk(fn(C.byref(desc), _stream()), "sfk_igemm")
+        e1.record()
+        _PROFILE.append((e0, e1, igemm_flops(desc), (desc.n_img, desc.out_h, desc.out_w, desc.a_c, desc.out_c, desc.num_taps, desc.num_acc)))
+        return
     _chk(fn(C.byref(desc), _stream()), "sfk_igemm_ref" if ref else "sfk_igemm")
+
+
+def profile_igemm(step_fn) -> dict:
+    """Run step_fn once with a CUDA-event pair around every tensor-core conv launch (on the launching stream)."""
+    global _PROFILE
+    _PROFILE = []
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+        recs = [(a.elapsed_time(b), f, shp) for a, b, f, shp in _PROFILE]
+    finally:
+        _PROFILE = None
+    return dict(ms=sum(r[0] for r in recs), flops=sum(r[1] for r in recs), launches=len(recs), per_launch=recs)
 
 
 def conv3x3_taps(cout: int):

@@ -81,6 +81,7 @@ typedef struct {
   const void* xin;           /* bf16 [n_img][out_h][out_w][out_c] */
   const float* colscale;     /* [n_img][out_c] */
   float* gs;                 /* [n_img][out_c] */
+  int32_t vec_stride;        /* row stride (floats) of colscale and gs; 0 = out_c */
   int32_t* err;              /* device int, set non-zero on an internal timeout */
   int32_t stages;            /* 0 = auto */
 } sfk_igemm_desc;
