@@ -22,29 +22,38 @@ int sfk_check_launch(const char* what);
 
 static inline bool sfk_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// ---- bf16 x8 vectors (16 bytes) -------------------------------------------------------------
-struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
-};
+// ---- bf16 x8 vectors (16 bytes) --------------------------------------------------------------
+// Carried as uint4 so that every access is ONE 128-bit LDG/STG (a struct of four bfloat162 gets scalarised
+// into four 32-bit accesses by nvcc); bf16 <-> fp32 is a 16-bit shift.
+typedef uint4 bf16x8;
 
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  f[0] = __uint_as_float(p.x << 16);
+  f[1] = __uint_as_float(p.x & 0xffff0000u);
+  f[2] = __uint_as_float(p.y << 16);
+  f[3] = __uint_as_float(p.y & 0xffff0000u);
+  f[4] = __uint_as_float(p.z << 16);
+  f[5] = __uint_as_float(p.z & 0xffff0000u);
+  f[6] = __uint_as_float(p.w << 16);
+  f[7] = __uint_as_float(p.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  p.x = pack2(f[0], f[1]);
+  p.y = pack2(f[2], f[3]);
+  p.z = pack2(f[4], f[5]);
+  p.w = pack2(f[6], f[7]);
   return p;
 }
-__device__ __forceinline__ bf16x8 ldg8(const void* p) {
-  return *reinterpret_cast<const bf16x8*>(p);
-}
-__device__ __forceinline__ void stg8(void* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+// read-only (non-coherent) 128-bit load: only for buffers this kernel never writes
+__device__ __forceinline__ bf16x8 ldg8(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// plain 128-bit load: for buffers updated in place by the same kernel
+__device__ __forceinline__ bf16x8 ld8(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg8(void* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = v; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -306,7 +306,7 @@ __global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restric
     unpack8(ldg8(f + base + v * 8), a);
     unpack8(ldg8(ref + base + v * 8), r);
     float o[8];
-    if (g && accumulate) unpack8(ldg8(g + base + v * 8), o);
+    if (g && accumulate) unpack8(ld8(g + base + v * 8), o);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float d = a[q] - r[q];
@@ -410,18 +410,29 @@ __global__ void demod_fwd_kernel(const float* __restrict__ s, int s_stride, cons
   }
 }
 
+// block = 32 input channels x 8 slices of the output-channel sum; Q rows are read coalesced along i
 __global__ void demod_bwd_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ Q, const float* __restrict__ d,
                                  const float* __restrict__ gdacc, float* __restrict__ gs, int gs_stride, int N, int Cin, int Cout) {
-  const int total = N * Cin;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int i = idx % Cin, n = idx / Cin;
-    float acc = 0.f;
-    for (int j = 0; j < Cout; ++j) {
-      const float dj = d[n * Cout + j];
-      acc = fmaf(gdacc[n * Cout + j] * dj * dj, __ldg(Q + static_cast<long>(j) * Cin + i), acc);
+  __shared__ float red[8][33];
+  const int n = blockIdx.y;
+  const int li = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + li;
+  float acc = 0.f;
+  if (i < Cin) {
+    for (int j = sl; j < Cout; j += 8) {
+      const float dj = __ldg(d + n * Cout + j);
+      acc = fmaf(__ldg(gdacc + n * Cout + j) * dj * dj, __ldg(Q + static_cast<long>(j) * Cin + i), acc);
     }
-    gs[static_cast<long>(n) * gs_stride + i] -= __ldg(s + static_cast<long>(n) * s_stride + i) * acc;
   }
+  red[sl][li] = acc;
+  __syncthreads();
+  if (sl == 0 && i < Cin) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][li];
+    gs[static_cast<long>(n) * gs_stride + i] -= __ldg(s + static_cast<long>(n) * s_stride + i) * t;
+  }
+  (void)N;
 }
 
 __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const float* __restrict__ s, int s_stride, bf16* __restrict__ wmod,
@@ -572,7 +583,7 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restr
     const long off = base + p * C + cv * 8;
     float ov[8], gv[8], o[8];
     unpack8(ldg8(out + off), ov);
-    unpack8(ldg8(gout + off), gv);
+    unpack8(ld8(gout + off), gv);   // gz may alias gout (in-place)
     const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -739,14 +750,32 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
-__global__ void linear_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx, int N, int In, int Out) {
-  const int total = N * In;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int i = idx % In, n = idx / In;
-    float acc = 0.f;
-    for (int o = 0; o < Out; ++o) acc = fmaf(__ldg(gy + static_cast<long>(n) * Out + o), __ldg(Wt + static_cast<long>(o) * In + i), acc);
-    gx[idx] = acc;
+// split over the output dimension: block (x = chunk of 256 inputs, y = slice of outputs) reads its W rows ONCE and
+// serves every sample from registers; partial sums are merged with atomics (gx is zeroed by the launcher).
+__global__ void linear_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx, int N, int In, int Out,
+                                  int o_per_slice) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o0 = blockIdx.y * o_per_slice;
+  const int o1 = min(Out, o0 + o_per_slice);
+  if (i >= In) return;
+  for (int nb = 0; nb < N; nb += 16) {
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.f;
+    for (int o = o0; o < o1; ++o) {
+      const float wv = __ldg(Wt + static_cast<long>(o) * In + i);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (nb + q < N) acc[q] = fmaf(__ldg(gy + static_cast<long>(nb + q) * Out + o), wv, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (nb + q < N) atomicAdd(gx + static_cast<long>(nb + q) * In + i, acc[q]);
   }
+}
+
+__global__ void zero_kernel(float* p, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) p[i] = 0.f;
 }
 
 __global__ void fuse_spatial_fwd_kernel(const float* sa, const float* sb, const float* al, const float* be, const float* c, float* s, int N, int D) {
@@ -1046,7 +1075,7 @@ int sfk_demod_fwd(const float* sv, int s_stride, const float* Q, float* d, int n
 int sfk_demod_bwd(const float* sv, int s_stride, const float* Q, const float* d, const float* gdacc, float* gs, int gs_stride, int n, int cin,
                   int cout, sfk_stream_t st) {
   SFK_REQUIRE(sv && Q && d && gdacc && gs, SFK_E_ARG, "demod_bwd: null");
-  demod_bwd_kernel<<<grid_for(static_cast<long>(n) * cin), kBlock, 0, S_(st)>>>(sv, s_stride, Q, d, gdacc, gs, gs_stride, n, cin, cout);
+  demod_bwd_kernel<<<dim3((cin + 31) / 32, n), 256, 0, S_(st)>>>(sv, s_stride, Q, d, gdacc, gs, gs_stride, n, cin, cout);
   return sfk_check_launch("demod_bwd");
 }
 
@@ -1114,7 +1143,11 @@ int sfk_linear_fwd(const float* x, const float* W, const float* bias, float* y, 
 
 int sfk_linear_bwd(const float* gy, const float* W, float* gx, int n, int in, int out, sfk_stream_t st) {
   SFK_REQUIRE(gy && W && gx, SFK_E_ARG, "linear_bwd: null");
-  linear_bwd_kernel<<<grid_for(static_cast<long>(n) * in), kBlock, 0, S_(st)>>>(gy, W, gx, n, in, out);
+  zero_kernel<<<grid_for(static_cast<long>(n) * in), kBlock, 0, S_(st)>>>(gx, static_cast<long>(n) * in);
+  int slices = out >= 64 ? 64 : 1;
+  const int per = (out + slices - 1) / slices;
+  slices = (out + per - 1) / per;
+  linear_bwd_kernel<<<dim3((in + 127) / 128, slices), 128, 0, S_(st)>>>(gy, W, gx, n, in, out, per);
   return sfk_check_launch("linear_bwd");
 }
 

@@ -209,8 +209,8 @@ __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h,
   if (valid) {
     if (flags & SFK_EP_ACCUM) {
       float o[16];
-      unpack8(ldg8(a.out + off), o);
-      unpack8(ldg8(a.out + off + 8), o + 8);
+      unpack8(ld8(a.out + off), o);
+      unpack8(ld8(a.out + off + 8), o + 8);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += o[i];
     }
@@ -357,6 +357,283 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc_kernel(const __grid_cons
   }
 }
 
+// =============================================================================================
+// Persistent variant (the default): each CTA owns one (image, N-block) and walks its output tiles.
+//   * the TMA/MMA pipeline runs across tile boundaries and the accumulator is double-buffered in TMEM,
+//     so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * filter taps that differ only in dy share ONE activation load: the box is TH+span rows tall and a
+//     tap's operand is the same smem tile entered (dy-dy_min)*TW rows further down (TW is a multiple of
+//     8 rows, so the swizzle phase is preserved) -- 3 loads instead of 9 for a 3x3 conv;
+//   * small weight sets (<= 72 KB for this CTA's N-block) are loaded once and stay resident in smem;
+//   * per-column epilogue vectors are staged in smem once per CTA; the style-gradient partial sums
+//     are accumulated in smem over all tiles and flushed with block_n atomics per CTA.
+constexpr int kMaxGroups = 9;
+constexpr int kMaxGroupTaps = 6;
+
+struct KGroup {
+  int plane, dx, dy_min, span, ntaps;
+  int dy_off[kMaxGroupTaps], acc[kMaxGroupTaps], brow[kMaxGroupTaps], first[kMaxGroupTaps], bidx[kMaxGroupTaps];
+};
+
+struct __align__(64) Igemm2Args {
+  CUtensorMap mapA[3];  // box height TH + span, span = 0,1,2
+  CUtensorMap mapB;
+  int n_img, out_h, out_w, out_c;
+  int TH, TW, tiles_h, tiles_w, n_blocks;
+  int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
+  int b_per_sample, b_resident;
+  int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
+  int layout_type, sbo_bytes, tmem_cols, flags, vec_stride;
+  float noise_w;
+  __nv_bfloat16* out;
+  const float* dscale;
+  const float* bias;
+  const float* noise;
+  const __nv_bfloat16* xin;
+  const float* colscale;
+  float* gs;
+  int* err;
+  KGroup groups[kMaxGroups];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_constant__ Igemm2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t bres_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float gs_acc[256];
+  __shared__ float col_dscale[256], col_bias[256], col_scale[256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + a.stages * a.a_stage_bytes;  // per-stage B tiles, or the resident weight set
+
+  const int grp = blockIdx.y;  // (image, N-block)
+  const int n = grp / a.n_blocks;
+  const int n0 = (grp % a.n_blocks) * a.block_n;
+  const int tiles_per_group = a.tiles_h * a.tiles_w;
+  const int bs = a.b_per_sample ? n : 0;
+
+  gs_acc[threadIdx.x] = 0.f;
+  if (threadIdx.x < a.block_n) {
+    const int c = n0 + threadIdx.x;
+    col_dscale[threadIdx.x] = (a.flags & SFK_EP_DSCALE) ? a.dscale[static_cast<long>(n) * a.out_c + c] : 1.f;
+    col_bias[threadIdx.x] = (a.flags & SFK_EP_BIAS) ? a.bias[c] : 0.f;
+    col_scale[threadIdx.x] = (a.flags & SFK_EP_COLSCALE) ? a.colscale[static_cast<long>(n) * a.vec_stride + c] : 1.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA[0])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA[2])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    mbar_init(&bres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(static_cast<uint32_t>(a.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      bool ok = true;
+      if (a.b_resident) {
+        mbar_expect_tx(&bres_bar, static_cast<uint32_t>(a.num_cblk * a.num_taps * a.block_n * a.row_bytes));
+        for (int cb = 0; cb < a.num_cblk; ++cb)
+          for (int g = 0; g < a.num_groups; ++g)
+            for (int j = 0; j < a.groups[g].ntaps; ++j)
+              tma_load_3d(smem_b + (cb * a.num_taps + a.groups[g].bidx[j]) * a.b_tap_bytes, &a.mapB, &bres_bar, cb * a.KC,
+                          a.groups[g].brow[j] + n0, bs);
+      }
+      int ks = 0;
+      for (int tile = blockIdx.x; tile < tiles_per_group && ok; tile += gridDim.x) {
+        const int h0 = (tile / a.tiles_w) * a.TH, w0 = (tile % a.tiles_w) * a.TW;
+        for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
+          for (int g = 0; g < a.num_groups; ++g, ++ks) {
+            const KGroup& G = a.groups[g];
+            const int stage = ks % a.stages;
+            const uint32_t phase = (ks / a.stages) & 1;
+            if (!mbar_wait(&empty_bar[stage], phase ^ 1, a.err)) {
+              ok = false;
+              break;
+            }
+            uint32_t bytes = static_cast<uint32_t>((a.TH + G.span) * a.TW * a.row_bytes);
+            if (!a.b_resident) bytes += static_cast<uint32_t>(G.ntaps * a.block_n * a.row_bytes);
+            mbar_expect_tx(&full_bar[stage], bytes);
+            tma_load_5d(smem_a + stage * a.a_stage_bytes, &a.mapA[G.span], &full_bar[stage], cb * a.KC, w0 + G.dx, h0 + G.dy_min,
+                        G.plane, n);
+            if (!a.b_resident) {
+              for (int j = 0; j < G.ntaps; ++j)
+                tma_load_3d(smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes, &a.mapB, &full_bar[stage], cb * a.KC,
+                            G.brow[j] + n0, bs);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a.block_n >> 3) << 17) |
+                             (static_cast<uint32_t>(128 >> 4) << 24);
+      const int kslices = a.KC / 16;
+      bool ok = true;
+      if (a.b_resident) ok = mbar_wait(&bres_bar, 0, a.err);
+      int ks = 0, it = 0;
+      for (int tile = blockIdx.x; tile < tiles_per_group && ok; tile += gridDim.x, ++it) {
+        const int as = it % a.acc_stages;
+        const uint32_t aph = (it / a.acc_stages) & 1;
+        if (!mbar_wait(&tmem_empty_bar[as], aph ^ 1, a.err)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * a.num_acc * a.block_n);
+        for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
+          for (int g = 0; g < a.num_groups; ++g, ++ks) {
+            const KGroup& G = a.groups[g];
+            const int stage = ks % a.stages;
+            const uint32_t phase = (ks / a.stages) & 1;
+            if (!mbar_wait(&full_bar[stage], phase, a.err)) {
+              ok = false;
+              break;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_base = smem_a + stage * a.a_stage_bytes;
+            for (int j = 0; j < G.ntaps; ++j) {
+              const uint64_t adesc = make_smem_desc(a_base + G.dy_off[j] * a.TW * a.row_bytes, a.sbo_bytes, a.layout_type);
+              const uint32_t b_addr = a.b_resident ? smem_b + (cb * a.num_taps + G.bidx[j]) * a.b_tap_bytes
+                                                   : smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes;
+              const uint64_t bdesc = make_smem_desc(b_addr, a.sbo_bytes, a.layout_type);
+              const uint32_t tmem_c = tmem_tile + static_cast<uint32_t>(G.acc[j] * a.block_n);
+              for (int k = 0; k < kslices; ++k) {
+                const uint32_t accum = (cb == 0 && G.first[j] && k == 0) ? 0u : 1u;
+                umma_bf16(tmem_c, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accum);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+          }
+        }
+        umma_commit(&tmem_full_bar[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int th = row / a.TW, tw = row % a.TW;
+    const int chunks = a.block_n / 16;
+    const int mycol = colsum16_column(lane);
+    const int flags = a.flags;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles_per_group; tile += gridDim.x, ++it) {
+      const int as = it % a.acc_stages;
+      const uint32_t aph = (it / a.acc_stages) & 1;
+      const int h = (tile / a.tiles_w) * a.TH + th, w = (tile % a.tiles_w) * a.TW + tw;
+      bool valid = (h < a.out_h) && (w < a.out_w);
+      // issue the per-pixel loads before blocking on the accumulator
+      const float nz = ((flags & SFK_EP_NOISE) && valid) ? a.noise_w * __ldg(a.noise + static_cast<long>(h) * a.out_w + w) : 0.f;
+      const bool ok = mbar_wait(&tmem_full_bar[as], aph, a.err);
+      valid = valid && ok;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int acc = 0; acc < a.num_acc; ++acc) {
+        const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
+        for (int c = 0; c < chunks; ++c) {
+          float v[16];
+          const long off = pix * a.out_c + n0 + c * 16;
+          float x[16];
+          if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {   // start the activation load before the TMEM read completes
+            if (valid) {
+              unpack8(ldg8(a.xin + off), x);
+              unpack8(ldg8(a.xin + off + 8), x + 8);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = 0.f;
+            }
+          }
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>((as * a.num_acc + acc) * a.block_n + c * 16);
+          tmem_ld16(taddr, v);
+          const float* cd = col_dscale + c * 16;
+          const float* cb_ = col_bias + c * 16;
+          if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], cd[i], nz + cb_[i]);
+          }
+          if (flags & SFK_EP_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (flags & SFK_EP_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = lrelu_fwd(v[i]);
+          }
+          if (flags & SFK_EP_GSDOT) {
+            float gsd[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gsd[i] = x[i] * v[i];
+            const float tot = warp_colsum16(gsd, lane);
+            if (lane < 16) atomicAdd(&gs_acc[c * 16 + mycol], tot);
+          }
+          if (flags & SFK_EP_XMASK) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
+          }
+          if (flags & SFK_EP_COLSCALE) {
+            const float* cs = col_scale + c * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= cs[i];
+          }
+          if (valid) {
+            if (flags & SFK_EP_ACCUM) {
+              float o[16];
+              unpack8(ld8(a.out + off), o);
+              unpack8(ld8(a.out + off + 8), o + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += o[i];
+            }
+            stg8(a.out + off, pack8(v));
+            stg8(a.out + off + 8, pack8(v + 8));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (128 arrivals)
+    }
+  }
+  __syncthreads();
+  if ((a.flags & SFK_EP_GSDOT) && threadIdx.x < a.block_n) {
+    atomicAdd(a.gs + static_cast<long>(n) * a.vec_stride + n0 + threadIdx.x, gs_acc[threadIdx.x]);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(static_cast<uint32_t>(a.tmem_cols))
+                 : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CUDA-core cross-check with the identical contract (one thread = one position x 16 channels).
 struct RefArgs {
@@ -479,7 +756,7 @@ void fill_taps(const sfk_igemm_desc* d, KTap* taps) {
 
 }  // namespace
 
-extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
+extern "C" int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream) {
   int rc = validate(d);
   if (rc) return rc;
   EncodeTiledFn enc = get_encode_fn();
@@ -563,6 +840,146 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   dim3 grid(static_cast<unsigned>(k.tiles_w * k.tiles_h * d->n_img), static_cast<unsigned>(d->out_c / d->block_n));
   igemm_tc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(k);
   return sfk_check_launch("igemm_tc_kernel");
+}
+
+namespace {
+int encode_a_map(EncodeTiledFn enc, CUtensorMap* map, const sfk_igemm_desc* d, int KC, int TW, int rows, CUtensorMapSwizzle swz) {
+  cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_w, (cuuint64_t)d->a_h, (cuuint64_t)d->a_planes, (cuuint64_t)d->n_img};
+  cuuint64_t strides[4] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->a_w * d->a_c * 2, (cuuint64_t)d->a_h * d->a_w * d->a_c * 2,
+                           (cuuint64_t)d->a_planes * d->a_h * d->a_w * d->a_c * 2};
+  cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)rows, 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+}  // namespace
+
+extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode_fn();
+  SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+
+  static Igemm2Args k;   // large POD; sfk_igemm is not re-entrant across host threads (documented in sfk.h)
+  memset(&k, 0, sizeof(k));
+  const int KC = (d->a_c % 64 == 0) ? 64 : (d->a_c % 32 == 0 ? 32 : 16);
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  k.KC = KC;
+  k.num_cblk = d->a_c / KC;
+  k.row_bytes = KC * 2;
+  k.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
+  k.sbo_bytes = 8 * k.row_bytes;
+  k.TW = d->out_w > 8 ? 16 : (d->out_w > 4 ? 8 : 4);
+  k.TH = 128 / k.TW;
+  k.tiles_w = (d->out_w + k.TW - 1) / k.TW;
+  k.tiles_h = (d->out_h + k.TH - 1) / k.TH;
+  k.n_img = d->n_img; k.out_h = d->out_h; k.out_w = d->out_w; k.out_c = d->out_c;
+  k.block_n = d->block_n; k.num_acc = d->num_acc; k.num_taps = d->num_taps;
+  k.n_blocks = d->out_c / d->block_n;
+  k.b_per_sample = d->b_samples > 1 ? 1 : 0;
+  k.flags = d->flags;
+  k.vec_stride = d->vec_stride > 0 ? d->vec_stride : d->out_c;
+  k.noise_w = d->noise_w;
+  k.out = static_cast<__nv_bfloat16*>(d->out);
+  k.dscale = d->dscale; k.bias = d->bias; k.noise = d->noise;
+  k.xin = static_cast<const __nv_bfloat16*>(d->xin);
+  k.colscale = d->colscale; k.gs = d->gs; k.err = d->err;
+
+  // ---- group taps that differ only in dy (shared activation load)
+  const bool share = k.TW >= 8;
+  int ng = 0;
+  int dymin[kMaxGroups], dymax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps];
+  for (int t = 0; t < d->num_taps; ++t) {
+    const sfk_tap& tp = d->taps[t];
+    int g = -1;
+    if (share) {
+      for (int q = 0; q < ng; ++q) {
+        if (k.groups[q].plane == tp.plane && k.groups[q].dx == tp.dx && k.groups[q].ntaps < kMaxGroupTaps) {
+          const int lo = tp.dy < dymin[q] ? tp.dy : dymin[q], hi = tp.dy > dymax[q] ? tp.dy : dymax[q];
+          if (hi - lo <= 2) { g = q; break; }
+        }
+      }
+    }
+    if (g < 0) {
+      SFK_REQUIRE(ng < kMaxGroups, SFK_E_SHAPE, "igemm: too many tap groups");
+      g = ng++;
+      k.groups[g].plane = tp.plane; k.groups[g].dx = tp.dx; k.groups[g].ntaps = 0;
+      dymin[g] = tp.dy; dymax[g] = tp.dy;
+    }
+    KGroup& G = k.groups[g];
+    if (tp.dy < dymin[g]) dymin[g] = tp.dy;
+    if (tp.dy > dymax[g]) dymax[g] = tp.dy;
+    tdy[g][G.ntaps] = tp.dy;
+    G.acc[G.ntaps] = tp.acc; G.brow[G.ntaps] = tp.brow; G.bidx[G.ntaps] = t;
+    G.ntaps++;
+  }
+  k.num_groups = ng;
+  bool seen[32] = {false};
+  int max_span = 0, max_gt = 0;
+  for (int g = 0; g < ng; ++g) {
+    KGroup& G = k.groups[g];
+    G.dy_min = dymin[g];
+    G.span = dymax[g] - dymin[g];
+    if (G.span > max_span) max_span = G.span;
+    if (G.ntaps > max_gt) max_gt = G.ntaps;
+    for (int j = 0; j < G.ntaps; ++j) {
+      G.dy_off[j] = tdy[g][j] - dymin[g];
+      G.first[j] = seen[G.acc[j]] ? 0 : 1;
+      seen[G.acc[j]] = true;
+    }
+  }
+  // ---- shared memory plan
+  k.b_tap_bytes = ((d->block_n * k.row_bytes + 1023) / 1024) * 1024;
+  const int b_total = k.num_cblk * k.num_taps * k.b_tap_bytes;
+  k.b_resident = b_total <= 72 * 1024 ? 1 : 0;
+  k.a_stage_bytes = (((k.TH + max_span) * k.TW * k.row_bytes + 1023) / 1024) * 1024;
+  k.b_stage_bytes = k.b_resident ? 0 : max_gt * k.b_tap_bytes;
+  const int tiles_per_group = k.tiles_h * k.tiles_w;
+  const int groups_total = d->n_img * k.n_blocks;
+  const int sms = sfk_num_sms();
+  int ctas_per_group = (2 * sms) / groups_total;
+  if (ctas_per_group < 1) ctas_per_group = 1;
+  if (ctas_per_group > tiles_per_group) ctas_per_group = tiles_per_group;
+  const int total_ctas = ctas_per_group * groups_total;
+  const int cols = d->num_acc * d->block_n;
+  int per_sm = (total_ctas > sms && cols <= 256) ? 2 : 1;
+  const int stage_bytes = k.a_stage_bytes + k.b_stage_bytes;
+  const int resident = k.b_resident ? b_total : 0;
+  if (per_sm == 2 && (100 * 1024 - resident - 1024) / stage_bytes < 2) per_sm = 1;
+  const int budget = (per_sm == 2 ? 100 : 200) * 1024 - resident - 1024;
+  int stages = d->stages > 0 ? d->stages : budget / stage_bytes;
+  const int ksteps_per_cta = k.num_cblk * ng * ((tiles_per_group + ctas_per_group - 1) / ctas_per_group);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > ksteps_per_cta) stages = ksteps_per_cta;
+  SFK_REQUIRE(stages >= 1 && stages * stage_bytes + resident + 1024 <= 220 * 1024, SFK_E_SHAPE, "igemm: tile does not fit shared memory");
+  k.stages = stages;
+  k.acc_stages = (2 * cols <= (per_sm == 2 ? 256 : 512)) ? 2 : 1;
+  const int want = k.acc_stages * cols;
+  k.tmem_cols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
+
+  for (int sp = 0; sp <= max_span; ++sp)
+    SFK_REQUIRE(encode_a_map(enc, &k.mapA[sp], d, KC, k.TW, k.TH + sp, swz) == 0, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(A) failed");
+  for (int sp = max_span + 1; sp < 3; ++sp) k.mapA[sp] = k.mapA[0];
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->a_c, (cuuint64_t)d->b_rows, (cuuint64_t)d->b_samples};
+    cuuint64_t strides[2] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->b_rows * d->a_c * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)d->block_n, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&k.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->b), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(B) failed");
+  }
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + resident + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
+  igemm_tc2_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(k);
+  return sfk_check_launch("igemm_tc2_kernel");
 }
 
 extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {

@@ -47,7 +47,7 @@ class SfkIgemmDesc(C.Structure):
 
 # every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
+    "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd",
@@ -128,8 +128,8 @@ def igemm_flops(d: SfkIgemmDesc) -> float:
     return 2.0 * d.n_img * d.out_h * d.out_w * d.num_taps * d.out_c * d.a_c
 
 
-def igemm(desc: SfkIgemmDesc, ref: bool = False):
-    fn = load().sfk_igemm_ref if ref else load().sfk_igemm
+def igemm(desc: SfkIgemmDesc, ref: bool = False, v1: bool = False):
+    fn = load().sfk_igemm_ref if ref else (load().sfk_igemm_v1 if v1 else load().sfk_igemm)
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -86,7 +86,9 @@ typedef struct {
   int32_t stages;            /* 0 = auto */
 } sfk_igemm_desc;
 
-int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);
+int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);   /* persistent kernel; call from one host thread at a time */
+/* One-tile-per-CTA variant of the same contract (first implementation; kept for A/B timing and as a second cross-check). */
+int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream);
 /* Same contract on CUDA cores with plain loops: the on-device cross-check of the tensor-core path. */
 int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream);
 

@@ -52,6 +52,9 @@ def _conv_weights(w):  # (Cout,Cin,3,3) fp32 -> [9][Cout][Cin] bf16
     (1, 4, 4, 64, 32, False),       # TW=4, mostly out-of-bounds tile
     (2, 16, 16, 64, 256, True),     # per-sample weights, two N blocks
     (3, 33, 17, 64, 128, False),    # odd sizes
+    (2, 128, 128, 32, 32, True),    # many tiles per CTA, resident weights, double-buffered TMEM
+    (1, 96, 80, 64, 64, True),      # resident weights, SW128
+    (2, 64, 64, 256, 128, False),   # streamed weights, 4 channel blocks
 ])
 def test_igemm_conv3x3_fwd(n, h, w, cin, cout, per_sample):
     from sfattack import lib
@@ -64,11 +67,11 @@ def test_igemm_conv3x3_fwd(n, h, w, cin, cout, per_sample):
     xb = _nhwc(x)
     wb = torch.stack([_conv_weights(wt[s]) for s in range(S)]).contiguous()
     err = torch.zeros(1, dtype=torch.int32, device=_dev())
-    for use_ref in (True, False):
+    for use_ref in ("ref", "v1", "v2"):
         out = torch.full((n, h, w, cout), float("nan"), device=_dev(), dtype=torch.bfloat16)
         d = lib.make_igemm_desc(xb, n, h, w, cin, 1, wb, S, 9 * cout, out, h, w, cout, 1, lib.pick_block_n(cout),
                                 lib.conv3x3_taps(cout), flags=lib.EP_BIAS | lib.EP_RELU, bias=bias, err=err)
-        lib.igemm(d, ref=use_ref)
+        lib.igemm(d, ref=use_ref == "ref", v1=use_ref == "v1")
         torch.cuda.synchronize()
         assert err.item() == 0, "kernel reported an internal timeout"
         _close(_nchw(out), ref, what=f"igemm fwd ref={use_ref}")
@@ -88,14 +91,14 @@ def test_igemm_dgrad_flags():
     ref_gs = (xin * gxt).sum((2, 3))
     ref_out = prev + s[:, :, None, None] * gxt * (xin > 0)
     wT = wt.permute(2, 3, 1, 0).contiguous().reshape(9 * cin, cout).bfloat16()   # [tap][cin][cout]
-    for use_ref in (True, False):
+    for use_ref in ("ref", "v1", "v2"):
         out = _nhwc(prev).clone()
         gs = torch.zeros(n, cin, device=_dev())
         err = torch.zeros(1, dtype=torch.int32, device=_dev())
         d = lib.make_igemm_desc(_nhwc(gz), n, h, w, cout, 1, wT, 1, 9 * cin, out, h, w, cin, 1, lib.pick_block_n(cin),
                                 lib.conv3x3_dgrad_taps(cin), flags=lib.EP_XMASK | lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM,
                                 xin=_nhwc(xin), colscale=s, gs=gs, err=err)
-        lib.igemm(d, ref=use_ref)
+        lib.igemm(d, ref=use_ref == "ref", v1=use_ref == "v1")
         torch.cuda.synchronize()
         assert err.item() == 0
         _close(_nchw(out), ref_out, what=f"dgrad out ref={use_ref}")
