@@ -12,6 +12,7 @@
 // warps4-7 = epilogue (TMEM lanes 32*(warp%4)..).  Two CTAs fit per SM so one CTA's epilogue
 // overlaps the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "sfk_common.cuh"
 
@@ -69,17 +70,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: returns false (and raises *err) if the barrier never flips.
+// Bounded wait: returns false (and raises *err) if the barrier never flips.  The abort flag lives in global memory, so it
+// is polled only once per 64 failed probes (try_wait itself suspends the thread for a hardware time slice): a load in the
+// spin loop would add its full latency to every wake-up.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait(bar, parity)) return true;
     if (clock64() - t0 > kTimeoutCycles || (err && *reinterpret_cast<volatile int*>(err) != 0)) {
       if (err) atomicExch(err, 1);
       return false;
     }
   }
-  return true;
 }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -368,18 +373,21 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc_kernel(const __grid_cons
 //   * per-column epilogue vectors are staged in smem once per CTA; the style-gradient partial sums
 //     are accumulated in smem over all tiles and flushed with block_n atomics per CTA.
 constexpr int kMaxGroups = 9;
-constexpr int kMaxGroupTaps = 6;
+constexpr int kMaxGroupTaps = 9;
 
 struct KGroup {
-  int plane, dx, dy_min, span, ntaps;
-  int dy_off[kMaxGroupTaps], acc[kMaxGroupTaps], brow[kMaxGroupTaps], first[kMaxGroupTaps], bidx[kMaxGroupTaps];
+  int plane, dx_min, dy_min, map, bytes, ntaps;   // map: which activation tensor map (box height); bytes: box size
+  int roff[kMaxGroupTaps];                        // operand start, in smem rows, of each tap inside the loaded box
+  int acc[kMaxGroupTaps], brow[kMaxGroupTaps], first[kMaxGroupTaps], bidx[kMaxGroupTaps];
+  // host-precomputed issue constants, read straight into uniform registers by the MMA warp
+  int a16[kMaxGroupTaps], b16[kMaxGroupTaps], col[kMaxGroupTaps];
 };
 
 struct __align__(64) Igemm2Args {
-  CUtensorMap mapA[3];  // box height TH + span, span = 0,1,2
+  CUtensorMap mapA[4];  // box height TH + 0..3 rows
   CUtensorMap mapB;
   int n_img, out_h, out_w, out_c;
-  int TH, TW, tiles_h, tiles_w, n_blocks;
+  int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
   int b_per_sample, b_resident;
   int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
@@ -396,6 +404,18 @@ struct __align__(64) Igemm2Args {
   KGroup groups[kMaxGroups];
 };
 
+// role-level cycle accounting (only when SFK_EP_PROFILE is set): [0] producer waiting for a free slot, [1] producer total,
+// [2] MMA waiting for data, [3] MMA waiting for a free accumulator, [4] MMA total, [5] epilogue waiting for the accumulator,
+// [6] epilogue total, [7] tiles
+__device__ unsigned long long g_role_cycles[8];
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+#define SFK_EP_PROFILE (1 << 16)
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -410,6 +430,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   __shared__ uint32_t tmem_base_s;
   __shared__ float gs_acc[256];
   __shared__ float col_dscale[256], col_bias[256], col_scale[256];
+  __shared__ int4 s_tap[kMaxGroups * kMaxGroupTaps];   // per tap: {A offset>>4 (+phase), B offset>>4, TMEM column, first}
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -424,6 +445,18 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   const int bs = a.b_per_sample ? n : 0;
 
   gs_acc[threadIdx.x] = 0.f;
+  if (threadIdx.x < kMaxGroups * kMaxGroupTaps) {
+    const int g = threadIdx.x / kMaxGroupTaps, j = threadIdx.x % kMaxGroupTaps;
+    int4 t = make_int4(0, 0, 0, 0);
+    if (g < a.num_groups && j < a.groups[g].ntaps) {
+      const KGroup& G = a.groups[g];
+      t.x = (G.roff[j] * a.row_bytes) >> 4;
+      t.y = ((a.b_resident ? G.bidx[j] : j) * a.b_tap_bytes) >> 4;
+      t.z = G.acc[j] * a.block_n;
+      t.w = G.first[j];
+    }
+    s_tap[threadIdx.x] = t;
+  }
   if (threadIdx.x < a.block_n) {
     const int c = n0 + threadIdx.x;
     col_dscale[threadIdx.x] = (a.flags & SFK_EP_DSCALE) ? a.dscale[static_cast<long>(n) * a.out_c + c] : 1.f;
@@ -432,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA[0])) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA[2])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapA[a.groups[0].map])) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.mapB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
@@ -471,6 +504,9 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                           a.groups[g].brow[j] + n0, bs);
       }
       int ks = 0;
+      const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
+      long long t_wait = 0;
+      const long long t_start = clock64();
       for (int tile = blockIdx.x; tile < tiles_per_group && ok; tile += gridDim.x) {
         const int h0 = (tile / a.tiles_w) * a.TH, w0 = (tile % a.tiles_w) * a.TW;
         for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
@@ -478,14 +514,16 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             const KGroup& G = a.groups[g];
             const int stage = ks % a.stages;
             const uint32_t phase = (ks / a.stages) & 1;
+            const long long tw0 = prof ? clock64() : 0;
             if (!mbar_wait(&empty_bar[stage], phase ^ 1, a.err)) {
               ok = false;
               break;
             }
-            uint32_t bytes = static_cast<uint32_t>((a.TH + G.span) * a.TW * a.row_bytes);
+            if (prof) t_wait += clock64() - tw0;
+            uint32_t bytes = static_cast<uint32_t>(G.bytes);
             if (!a.b_resident) bytes += static_cast<uint32_t>(G.ntaps * a.block_n * a.row_bytes);
             mbar_expect_tx(&full_bar[stage], bytes);
-            tma_load_5d(smem_a + stage * a.a_stage_bytes, &a.mapA[G.span], &full_bar[stage], cb * a.KC, w0 + G.dx, h0 + G.dy_min,
+            tma_load_5d(smem_a + stage * a.a_stage_bytes, &a.mapA[G.map], &full_bar[stage], cb * a.KC, w0 + G.dx_min, h0 + G.dy_min,
                         G.plane, n);
             if (!a.b_resident) {
               for (int j = 0; j < G.ntaps; ++j)
@@ -495,20 +533,32 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           }
         }
       }
+      if (prof) {
+        atomicAdd(&g_role_cycles[1], static_cast<unsigned long long>(clock64() - t_start));
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop convergently (so descriptors live in uniform registers without vote loops);
+    // one elected lane issues tcgen05.mma / tcgen05.commit.
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a.block_n >> 3) << 17) |
                              (static_cast<uint32_t>(128 >> 4) << 24);
       const int kslices = a.KC / 16;
+      const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
+      long long t_wd = 0, t_wa = 0, t_issue = 0;
+      const long long t_start = clock64();
+      const uint64_t desc_hi = make_smem_desc(0, a.sbo_bytes, a.layout_type);   // everything but the start address
       bool ok = true;
       if (a.b_resident) ok = mbar_wait(&bres_bar, 0, a.err);
       int ks = 0, it = 0;
       for (int tile = blockIdx.x; tile < tiles_per_group && ok; tile += gridDim.x, ++it) {
         const int as = it % a.acc_stages;
         const uint32_t aph = (it / a.acc_stages) & 1;
+        const long long ta0 = prof ? clock64() : 0;
         if (!mbar_wait(&tmem_empty_bar[as], aph ^ 1, a.err)) break;
+        if (prof) t_wa += clock64() - ta0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * a.num_acc * a.block_n);
         for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
@@ -516,46 +566,66 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             const KGroup& G = a.groups[g];
             const int stage = ks % a.stages;
             const uint32_t phase = (ks / a.stages) & 1;
+            const long long td0 = prof ? clock64() : 0;
             if (!mbar_wait(&full_bar[stage], phase, a.err)) {
               ok = false;
               break;
             }
+            if (prof) t_wd += clock64() - td0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_base = smem_a + stage * a.a_stage_bytes;
-            for (int j = 0; j < G.ntaps; ++j) {
-              const uint64_t adesc = make_smem_desc(a_base + G.dy_off[j] * a.TW * a.row_bytes, a.sbo_bytes, a.layout_type);
-              const uint32_t b_addr = a.b_resident ? smem_b + (cb * a.num_taps + G.bidx[j]) * a.b_tap_bytes
-                                                   : smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes;
-              const uint64_t bdesc = make_smem_desc(b_addr, a.sbo_bytes, a.layout_type);
-              const uint32_t tmem_c = tmem_tile + static_cast<uint32_t>(G.acc[j] * a.block_n);
-              for (int k = 0; k < kslices; ++k) {
-                const uint32_t accum = (cb == 0 && G.first[j] && k == 0) ? 0u : 1u;
-                umma_bf16(tmem_c, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, accum);
+            // everything tap-specific was folded into s_tap once per CTA: ~10 instructions per MMA issued
+            const uint32_t a_lo = (smem_a + stage * a.a_stage_bytes) >> 4;
+            const uint32_t b_lo = (a.b_resident ? smem_b + cb * a.num_taps * a.b_tap_bytes : smem_b + stage * a.b_stage_bytes) >> 4;
+            const int nt = G.ntaps;
+            for (int j = 0; j < nt; ++j) {
+              const uint64_t adesc = desc_hi | static_cast<uint64_t>(a_lo + static_cast<uint32_t>(G.a16[j]));
+              const uint64_t bdesc = desc_hi | static_cast<uint64_t>(b_lo + static_cast<uint32_t>(G.b16[j]));
+              const uint32_t tmem_c = tmem_tile + static_cast<uint32_t>(G.col[j]);
+              const long long ti0 = prof ? clock64() : 0;
+              if (leader) {
+                umma_bf16(tmem_c, adesc, bdesc, idesc, (cb == 0 && G.first[j]) ? 0u : 1u);
+#pragma unroll
+                for (int k = 1; k < 4; ++k)
+                  if (k < kslices) umma_bf16(tmem_c, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, 1u);
               }
+              if (prof) t_issue += clock64() - ti0;
             }
-            umma_commit(&empty_bar[stage]);
+            __syncwarp();
+            if (leader) umma_commit(&empty_bar[stage]);
           }
         }
-        umma_commit(&tmem_full_bar[as]);
+        __syncwarp();
+        if (leader) umma_commit(&tmem_full_bar[as]);
+      }
+      if (prof && leader) {
+        atomicAdd(&g_role_cycles[2], static_cast<unsigned long long>(t_wd));
+        atomicAdd(&g_role_cycles[3], static_cast<unsigned long long>(t_wa));
+        atomicAdd(&g_role_cycles[0], static_cast<unsigned long long>(t_issue));   // (slot 0 doubles as MMA-issue time; producer wait = [1]-busy)
+        atomicAdd(&g_role_cycles[4], static_cast<unsigned long long>(clock64() - t_start));
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int th = row / a.TW, tw = row % a.TW;
+    const int th = row / a.TWB, tw = row % a.TWB;
     const int chunks = a.block_n / 16;
     const int mycol = colsum16_column(lane);
     const int flags = a.flags;
+    const bool prof = (flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
+    long long t_we = 0;
+    const long long t_start = clock64();
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles_per_group; tile += gridDim.x, ++it) {
       const int as = it % a.acc_stages;
       const uint32_t aph = (it / a.acc_stages) & 1;
       const int h = (tile / a.tiles_w) * a.TH + th, w = (tile % a.tiles_w) * a.TW + tw;
-      bool valid = (h < a.out_h) && (w < a.out_w);
+      bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
       // issue the per-pixel loads before blocking on the accumulator
       const float nz = ((flags & SFK_EP_NOISE) && valid) ? a.noise_w * __ldg(a.noise + static_cast<long>(h) * a.out_w + w) : 0.f;
+      const long long te0 = prof ? clock64() : 0;
       const bool ok = mbar_wait(&tmem_full_bar[as], aph, a.err);
+      if (prof) t_we += clock64() - te0;
       valid = valid && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int acc = 0; acc < a.num_acc; ++acc) {
@@ -621,6 +691,11 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (128 arrivals)
+    }
+    if (prof) {
+      atomicAdd(&g_role_cycles[5], static_cast<unsigned long long>(t_we));
+      atomicAdd(&g_role_cycles[6], static_cast<unsigned long long>(clock64() - t_start));
+      atomicAdd(&g_role_cycles[7], static_cast<unsigned long long>(it));
     }
   }
   __syncthreads();
@@ -886,54 +961,78 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   k.xin = static_cast<const __nv_bfloat16*>(d->xin);
   k.colscale = d->colscale; k.gs = d->gs; k.err = d->err;
 
-  // ---- group taps that differ only in dy (shared activation load)
+  // ---- group taps that can share ONE activation load
+  //   halo mode (row pitch 16): all taps of a plane whose shifts span <= 2 in x and y read one (TH+span_y[+1]) x 16 box;
+  //                             a tap enters it dy*16+dx rows down; the tile keeps TW = 16 - span_x useful columns
+  //   dy mode (otherwise):      taps that differ only in dy share a box TH+span rows tall (row offsets are multiples of 8)
+  static int halo_env = -1;
+  if (halo_env < 0) { const char* e = getenv("SFK_HALO"); halo_env = e ? atoi(e) : 0; }   // experimental, off: results differ
+  const bool halo = halo_env && k.TW == 16;
   const bool share = k.TW >= 8;
   int ng = 0;
-  int dymin[kMaxGroups], dymax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps];
+  int dymin[kMaxGroups], dymax[kMaxGroups], dxmin[kMaxGroups], dxmax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps], tdx[kMaxGroups][kMaxGroupTaps];
   for (int t = 0; t < d->num_taps; ++t) {
     const sfk_tap& tp = d->taps[t];
     int g = -1;
     if (share) {
       for (int q = 0; q < ng; ++q) {
-        if (k.groups[q].plane == tp.plane && k.groups[q].dx == tp.dx && k.groups[q].ntaps < kMaxGroupTaps) {
-          const int lo = tp.dy < dymin[q] ? tp.dy : dymin[q], hi = tp.dy > dymax[q] ? tp.dy : dymax[q];
-          if (hi - lo <= 2) { g = q; break; }
-        }
+        if (k.groups[q].plane != tp.plane || k.groups[q].ntaps >= kMaxGroupTaps) continue;
+        if (!halo && dxmin[q] != tp.dx) continue;
+        const int lo = tp.dy < dymin[q] ? tp.dy : dymin[q], hi = tp.dy > dymax[q] ? tp.dy : dymax[q];
+        const int xlo = tp.dx < dxmin[q] ? tp.dx : dxmin[q], xhi = tp.dx > dxmax[q] ? tp.dx : dxmax[q];
+        if (hi - lo <= 2 && xhi - xlo <= 2) { g = q; break; }
       }
     }
     if (g < 0) {
       SFK_REQUIRE(ng < kMaxGroups, SFK_E_SHAPE, "igemm: too many tap groups");
       g = ng++;
-      k.groups[g].plane = tp.plane; k.groups[g].dx = tp.dx; k.groups[g].ntaps = 0;
-      dymin[g] = tp.dy; dymax[g] = tp.dy;
+      k.groups[g].plane = tp.plane; k.groups[g].ntaps = 0;
+      dymin[g] = dymax[g] = tp.dy; dxmin[g] = dxmax[g] = tp.dx;
     }
     KGroup& G = k.groups[g];
     if (tp.dy < dymin[g]) dymin[g] = tp.dy;
     if (tp.dy > dymax[g]) dymax[g] = tp.dy;
-    tdy[g][G.ntaps] = tp.dy;
+    if (tp.dx < dxmin[g]) dxmin[g] = tp.dx;
+    if (tp.dx > dxmax[g]) dxmax[g] = tp.dx;
+    tdy[g][G.ntaps] = tp.dy; tdx[g][G.ntaps] = tp.dx;
     G.acc[G.ntaps] = tp.acc; G.brow[G.ntaps] = tp.brow; G.bidx[G.ntaps] = t;
     G.ntaps++;
   }
   k.num_groups = ng;
+  int max_xspan = 0;
+  for (int g = 0; g < ng; ++g) if (dxmax[g] - dxmin[g] > max_xspan) max_xspan = dxmax[g] - dxmin[g];
+  k.TWB = k.TW;
+  k.TW = k.TWB - max_xspan;                      // useful columns per tile row
+  k.tiles_w = (d->out_w + k.TW - 1) / k.TW;
   bool seen[32] = {false};
-  int max_span = 0, max_gt = 0;
+  int max_rows_extra = 0, max_gt = 0;
   for (int g = 0; g < ng; ++g) {
     KGroup& G = k.groups[g];
     G.dy_min = dymin[g];
-    G.span = dymax[g] - dymin[g];
-    if (G.span > max_span) max_span = G.span;
+    G.dx_min = dxmin[g];
+    const int extra = (dymax[g] - dymin[g]) + ((dxmax[g] - dxmin[g]) > 0 ? 1 : 0);   // +1 row: the M index runs past the last row
+    G.map = extra;
+    G.bytes = (k.TH + extra) * k.TWB * k.row_bytes;
+    if (extra > max_rows_extra) max_rows_extra = extra;
     if (G.ntaps > max_gt) max_gt = G.ntaps;
     for (int j = 0; j < G.ntaps; ++j) {
-      G.dy_off[j] = tdy[g][j] - dymin[g];
+      G.roff[j] = (tdy[g][j] - dymin[g]) * k.TWB + (tdx[g][j] - dxmin[g]);
       G.first[j] = seen[G.acc[j]] ? 0 : 1;
       seen[G.acc[j]] = true;
     }
   }
+  const int max_span = max_rows_extra;
   // ---- shared memory plan
   k.b_tap_bytes = ((d->block_n * k.row_bytes + 1023) / 1024) * 1024;
   const int b_total = k.num_cblk * k.num_taps * k.b_tap_bytes;
   k.b_resident = b_total <= 72 * 1024 ? 1 : 0;
-  k.a_stage_bytes = (((k.TH + max_span) * k.TW * k.row_bytes + 1023) / 1024) * 1024;
+  for (int g = 0; g < ng; ++g)
+    for (int j = 0; j < k.groups[g].ntaps; ++j) {
+      k.groups[g].a16[j] = (k.groups[g].roff[j] * k.row_bytes) >> 4;
+      k.groups[g].b16[j] = ((k.b_resident ? k.groups[g].bidx[j] : j) * k.b_tap_bytes) >> 4;
+      k.groups[g].col[j] = k.groups[g].acc[j] * d->block_n;
+    }
+  k.a_stage_bytes = (((k.TH + max_span) * k.TWB * k.row_bytes + 1023) / 1024) * 1024;
   k.b_stage_bytes = k.b_resident ? 0 : max_gt * k.b_tap_bytes;
   const int tiles_per_group = k.tiles_h * k.tiles_w;
   const int groups_total = d->n_img * k.n_blocks;
@@ -959,8 +1058,8 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   k.tmem_cols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
 
   for (int sp = 0; sp <= max_span; ++sp)
-    SFK_REQUIRE(encode_a_map(enc, &k.mapA[sp], d, KC, k.TW, k.TH + sp, swz) == 0, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(A) failed");
-  for (int sp = max_span + 1; sp < 3; ++sp) k.mapA[sp] = k.mapA[0];
+    SFK_REQUIRE(encode_a_map(enc, &k.mapA[sp], d, KC, k.TWB, k.TH + sp, swz) == 0, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(A) failed");
+  for (int sp = max_span + 1; sp < 4; ++sp) k.mapA[sp] = k.mapA[0];
   {
     cuuint64_t dims[3] = {(cuuint64_t)d->a_c, (cuuint64_t)d->b_rows, (cuuint64_t)d->b_samples};
     cuuint64_t strides[2] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->b_rows * d->a_c * 2};
@@ -980,6 +1079,15 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   dim3 grid(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
   igemm_tc2_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(k);
   return sfk_check_launch("igemm_tc2_kernel");
+}
+
+extern "C" int sfk_role_cycles(unsigned long long* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, g_role_cycles, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_role_cycles, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
 }
 
 extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {

@@ -47,7 +47,7 @@ class SfkIgemmDesc(C.Structure):
 
 # every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
+    "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd",
@@ -138,6 +138,15 @@ def igemm(desc: SfkIgemmDesc, ref: bool = False, v1: bool = False):
         _PROFILE.append((e0, e1, igemm_flops(desc), (desc.n_img, desc.out_h, desc.out_w, desc.a_c, desc.out_c, desc.num_taps, desc.num_acc)))
         return
     _chk(fn(C.byref(desc), _stream()), "sfk_igemm_ref" if ref else "sfk_igemm")
+
+
+EP_PROFILE = 1 << 16
+
+
+def role_cycles(reset=True):
+    buf = (C.c_ulonglong * 8)()
+    _chk(load().sfk_role_cycles(buf, int(reset)), "role_cycles")
+    return list(buf)
 
 
 def profile_igemm(step_fn) -> dict:

@@ -89,6 +89,9 @@ typedef struct {
 int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);   /* persistent kernel; call from one host thread at a time */
 /* One-tile-per-CTA variant of the same contract (first implementation; kept for A/B timing and as a second cross-check). */
 int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream);
+/* Profiling aid: with flag bit 16 set, sfk_igemm accumulates per-role wait/total cycles (producer, MMA issuer, epilogue);
+ * this copies the 8 counters out (synchronising) and optionally resets them. */
+int sfk_role_cycles(unsigned long long* out8, int reset);
 /* Same contract on CUDA cores with plain loops: the on-device cross-check of the tensor-core path. */
 int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream);
 

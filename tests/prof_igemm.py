@@ -9,6 +9,7 @@ def main():
     n, h, w, cin, cout = map(int, sys.argv[1:6])
     mode = sys.argv[6] if len(sys.argv) > 6 else "fwd"
     reps = int(sys.argv[7]) if len(sys.argv) > 7 else 5
+    stages = int(sys.argv[8]) if len(sys.argv) > 8 else 0
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     x = torch.randn(n, h, w, cin, generator=g, device=dev).bfloat16()
@@ -33,6 +34,10 @@ def main():
         out = torch.empty(n, 4, h + 1, w + 1, cout, device=dev, dtype=torch.bfloat16)
         d = lib.make_igemm_desc(x, n, h, w, cin, 1, wt, n, 9 * cout, out, h + 1, w + 1, cout, 4, lib.pick_block_n(cout, 4), lib.tconv_taps(cout), err=err)
         bytes_alg = 2 * n * h * w * (cin + 4 * cout)
+    d.stages = stages
+    if os.environ.get('SFK_ROLES'):
+        d.flags |= lib.EP_PROFILE
+        lib.role_cycles(True)
     for _ in range(2):
         lib.igemm(d)
     torch.cuda.synchronize()
@@ -44,7 +49,12 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = lib.igemm_flops(d)
-    print(f"{mode} n={n} {h}x{w} cin={cin} cout={cout}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s  {bytes_alg/ms/1e6:.1f} GB/s (algorithmic)  err={err.item()}")
+    if os.environ.get('SFK_ROLES'):
+        rc = lib.role_cycles(True)
+        tiles = max(rc[7], 1)
+        names = ['mma_issue', 'prod_total', 'mma_wait_data', 'mma_wait_acc', 'mma_total', 'epi_wait', 'epi_total']
+        print('  role cycles per tile: ' + ', '.join(f'{n}={v / tiles:.0f}' for n, v in zip(names, rc[:7])) + f'  (tiles={tiles})')
+    print(f"stages={stages} {mode} n={n} {h}x{w} cin={cin} cout={cout}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s  {bytes_alg/ms/1e6:.1f} GB/s (algorithmic)  err={err.item()}")
 
 if __name__ == "__main__":
     main()
