@@ -331,30 +331,40 @@ __global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restric
 __global__ void image_loss_grad_kernel(const float* __restrict__ img, const float* __restrict__ ref, const float* __restrict__ gpool,
                                        float* __restrict__ g, float* __restrict__ loss, float coef_loss, float coef_grad, int S, int k) {
   const int n = blockIdx.y;
-  const long per = 3L * S * S;
-  const int Sp = S / k;
+  const long per4 = 3L * S * S / 4;
+  const int Sp = S / k, S4 = S / 4;
   const float invk2 = 1.f / static_cast<float>(k * k);
   float lsum = 0.f;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int w = i % S;
-    long p = i / S;
+  const float4* iv = reinterpret_cast<const float4*>(img + static_cast<long>(n) * 3 * S * S);
+  const float4* rv = reinterpret_cast<const float4*>(ref + static_cast<long>(n) * 3 * S * S);
+  float4* gv = reinterpret_cast<float4*>(g + static_cast<long>(n) * 3 * S * S);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int w4 = i % S4;
+    long p = i / S4;
     const int h = p % S;
     const int c = p / S;
-    const long off = static_cast<long>(n) * per + i;
-    const float d = img[off] - ref[off];
-    lsum += d * d;
-    float gv = coef_grad * d;
-    if (gpool) gv += invk2 * __ldg(gpool + ((static_cast<long>(n) * 3 + c) * Sp + h / k) * Sp + w / k);
-    g[off] = gv;
+    const float4 a = __ldg(iv + i), r = __ldg(rv + i);
+    const float* ap = reinterpret_cast<const float*>(&a);
+    const float* rp = reinterpret_cast<const float*>(&r);
+    float4 o;
+    float* op = reinterpret_cast<float*>(&o);
+    const float* gr = gpool ? gpool + ((static_cast<long>(n) * 3 + c) * Sp + h / k) * Sp : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = ap[j] - rp[j];
+      lsum += d * d;
+      op[j] = coef_grad * d + (gr ? invk2 * __ldg(gr + (w4 * 4 + j) / k) : 0.f);
+    }
+    gv[i] = o;
   }
   lsum = warp_sum(lsum);
   __shared__ float red[kBlock / 32];
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
   __syncthreads();
   if (threadIdx.x == 0 && loss) {
-    float s = 0.f;
-    for (int q = 0; q < blockDim.x / 32; ++q) s += red[q];
-    atomicAdd(loss + n, coef_loss * s);
+    float t = 0.f;
+    for (int q = 0; q < blockDim.x / 32; ++q) t += red[q];
+    atomicAdd(loss + n, coef_loss * t);
   }
 }
 
@@ -457,109 +467,177 @@ __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const f
 // demod, noise, bias, leaky-relu
 __device__ __forceinline__ float blur_w(int t) { return (t == 0 || t == 3) ? 0.25f : 0.75f; }
 
-__global__ void blur_act_fwd_kernel(const bf16* __restrict__ T, bf16* __restrict__ out, const float* __restrict__ d, const float* __restrict__ noise,
-                                    float noise_w, const float* __restrict__ bias, int H, int W, int C) {
-  const int n = blockIdx.y;
-  const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1;
-  const long total = static_cast<long>(Ho) * Wo * vecs;
-  const bf16* Tn = T + static_cast<long>(n) * 4 * Hp * Wp * C;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int v = idx % vecs;
-    long p = idx / vecs;
-    const int pw = p % Wo;
-    const int po = p / Wo;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// Register-blocked separable 4x4 FIR: one thread produces a 2 x 4 block of positions x 8 channels.  Input rows are streamed:
+// each of the 5 rows is loaded once (7 vectors), blurred horizontally into 4 partial columns, then scattered into the 2 output
+// rows -- 35 loads for 8 outputs (4.4 per output instead of 16).
+//   acc[i][j] = sum_{t,u} in[row0+i+t][col0+j+u] * k[t] * k[u]
+template <class Load>
+__device__ __forceinline__ void blur_block_2x4(int row0, int col0, Load&& ld, float (&acc)[2][4][8]) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int q = po + t - 1;
-      if (q < 0 || q > 2 * H) continue;
-      const float wt = blur_w(t);
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = pw + u - 1;
-        if (r < 0 || r > 2 * W) continue;
-        const float wgt = wt * blur_w(u);
-        const int plane = (q & 1) * 2 + (r & 1);
-        float tv[8];
-        unpack8(ldg8(Tn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + v * 8), tv);
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, tv[i], acc[i]);
+      for (int c = 0; c < 8; ++c) acc[i][j][c] = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < 5; ++rr) {
+    float h[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) h[j][c] = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 7; ++cc) {
+      float v[8];
+      ld(row0 + rr, col0 + cc, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = cc - j;
+        if (u >= 0 && u < 4) {
+          const float wu = blur_w(u);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) h[j][c] = fmaf(wu, v[c], h[j][c]);
+        }
       }
     }
-    const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(po) * Wo + pw) : 0.f;
-    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = v * 8 + i;
-      o[i] = lrelu_fwd(acc[i] * d[static_cast<long>(n) * C + c] + nz + bias[c]);
+    for (int i = 0; i < 2; ++i) {
+      const int t = rr - i;
+      if (t >= 0 && t < 4) {
+        const float wt = blur_w(t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][j][c] = fmaf(wt, h[j][c], acc[i][j][c]);
+      }
     }
-    stg8(out + ((static_cast<long>(n) * Ho + po) * Wo + pw) * C + v * 8, pack8(o));
   }
 }
 
-// thread = one gT position (q,r) in [0,2H]x[0,2W] x 8 channels.  gz = d*slope(out)*gout is recomputed at the
-// 16 contributing output pixels; the thread also owns output pixel (q,r) for the demod reduction.
-__global__ void blur_act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ gout, bf16* __restrict__ gT, const float* __restrict__ d,
-                                    const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
-                                    int H, int W, int C) {
-  extern __shared__ float sacc[];
-  const int n = blockIdx.y;
-  const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1;
-  const int Hq = 2 * H + 2, Wq = 2 * W + 2;   // cover every (plane, m, n) slot so unused slots are written as zero
-  const long total = static_cast<long>(Hq) * Wq * vecs;
-  const bf16* on = out + static_cast<long>(n) * Ho * Wo * C;
-  const bf16* gn = gout + static_cast<long>(n) * Ho * Wo * C;
-  bf16* gTn = gT + static_cast<long>(n) * 4 * Hp * Wp * C;
-  const int cv = threadIdx.x % vecs;  // constant across the grid-stride loop (total threads % vecs == 0)
+// Shared-memory tiled version of the blur (forward) and its transpose (backward).
+//   load phase   : the 19 x (TC+3) input halo of a 16 x TC output tile is fetched ONCE, 16 B per thread, all loads independent
+//                  (backward: gy = slope(out)*gout is formed here and the demodulation reduction sum gy*y is taken on the
+//                  tile's own 16 x TC pixels);
+//   compute phase: each thread produces a 2 x 4 block of positions x 8 channels from shared memory with the separable
+//                  register-blocked FIR above (35 LDS.128 per 8 outputs);
+//   bank layout  : positions are 64 B (CV=4 channel vectors) apart with 64 B of padding after every 4th one, so the two
+//                  column blocks served in one LDS.128 phase fall into different halves of the 32 banks.
+struct BlurGeom {
+  int CV, bc, TC, pitch;   // channel vectors per position, column blocks per tile, tile columns, padded positions per row
+};
+__host__ __device__ inline int blur_cp(int r) { return r + (r >> 2); }
+__host__ __device__ inline BlurGeom blur_geom(int vecs) {
+  BlurGeom g;
+  g.CV = vecs < 4 ? vecs : 4;
+  g.bc = (256 / g.CV) / 8;
+  g.TC = g.bc * 4;
+  g.pitch = blur_cp(g.TC + 2) + 1;
+  return g;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restrict__ src0 /* fwd: T (phase planar) ; bwd: out */,
+                                                        const bf16* __restrict__ src1 /* bwd: gout */, bf16* __restrict__ dst,
+                                                        const float* __restrict__ d, const float* __restrict__ noise, float noise_w,
+                                                        const float* __restrict__ bias, float* __restrict__ gdacc, int H, int W, int C) {
+  extern __shared__ uint4 tile[];
+  __shared__ float sred[32];
+  const int n = blockIdx.y, cg = blockIdx.z;
+  const int vecs = C / 8;
+  const BlurGeom G = blur_geom(vecs);
+  const int CV = G.CV, TC = G.TC, pitch = G.pitch, bc = G.bc;
+  const int Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1;
+  const int rows_out = BWD ? 2 * H + 2 : Ho;   // bwd writes every slot of every phase plane
+  const int cols_out = BWD ? 2 * W + 2 : Wo;
+  const int tiles_r = (rows_out + 15) / 16, tiles_c = (cols_out + TC - 1) / TC;
+  const int v = threadIdx.x % CV, cvec = cg * CV + v;       // this thread's channel vector (fixed for the whole kernel)
+  const int b = threadIdx.x / CV, jb = b % bc, ib = b / bc;  // its 2x4 block inside a tile
   float dv[8], bv[8], racc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    dv[i] = d[static_cast<long>(n) * C + cv * 8 + i];
-    bv[i] = bias[cv * 8 + i];
-    racc[i] = 0.f;
+  for (int c = 0; c < 8; ++c) {
+    dv[c] = d[static_cast<long>(n) * C + cvec * 8 + c];
+    bv[c] = bias[cvec * 8 + c];
+    racc[c] = 0.f;
   }
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    long p = idx / vecs;
-    const int r = p % Wq;
-    const int q = p / Wq;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (q <= 2 * H && r <= 2 * W) {
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int o = q - t + 1;
-        if (o < 0 || o >= Ho) continue;
-        const float wt = blur_w(t);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int pw = r - u + 1;
-          if (pw < 0 || pw >= Wo) continue;
-          const float wgt = wt * blur_w(u);
-          const long off = (static_cast<long>(o) * Wo + pw) * C + cv * 8;
+  const bf16* s0 = BWD ? src0 + static_cast<long>(n) * Ho * Wo * C : src0 + static_cast<long>(n) * 4 * Hp * Wp * C;
+  const bf16* s1 = BWD ? src1 + static_cast<long>(n) * Ho * Wo * C : nullptr;
+  bf16* dn = BWD ? dst + static_cast<long>(n) * 4 * Hp * Wp * C : dst + static_cast<long>(n) * Ho * Wo * C;
+  const int halo = BWD ? 2 : 1;
+  const int in_cols = TC + 3;
+  const int n_in = 19 * in_cols * CV;
+  for (int t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const int R0 = (t / tiles_c) * 16, C0 = (t % tiles_c) * TC;
+    // ---- load phase
+    for (int e = threadIdx.x; e < n_in; e += 256) {
+      const int c = (e / CV) % in_cols, r = e / (CV * in_cols);
+      const int q = R0 - halo + r, rr = C0 - halo + c;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (!BWD) {
+        if (q >= 0 && q <= 2 * H && rr >= 0 && rr <= 2 * W) {
+          const int plane = (q & 1) * 2 + (rr & 1);
+          val = ldg8(s0 + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (rr >> 1)) * C + cvec * 8);
+        }
+      } else {
+        if (q >= 0 && q < Ho && rr >= 0 && rr < Wo) {
+          const long off = (static_cast<long>(q) * Wo + rr) * C + cvec * 8;
           float ov[8], gv[8];
-          unpack8(ldg8(on + off), ov);
-          unpack8(ldg8(gn + off), gv);
+          unpack8(ldg8(s0 + off), ov);
+          unpack8(ldg8(s1 + off), gv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt * lrelu_slope(ov[i]), gv[i], acc[i]);
+          for (int cc = 0; cc < 8; ++cc) gv[cc] *= lrelu_slope(ov[cc]);
+          if (r >= 2 && r < 18 && c >= 2 && c < 2 + TC) {   // the tile's own pixels: demodulation reduction
+            const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(q) * Wo + rr) : 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) racc[cc] = fmaf(gv[cc], lrelu_inv(ov[cc]) - nz - bv[cc], racc[cc]);
+          }
+          val = pack8(gv);
         }
       }
-      if (q < Ho && r < Wo) {
-        const long off = (static_cast<long>(q) * Wo + r) * C + cv * 8;
-        float ov[8], gv[8];
-        unpack8(ldg8(on + off), ov);
-        unpack8(ldg8(gn + off), gv);
-        const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(q) * Wo + r) : 0.f;
+      tile[(r * pitch + blur_cp(c)) * CV + v] = val;
+    }
+    __syncthreads();
+    // ---- compute phase
+    float acc[2][4][8];
+    blur_block_2x4(2 * ib, 4 * jb, [&](int r, int c, float* f) { unpack8(tile[(r * pitch + blur_cp(c)) * CV + v], f); }, acc);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) racc[i] = fmaf(gv[i] * lrelu_slope(ov[i]), lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
+    for (int i = 0; i < 2; ++i) {
+      const int q = R0 + 2 * ib + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = C0 + 4 * jb + j;
+        if (q >= rows_out || rr >= cols_out) continue;
+        float o[8];
+        if (!BWD) {
+          const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(q) * Wo + rr) : 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = lrelu_fwd(fmaf(acc[i][j][c], dv[c], nz + bv[c]));
+          stg8(dn + (static_cast<long>(q) * Wo + rr) * C + cvec * 8, pack8(o));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = acc[i][j][c] * dv[c];
+          const int plane = (q & 1) * 2 + (rr & 1);
+          stg8(dn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (rr >> 1)) * C + cvec * 8, pack8(o));
+        }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= dv[i];
-    const int plane = (q & 1) * 2 + (r & 1);
-    stg8(gTn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + cv * 8, pack8(acc));
+    __syncthreads();
   }
-  flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
+  if (BWD) {
+    // per-channel totals: threads with the same v (tid % CV) reduce through shared memory, then 8*CV atomics per block
+    float* facc = reinterpret_cast<float*>(tile);   // reuse: [CV*8]
+    if (threadIdx.x < CV * 8) facc[threadIdx.x] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float x = racc[c];
+      // lanes l and l^CV, l^2CV, ... share v: butterfly over the bits above log2(CV)
+      for (int o = 16; o >= CV; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) < CV) atomicAdd(&facc[v * 8 + c], x);
+    }
+    __syncthreads();
+    if (threadIdx.x < CV * 8) atomicAdd(gdacc + static_cast<long>(n) * C + cg * CV * 8 + threadIdx.x, facc[threadIdx.x]);
+  }
+  (void)sred;
 }
 
 __global__ void act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ gout, bf16* __restrict__ gz, const float* __restrict__ d,
@@ -857,20 +935,37 @@ __device__ __forceinline__ float pooled_grad(const float* __restrict__ gpool, in
   return __ldg(gpool + ((static_cast<long>(n) * 3 + c) * Sp + h / k) * Sp + w / k);
 }
 
+// 4 consecutive pixels of one row per thread (float4): S % 4 == 0 and (k == 1 or 4 % k == 0 or k % 4 == 0) hold for S = 2^m
 __global__ void update_linf_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ gpool, float alpha, float eps,
                                    float dir, float lo, float hi, float* __restrict__ stats, int S, int k) {
   const int n = blockIdx.y;
-  const long per = 3L * S * S;
+  const long per4 = 3L * S * S / 4;
+  const int Sp = S / k, S4 = S / 4;
   float dsum = 0.f;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long off = static_cast<long>(n) * per + i;
-    const float g = pooled_grad(gpool, n, i, S, k);
-    const float c0 = x0[off];
-    float v = x[off] + dir * alpha * sgn(g);
-    const float dl = fminf(fmaxf(v - c0, -eps), eps);
-    v = fminf(fmaxf(c0 + dl, lo), hi);
-    x[off] = v;
-    dsum += fabsf(v - c0);
+  float4* xv = reinterpret_cast<float4*>(x + static_cast<long>(n) * 3 * S * S);
+  const float4* x0v = reinterpret_cast<const float4*>(x0 + static_cast<long>(n) * 3 * S * S);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int w4 = i % S4;
+    long p = i / S4;
+    const int h = p % S;
+    const int c = p / S;
+    const float* gr = gpool + ((static_cast<long>(n) * 3 + c) * Sp + h / k) * Sp;
+    const float4 c0 = __ldg(x0v + i);
+    float4 v = xv[i];
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = __ldg(gr + (w4 * 4 + j) / k);
+    float* vp = reinterpret_cast<float*>(&v);
+    const float* cp = reinterpret_cast<const float*>(&c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = vp[j] + dir * alpha * sgn(g[j]);
+      const float dl = fminf(fmaxf(t - cp[j], -eps), eps);
+      t = fminf(fmaxf(cp[j] + dl, lo), hi);
+      vp[j] = t;
+      dsum += fabsf(t - cp[j]);
+    }
+    xv[i] = v;
   }
   block_add(dsum, stats ? stats + n : nullptr);
 }
@@ -975,6 +1070,15 @@ inline unsigned per_sample_blocks(long items, int n) {
   return static_cast<unsigned>(b);
 }
 
+inline unsigned per_sample_blocks128(long items, int n) {
+  long b = (items + 127) / 128;
+  long cap = (static_cast<long>(sfk_num_sms()) * 12 + n - 1) / n;
+  if (cap < 1) cap = 1;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -1046,8 +1150,8 @@ int sfk_mse_tap(const void* f, const void* ref, void* g, float* loss, float coef
 
 int sfk_image_loss_grad(const float* img, const float* ref, const float* gpool, float* g, float* loss, float coef_loss, float coef_grad, int n,
                         int size, int k, sfk_stream_t s) {
-  SFK_REQUIRE(img && ref && g && size % k == 0, SFK_E_ARG, "image_loss_grad: bad args");
-  image_loss_grad_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(s)>>>(img, ref, gpool, g, loss, coef_loss, coef_grad, size, k);
+  SFK_REQUIRE(img && ref && g && size % k == 0 && size % 4 == 0, SFK_E_ARG, "image_loss_grad: bad args");
+  image_loss_grad_kernel<<<dim3(per_sample_blocks(3L * size * size / 4, n), n), kBlock, 0, S_(s)>>>(img, ref, gpool, g, loss, coef_loss, coef_grad, size, k);
   return sfk_check_launch("image_loss_grad");
 }
 
@@ -1087,20 +1191,44 @@ int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void
   return sfk_check_launch("modulate_weights");
 }
 
+static int blur_launch(bool bwd, const void* a0, const void* a1, void* dst, const float* d, const float* noise, float noise_w, const float* bias,
+                       float* gdacc, int n, int h, int w, int c, sfk_stream_t st) {
+  const int vecs = c / 8;
+  const BlurGeom G = blur_geom(vecs);
+  SFK_REQUIRE(vecs % G.CV == 0 && (G.CV == 1 || G.CV == 2 || G.CV == 4), SFK_E_SHAPE, "blur: channel count must be 8, 16 or a multiple of 32");
+  const size_t smem = static_cast<size_t>(19) * G.pitch * G.CV * 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(blur_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(blur_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  const int rows = bwd ? 2 * h + 2 : 2 * h, cols = bwd ? 2 * w + 2 : 2 * w;
+  const long tiles = static_cast<long>((rows + 15) / 16) * ((cols + G.TC - 1) / G.TC);
+  const int cgs = vecs / G.CV;
+  long bx = tiles;
+  const long cap = (static_cast<long>(sfk_num_sms()) * 4 + n * cgs - 1) / (n * cgs);
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  dim3 grid(static_cast<unsigned>(bx), n, cgs);
+  if (bwd)
+    blur_tile_kernel<true><<<grid, 256, smem, S_(st)>>>(static_cast<const bf16*>(a0), static_cast<const bf16*>(a1), static_cast<bf16*>(dst), d, noise,
+                                                        noise_w, bias, gdacc, h, w, c);
+  else
+    blur_tile_kernel<false><<<grid, 256, smem, S_(st)>>>(static_cast<const bf16*>(a0), nullptr, static_cast<bf16*>(dst), d, noise, noise_w, bias,
+                                                         nullptr, h, w, c);
+  return sfk_check_launch(bwd ? "blur_act_bwd" : "blur_act_fwd");
+}
+
 int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias, int n, int h, int w, int c,
                      sfk_stream_t st) {
   SFK_REQUIRE(T && out && d && bias && c % 8 == 0, SFK_E_ARG, "blur_act_fwd: bad args");
-  blur_act_fwd_kernel<<<dim3(per_sample_blocks(4L * h * w * (c / 8), n), n), kBlock, 0, S_(st)>>>(static_cast<const bf16*>(T), static_cast<bf16*>(out), d,
-                                                                                                  noise, noise_w, bias, h, w, c);
-  return sfk_check_launch("blur_act_fwd");
+  return blur_launch(false, T, nullptr, out, d, noise, noise_w, bias, nullptr, n, h, w, c, st);
 }
 
 int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d, const float* noise, float noise_w, const float* bias,
                      float* gdacc, int n, int h, int w, int c, sfk_stream_t st) {
-  SFK_REQUIRE(out && gout && gT && d && bias && gdacc && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "blur_act_bwd: bad args");
-  blur_act_bwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(2 * h + 2) * (2 * w + 2) * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
-      static_cast<const bf16*>(out), static_cast<const bf16*>(gout), static_cast<bf16*>(gT), d, noise, noise_w, bias, gdacc, h, w, c);
-  return sfk_check_launch("blur_act_bwd");
+  SFK_REQUIRE(out && gout && gT && d && bias && gdacc && c % 8 == 0, SFK_E_ARG, "blur_act_bwd: bad args");
+  return blur_launch(true, out, gout, gT, d, noise, noise_w, bias, gdacc, n, h, w, c, st);
 }
 
 int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w, const float* bias, float* gdacc,
@@ -1115,7 +1243,7 @@ int sfk_torgb_fwd(const void* x, const float* wrgb, const float* sv, int s_strid
                   int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(x && wrgb && sv && bias && rgb && c % 8 == 0, SFK_E_ARG, "torgb_fwd: bad args");
   int lp = 1;
-  while (lp < 32 && lp * 2 <= c / 8) lp *= 2;
+  while (lp < 32 && lp * 16 <= c / 8) lp *= 2;   // C<=64: one thread per pixel (full 64-128 B reads, coalesced planar stores)
   torgb_fwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * lp, n), n), kBlock, 3 * c * sizeof(float), S_(st)>>>(
       static_cast<const bf16*>(x), wrgb, sv, s_stride, bias, skip, rgb, h, w, c, lp);
   return sfk_check_launch("torgb_fwd");
@@ -1184,8 +1312,8 @@ int sfk_nhwc_bf16_to_nchw(const void* x, float* y, int n, int c, int h, int w, s
 
 int sfk_attack_update_linf(float* x, const float* x0, const float* gpool, float alpha, float eps, float dir, float lo, float hi, float* stats,
                            int n, int size, int k, sfk_stream_t st) {
-  SFK_REQUIRE(x && x0 && gpool && size % k == 0, SFK_E_ARG, "attack_update_linf: bad args");
-  update_linf_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, x0, gpool, alpha, eps, dir, lo, hi, stats, size, k);
+  SFK_REQUIRE(x && x0 && gpool && size % k == 0 && size % 4 == 0, SFK_E_ARG, "attack_update_linf: bad args");
+  update_linf_kernel<<<dim3(per_sample_blocks(3L * size * size / 4, n), n), kBlock, 0, S_(st)>>>(x, x0, gpool, alpha, eps, dir, lo, hi, stats, size, k);
   return sfk_check_launch("attack_update_linf");
 }
 
