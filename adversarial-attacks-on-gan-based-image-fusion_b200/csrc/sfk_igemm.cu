@@ -389,7 +389,7 @@ struct __align__(64) Igemm2Args {
   int n_img, out_h, out_w, out_c;
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
-  int b_per_sample, b_resident;
+  int b_per_sample, b_resident, dual_issue;
   int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
   int layout_type, sbo_bytes, tmem_cols, flags, vec_stride;
   float noise_w;
@@ -402,6 +402,9 @@ struct __align__(64) Igemm2Args {
   float* gs;
   int* err;
   KGroup groups[kMaxGroups];
+  // taps flattened in issue order for the MMA warp (kept in registers): operand offsets (16 B units), TMEM column,
+  // flags bit0 = first MMA into its accumulator, bit1 = first tap of a load group (wait for data), bit2 = last (release slot)
+  int f_a16[SFK_MAX_TAPS], f_b16[SFK_MAX_TAPS], f_col[SFK_MAX_TAPS], f_flags[SFK_MAX_TAPS];
 };
 
 // role-level cycle accounting (only when SFK_EP_PROFILE is set): [0] producer waiting for a free slot, [1] producer total,
@@ -429,7 +432,9 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   __shared__ uint64_t bres_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float gs_acc[256];
-  __shared__ float col_dscale[256], col_bias[256], col_scale[256];
+  __shared__ __align__(16) float col_dscale[256];
+  __shared__ __align__(16) float col_bias[256];
+  __shared__ __align__(16) float col_scale[256];
   __shared__ int4 s_tap[kMaxGroups * kMaxGroupTaps];   // per tap: {A offset>>4 (+phase), B offset>>4, TMEM column, first}
 
   const int warp = threadIdx.x >> 5;
@@ -537,8 +542,13 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         atomicAdd(&g_role_cycles[1], static_cast<unsigned long long>(clock64() - t_start));
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || (warp == 3 && a.dual_issue)) {
+    // ===================== MMA issuer(s) =====================
+    // Issue is instruction-latency bound for small N, so with a double-buffered accumulator TWO warps issue: warp 1 owns the
+    // even tiles (accumulator stage 0), warp 3 the odd ones (stage 1).  MMAs into different accumulators are independent,
+    // each warp consumes exactly the ring slots of its own tiles, and every barrier still sees one arrival per use.
+    // Only enabled when the ring holds two whole tiles (stages >= 2 * slots per tile): an mbarrier parity wait cannot tell a
+    // phase from the one two wraps earlier, so the two consumers must never be more than one wrap apart.
     // The whole warp walks the loop convergently (so descriptors live in uniform registers without vote loops);
     // one elected lane issues tcgen05.mma / tcgen05.commit.
     {
@@ -547,13 +557,25 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                              (static_cast<uint32_t>(128 >> 4) << 24);
       const int kslices = a.KC / 16;
       const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
-      long long t_wd = 0, t_wa = 0, t_issue = 0;
+      long long t_wd = 0, t_wa = 0;
+      const int nflat = a.num_taps;
+      int A16[SFK_MAX_TAPS], B16[SFK_MAX_TAPS], COL[SFK_MAX_TAPS], FL[SFK_MAX_TAPS];
+#pragma unroll
+      for (int t = 0; t < SFK_MAX_TAPS; ++t) {
+        A16[t] = a.f_a16[t];
+        B16[t] = a.f_b16[t];
+        COL[t] = a.f_col[t];
+        FL[t] = a.f_flags[t];
+      }
       const long long t_start = clock64();
       const uint64_t desc_hi = make_smem_desc(0, a.sbo_bytes, a.layout_type);   // everything but the start address
       bool ok = true;
       if (a.b_resident) ok = mbar_wait(&bres_bar, 0, a.err);
-      int ks = 0, it = 0;
-      for (int tile = blockIdx.x; tile < tiles_per_group && ok; tile += gridDim.x, ++it) {
+      const int par = (warp == 3) ? 1 : 0;
+      const int step = a.dual_issue ? 2 : 1;
+      const int kpt = a.num_cblk * a.num_groups;   // ring slots per tile
+      for (int it = par; blockIdx.x + it * static_cast<int>(gridDim.x) < tiles_per_group && ok; it += step) {
+        int ks = it * kpt;
         const int as = it % a.acc_stages;
         const uint32_t aph = (it / a.acc_stages) & 1;
         const long long ta0 = prof ? clock64() : 0;
@@ -562,36 +584,36 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * a.num_acc * a.block_n);
         for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
-          for (int g = 0; g < a.num_groups; ++g, ++ks) {
-            const KGroup& G = a.groups[g];
-            const int stage = ks % a.stages;
-            const uint32_t phase = (ks / a.stages) & 1;
-            const long long td0 = prof ? clock64() : 0;
-            if (!mbar_wait(&full_bar[stage], phase, a.err)) {
-              ok = false;
-              break;
-            }
-            if (prof) t_wd += clock64() - td0;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // everything tap-specific was folded into s_tap once per CTA: ~10 instructions per MMA issued
-            const uint32_t a_lo = (smem_a + stage * a.a_stage_bytes) >> 4;
-            const uint32_t b_lo = (a.b_resident ? smem_b + cb * a.num_taps * a.b_tap_bytes : smem_b + stage * a.b_stage_bytes) >> 4;
-            const int nt = G.ntaps;
-            for (int j = 0; j < nt; ++j) {
-              const uint64_t adesc = desc_hi | static_cast<uint64_t>(a_lo + static_cast<uint32_t>(G.a16[j]));
-              const uint64_t bdesc = desc_hi | static_cast<uint64_t>(b_lo + static_cast<uint32_t>(G.b16[j]));
-              const uint32_t tmem_c = tmem_tile + static_cast<uint32_t>(G.col[j]);
-              const long long ti0 = prof ? clock64() : 0;
-              if (leader) {
-                umma_bf16(tmem_c, adesc, bdesc, idesc, (cb == 0 && G.first[j]) ? 0u : 1u);
+          uint32_t a_lo = 0, b_lo = 0;
+          int stage = 0;
+#pragma unroll
+          for (int t = 0; t < SFK_MAX_TAPS; ++t) {
+            if (t < nflat && ok) {
+              if (FL[t] & 2) {   // first tap of a load group: wait for its box (and weight tiles)
+                stage = ks % a.stages;
+                const uint32_t phase = (ks / a.stages) & 1;
+                const long long td0 = prof ? clock64() : 0;
+                ok = mbar_wait(&full_bar[stage], phase, a.err);
+                if (prof) t_wd += clock64() - td0;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                a_lo = (smem_a + stage * a.a_stage_bytes) >> 4;
+                b_lo = (a.b_resident ? smem_b + cb * a.num_taps * a.b_tap_bytes : smem_b + stage * a.b_stage_bytes) >> 4;
+              }
+              const uint64_t adesc = desc_hi | static_cast<uint64_t>(a_lo + static_cast<uint32_t>(A16[t]));
+              const uint64_t bdesc = desc_hi | static_cast<uint64_t>(b_lo + static_cast<uint32_t>(B16[t]));
+              const uint32_t tmem_c = tmem_tile + static_cast<uint32_t>(COL[t]);
+              if (leader && ok) {
+                umma_bf16(tmem_c, adesc, bdesc, idesc, (cb == 0 && (FL[t] & 1)) ? 0u : 1u);
 #pragma unroll
                 for (int k = 1; k < 4; ++k)
                   if (k < kslices) umma_bf16(tmem_c, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, 1u);
               }
-              if (prof) t_issue += clock64() - ti0;
+              if (FL[t] & 4) {   // last tap of the group: the slot is free once these MMAs retire
+                __syncwarp();
+                if (leader) umma_commit(&empty_bar[stage]);
+                ++ks;
+              }
             }
-            __syncwarp();
-            if (leader) umma_commit(&empty_bar[stage]);
           }
         }
         __syncwarp();
@@ -600,7 +622,6 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       if (prof && leader) {
         atomicAdd(&g_role_cycles[2], static_cast<unsigned long long>(t_wd));
         atomicAdd(&g_role_cycles[3], static_cast<unsigned long long>(t_wa));
-        atomicAdd(&g_role_cycles[0], static_cast<unsigned long long>(t_issue));   // (slot 0 doubles as MMA-issue time; producer wait = [1]-busy)
         atomicAdd(&g_role_cycles[4], static_cast<unsigned long long>(clock64() - t_start));
       }
     }
@@ -615,14 +636,28 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     const bool prof = (flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
     long long t_we = 0;
     const long long t_start = clock64();
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles_per_group; tile += gridDim.x, ++it) {
+    // tile coordinates advance incrementally (no division per tile); the per-pixel noise value of the NEXT tile is fetched
+    // before blocking on the accumulator of the current one, so its latency is off the critical path
+    int tile = blockIdx.x;
+    int t_h = tile / a.tiles_w, t_w = tile % a.tiles_w;
+    const bool use_noise = (flags & SFK_EP_NOISE) != 0;
+    auto noise_at = [&](int hh, int ww) -> float {
+      return (use_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) ? a.noise_w * __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;
+    };
+    float nz_next = tile < tiles_per_group ? noise_at(t_h * a.TH + th, t_w * a.TW + tw) : 0.f;
+    for (int it = 0; tile < tiles_per_group; ++it) {
       const int as = it % a.acc_stages;
       const uint32_t aph = (it / a.acc_stages) & 1;
-      const int h = (tile / a.tiles_w) * a.TH + th, w = (tile % a.tiles_w) * a.TW + tw;
+      const int h = t_h * a.TH + th, w = t_w * a.TW + tw;
       bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
-      // issue the per-pixel loads before blocking on the accumulator
-      const float nz = ((flags & SFK_EP_NOISE) && valid) ? a.noise_w * __ldg(a.noise + static_cast<long>(h) * a.out_w + w) : 0.f;
+      const float nz = nz_next;
+      tile += gridDim.x;
+      t_w += gridDim.x;
+      while (t_w >= a.tiles_w) {
+        t_w -= a.tiles_w;
+        ++t_h;
+      }
+      if (tile < tiles_per_group) nz_next = noise_at(t_h * a.TH + th, t_w * a.TW + tw);
       const long long te0 = prof ? clock64() : 0;
       const bool ok = mbar_wait(&tmem_full_bar[as], aph, a.err);
       if (prof) t_we += clock64() - te0;
@@ -646,11 +681,17 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                  static_cast<uint32_t>((as * a.num_acc + acc) * a.block_n + c * 16);
           tmem_ld16(taddr, v);
-          const float* cd = col_dscale + c * 16;
-          const float* cb_ = col_bias + c * 16;
           if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
+            const float4* cd = reinterpret_cast<const float4*>(col_dscale + c * 16);
+            const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], cd[i], nz + cb_[i]);
+            for (int i = 0; i < 4; ++i) {
+              const float4 dd = cd[i], bb = cb_[i];
+              v[4 * i + 0] = fmaf(v[4 * i + 0], dd.x, nz + bb.x);
+              v[4 * i + 1] = fmaf(v[4 * i + 1], dd.y, nz + bb.y);
+              v[4 * i + 2] = fmaf(v[4 * i + 2], dd.z, nz + bb.z);
+              v[4 * i + 3] = fmaf(v[4 * i + 3], dd.w, nz + bb.w);
+            }
           }
           if (flags & SFK_EP_RELU) {
 #pragma unroll
@@ -672,9 +713,15 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
           }
           if (flags & SFK_EP_COLSCALE) {
-            const float* cs = col_scale + c * 16;
+            const float4* cs = reinterpret_cast<const float4*>(col_scale + c * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= cs[i];
+            for (int i = 0; i < 4; ++i) {
+              const float4 ss = cs[i];
+              v[4 * i + 0] *= ss.x;
+              v[4 * i + 1] *= ss.y;
+              v[4 * i + 2] *= ss.z;
+              v[4 * i + 3] *= ss.w;
+            }
           }
           if (valid) {
             if (flags & SFK_EP_ACCUM) {
@@ -695,7 +742,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     if (prof) {
       atomicAdd(&g_role_cycles[5], static_cast<unsigned long long>(t_we));
       atomicAdd(&g_role_cycles[6], static_cast<unsigned long long>(clock64() - t_start));
-      atomicAdd(&g_role_cycles[7], static_cast<unsigned long long>(it));
+      atomicAdd(&g_role_cycles[7], static_cast<unsigned long long>((tiles_per_group - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)));
     }
   }
   __syncthreads();
@@ -1032,6 +1079,16 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
       k.groups[g].b16[j] = ((k.b_resident ? k.groups[g].bidx[j] : j) * k.b_tap_bytes) >> 4;
       k.groups[g].col[j] = k.groups[g].acc[j] * d->block_n;
     }
+  {
+    int t = 0;
+    for (int g = 0; g < ng; ++g)
+      for (int j = 0; j < k.groups[g].ntaps; ++j, ++t) {
+        k.f_a16[t] = k.groups[g].a16[j];
+        k.f_b16[t] = k.groups[g].b16[j];
+        k.f_col[t] = k.groups[g].col[j];
+        k.f_flags[t] = (k.groups[g].first[j] ? 1 : 0) | (j == 0 ? 2 : 0) | (j == k.groups[g].ntaps - 1 ? 4 : 0);
+      }
+  }
   k.a_stage_bytes = (((k.TH + max_span) * k.TWB * k.row_bytes + 1023) / 1024) * 1024;
   k.b_stage_bytes = k.b_resident ? 0 : max_gt * k.b_tap_bytes;
   const int tiles_per_group = k.tiles_h * k.tiles_w;
@@ -1054,6 +1111,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   SFK_REQUIRE(stages >= 1 && stages * stage_bytes + resident + 1024 <= 220 * 1024, SFK_E_SHAPE, "igemm: tile does not fit shared memory");
   k.stages = stages;
   k.acc_stages = (2 * cols <= (per_sm == 2 ? 256 : 512)) ? 2 : 1;
+  k.dual_issue = (k.acc_stages == 2 && stages >= 2 * k.num_cblk * ng) ? 1 : 0;
   const int want = k.acc_stages * cols;
   k.tmem_cols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
 

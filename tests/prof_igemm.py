@@ -52,7 +52,7 @@ def main():
     if os.environ.get('SFK_ROLES'):
         rc = lib.role_cycles(True)
         tiles = max(rc[7], 1)
-        names = ['mma_issue', 'prod_total', 'mma_wait_data', 'mma_wait_acc', 'mma_total', 'epi_wait', 'epi_total']
+        names = ['unused', 'prod_total', 'mma_wait_data', 'mma_wait_acc', 'mma_total', 'epi_wait', 'epi_total']
         print('  role cycles per tile: ' + ', '.join(f'{n}={v / tiles:.0f}' for n, v in zip(names, rc[:7])) + f'  (tiles={tiles})')
     print(f"stages={stages} {mode} n={n} {h}x{w} cin={cin} cout={cout}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s  {bytes_alg/ms/1e6:.1f} GB/s (algorithmic)  err={err.item()}")
 
