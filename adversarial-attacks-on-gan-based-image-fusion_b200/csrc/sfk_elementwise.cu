@@ -328,6 +328,28 @@ __global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restric
   }
 }
 
+// fp32 variant for latent codes: loss[n] += coef_loss*sum((a-b)^2); g (=|+=) coef_grad*(a-b)
+__global__ void mse_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ g, float* __restrict__ loss,
+                               float coef_loss, float coef_grad, int accumulate, long per_sample) {
+  const int n = blockIdx.y;
+  const long base = static_cast<long>(n) * per_sample;
+  float lsum = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per_sample; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float d = a[base + i] - b[base + i];
+    lsum += d * d;
+    if (g) g[base + i] = (accumulate ? g[base + i] : 0.f) + coef_grad * d;
+  }
+  lsum = warp_sum(lsum);
+  __shared__ float red[kBlock / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float t = 0.f;
+    for (int q = 0; q < blockDim.x / 32; ++q) t += red[q];
+    atomicAdd(loss + n, coef_loss * t);
+  }
+}
+
 __global__ void image_loss_grad_kernel(const float* __restrict__ img, const float* __restrict__ ref, const float* __restrict__ gpool,
                                        float* __restrict__ g, float* __restrict__ loss, float coef_loss, float coef_grad, int S, int k) {
   const int n = blockIdx.y;
@@ -990,13 +1012,15 @@ __global__ void update_patch_kernel(float* __restrict__ x, const float* __restri
   block_add(dsum, stats ? stats + n : nullptr);
 }
 
-__global__ void update_adam_kernel(float* __restrict__ x, const float* __restrict__ gpool, float* __restrict__ m, float* __restrict__ v, float lr,
-                                   float b1, float b2, float eps, float bc1, float bc2, float gscale, int S, int k) {
+__global__ void update_adam_kernel(float* __restrict__ x, const float* __restrict__ gpool, const float* __restrict__ gfull, float gfull_scale,
+                                   float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2, float eps, float bc1, float bc2,
+                                   float gscale, int S, int k) {
   const int n = blockIdx.y;
   const long per = 3L * S * S;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long off = static_cast<long>(n) * per + i;
-    const float g = gscale * pooled_grad(gpool, n, i, S, k);
+    float g = gscale * pooled_grad(gpool, n, i, S, k);
+    if (gfull) g += gfull_scale * gfull[off];
     const float mm = b1 * m[off] + (1.f - b1) * g;
     const float vv = b2 * v[off] + (1.f - b2) * g * g;
     m[off] = mm;
@@ -1146,6 +1170,13 @@ int sfk_mse_tap(const void* f, const void* ref, void* g, float* loss, float coef
                                                                                       static_cast<bf16*>(g), loss, coef_loss, coef_grad, accumulate,
                                                                                       relu_mask, per_sample);
   return sfk_check_launch("mse_tap");
+}
+
+int sfk_mse_f32(const float* a, const float* b, float* g, float* loss, float coef_loss, float coef_grad, int accumulate, int n, long per_sample,
+                sfk_stream_t s) {
+  SFK_REQUIRE(a && b, SFK_E_ARG, "mse_f32: null");
+  mse_f32_kernel<<<dim3(per_sample_blocks(per_sample, n), n), kBlock, 0, S_(s)>>>(a, b, g, loss, coef_loss, coef_grad, accumulate, per_sample);
+  return sfk_check_launch("mse_f32");
 }
 
 int sfk_image_loss_grad(const float* img, const float* ref, const float* gpool, float* g, float* loss, float coef_loss, float coef_grad, int n,
@@ -1325,11 +1356,11 @@ int sfk_attack_update_patch(float* x, const float* x0, float* patch, const float
   return sfk_check_launch("attack_update_patch");
 }
 
-int sfk_attack_update_adam(float* x, const float* gpool, float* m, float* v, float lr, float b1, float b2, float eps, int t, float gscale, int n,
-                           int size, int k, sfk_stream_t st) {
+int sfk_attack_update_adam(float* x, const float* gpool, const float* gfull, float gfull_scale, float* m, float* v, float lr, float b1, float b2,
+                           float eps, int t, float gscale, int n, int size, int k, sfk_stream_t st) {
   SFK_REQUIRE(x && gpool && m && v && t >= 1 && size % k == 0, SFK_E_ARG, "attack_update_adam: bad args");
   const float bc1 = 1.f - powf(b1, static_cast<float>(t)), bc2 = 1.f - powf(b2, static_cast<float>(t));
-  update_adam_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, gpool, m, v, lr, b1, b2, eps, bc1, bc2, gscale, size, k);
+  update_adam_kernel<<<dim3(per_sample_blocks(3L * size * size, n), n), kBlock, 0, S_(st)>>>(x, gpool, gfull, gfull_scale, m, v, lr, b1, b2, eps, bc1, bc2, gscale, size, k);
   return sfk_check_launch("attack_update_adam");
 }
 

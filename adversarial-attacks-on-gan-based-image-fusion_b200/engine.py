@@ -504,3 +504,125 @@ class AttackEngine:
         torch.cuda.synchronize(self.dev)
         if int(self.err.item()) != 0:
             raise lib.SfkError("a tensor-core kernel reported an internal pipeline timeout")
+
+
+# =================================================================================================
+@dataclass
+class ReconLossCfg:
+    """The loss menu of the reference's live loop `optimize_vgg` (code/attack/attack_main2.py:626-649):
+    10*l_latent_target + l_img_rec_target - l_latent_org + 20*l_img_org + l_lpips_img  (variants: interpolation.py:818,
+    inter_copy.py:658 use other weights and a VGG term on the reconstruction)."""
+    w_latent_target: float = 10.0
+    w_latent_org: float = -1.0
+    w_img_rec_target: float = 1.0
+    w_img_org: float = 20.0
+    w_lpips_img: float = 1.0
+    w_lpips_rec: float = 0.0          # VGG term on the reconstruction ...
+    lpips_rec_ref: str = "target"     # ... against the target's ("target") or the clean image's ("org") features
+
+
+class ReconAttackEngine:
+    """Reference-actual attack graph: pixels -> avg-pool -> encoder -> decoder reconstruction of ONE image, losses in latent,
+    pixel and VGG space, Adam on the pixels (attack_main2.py:584-671); also serves patch.attack (adversarial_patch.py:94-160).
+    Images are in the reference's [-1,1] range."""
+
+    def __init__(self, gspec: GenSpec, GP, espec: EncSpec, EP, vgg_sd, batch: int = 1, device="cuda:0",
+                 loss: Optional[ReconLossCfg] = None, vgg_res: int = 256, vgg_width_div: int = 1):
+        lib.load()
+        self.dev = torch.device(device)
+        self.cfg = loss or ReconLossCfg()
+        self.B, self.S, self.R = batch, gspec.size, espec.in_res
+        self.k_in, self.k_vgg, self.vgg_res = self.S // self.R, self.S // vgg_res, vgg_res
+        assert vgg_res == self.R, "the reference pools the image once and feeds both the encoder and VGG (attack_main2.py:619-624)"
+        B, dev, S, R = batch, self.dev, self.S, self.R
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        enc_w = [(EP[f"convs.{i}.weight"], EP[f"convs.{i}.bias"]) for i in range(len(espec.widths))]
+        self.enc = ConvStack(encoder_layers(espec), enc_w, B, R, dev, self.err)
+        self.head_w, self.head_b = f32(EP["head.weight"]), f32(EP["head.bias"])     # optimize_vgg calls encoder() directly: no latent_avg
+        L, D, cl = espec.n_latent, espec.style_dim, espec.widths[-1]
+        self.LD = L * D
+        self.feat, self.gfeat = _empty((B, cl), dev, torch.float32), _empty((B, cl), dev, torch.float32)
+        self.codes, self.gcodes, self.gw = (_empty((B, L, D), dev, torch.float32) for _ in range(3))
+        self.lat_t, self.lat_o = _empty((B, L, D), dev, torch.float32), _empty((B, L, D), dev, torch.float32)
+        self.syn = SynthesisEngine(gspec, GP, B, dev, self.err)
+        from .params import VGG_EXECUTED
+        vals = list(vgg_sd.values())
+        vgg_w = [(vals[2 * i], vals[2 * i + 1]) for i in range(VGG_EXECUTED)]
+        self.vgg_img = ConvStack(vgg_layers(vgg_width_div), vgg_w, B, vgg_res, dev, self.err)
+        self.vgg_rec = ConvStack(vgg_layers(vgg_width_div), vgg_w, B, vgg_res, dev, self.err) if self.cfg.w_lpips_rec != 0.0 else None
+        self.org_feats = [torch.empty_like(t) for t in self.vgg_img.tap_outputs()]
+        self.tgt_feats = [torch.empty_like(t) for t in self.vgg_img.tap_outputs()]
+        self.x, self.x_org, self.x_tgt, self.g_full, self.g_rec = (_empty((B, 3, S, S), dev, torch.float32) for _ in range(5))
+        self.xin, self.g_xin, self.rec_in = (_empty((B, 3, R, R), dev, torch.float32) for _ in range(3))
+        self.loss = _zeros((B,), dev)
+        self.m, self.v = torch.zeros_like(self.x), torch.zeros_like(self.x)
+
+    def _encode(self, x):
+        lib.avgpool_affine_fwd(x, self.xin, self.k_in, 1.0, 0.0)
+        lib.gap_fwd(self.enc.forward(self.xin), self.feat)
+        lib.linear_fwd(self.feat, self.head_w, self.head_b, self.codes.view(self.B, -1))
+
+    def set_inputs(self, img: torch.Tensor, img_target: torch.Tensor):
+        """no_grad setup of optimize_vgg (attack_main2.py:588-603): latents and VGG features of the clean and target image."""
+        self.x_org.copy_(img)
+        self.x_tgt.copy_(img_target)
+        self.x.copy_(img)
+        for src, lat, feats in ((self.x_tgt, self.lat_t, self.tgt_feats), (self.x_org, self.lat_o, self.org_feats)):
+            self._encode(src)
+            lat.copy_(self.codes)
+            self.vgg_img.forward(self.xin)
+            for r, t in zip(feats, self.vgg_img.tap_outputs()):
+                r.copy_(t)
+        self.m.zero_()
+        self.v.zero_()
+
+    def reconstruct(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._encode(self.x if x is None else x)
+        self.syn.styles_from_wplus(self.codes)
+        return self.syn.forward()
+
+    def forward_backward(self):
+        """-> loss (B,), g_xin (pooled-resolution gradient; full-res = g_xin[h/k][w/k]/k^2), g_full (direct full-res term)."""
+        c, B, S = self.cfg, self.B, self.S
+        per = 3 * S * S
+        self.loss.zero_()
+        img_rec = self.reconstruct()
+        lib.mse_f32(self.codes, self.lat_t, self.gcodes, self.loss, c.w_latent_target / self.LD, 2 * c.w_latent_target / self.LD, False)
+        lib.mse_f32(self.codes, self.lat_o, self.gcodes, self.loss, c.w_latent_org / self.LD, 2 * c.w_latent_org / self.LD, True)
+        g_vin = None
+        if self.vgg_rec is not None:
+            lib.avgpool_affine_fwd(img_rec, self.rec_in, self.k_vgg, 1.0, 0.0)
+            self.vgg_rec.forward(self.rec_in)
+            refs = self.tgt_feats if c.lpips_rec_ref == "target" else self.org_feats
+            g_vin = self.vgg_rec.backward(refs, c.w_lpips_rec, self.loss)
+        lib.image_loss_grad(img_rec, self.x_tgt, g_vin, self.g_rec, self.loss, c.w_img_rec_target / per, 2 * c.w_img_rec_target / per,
+                            self.k_vgg)
+        gs = self.syn.backward(self.g_rec)
+        self.syn.wplus_grad_from_styles(gs, self.gw)
+        lib.axpby(self.gcodes, self.gw, self.gcodes, 1.0, 1.0)
+        lib.linear_bwd(self.gcodes.view(B, -1), self.head_w, self.gfeat)
+        lib.gap_bwd(self.enc.out[-1], self.gfeat, self.enc.g[-1])
+        g_enc = self.enc.backward(top_grad_ready=True)
+        if c.w_lpips_img != 0.0:
+            self.vgg_img.forward(self.xin)
+            g_v = self.vgg_img.backward(self.org_feats, c.w_lpips_img, self.loss)
+            lib.axpby(g_enc, g_v, self.g_xin, 1.0, 1.0)
+        else:
+            self.g_xin.copy_(g_enc)
+        lib.image_loss_grad(self.x, self.x_org, None, self.g_full, self.loss, c.w_img_org / per, 2 * c.w_img_org / per, 1)
+        return self.loss, self.g_xin, self.g_full
+
+    def adam_step(self, t: int, lr: float):
+        k = self.k_in
+        lib.attack_update_adam(self.x, self.g_xin, self.m, self.v, lr, t, 1.0 / (k * k), k, gfull=self.g_full, gfull_scale=1.0)
+
+    def full_res_grad(self) -> torch.Tensor:
+        k = self.k_in
+        g = self.g_xin.repeat_interleave(k, 2).repeat_interleave(k, 3) if k > 1 else self.g_xin
+        return g / (k * k) + self.g_full
+
+    def check(self):
+        torch.cuda.synchronize(self.dev)
+        if int(self.err.item()) != 0:
+            raise lib.SfkError("a tensor-core kernel reported an internal pipeline timeout")

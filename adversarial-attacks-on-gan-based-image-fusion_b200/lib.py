@@ -49,7 +49,7 @@ class SfkIgemmDesc(C.Structure):
 EXPORTS = [
     "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
-    "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
+    "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd",
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
     "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_update_patch",
@@ -235,6 +235,12 @@ def mse_tap(f, ref, g, loss, coef_loss, coef_grad, accumulate=False, relu_mask=F
                             C.c_long(per), _stream()), "mse_tap")
 
 
+def mse_f32(a, b, g, loss, coef_loss, coef_grad, accumulate=False):
+    n = a.shape[0]
+    _chk(load().sfk_mse_f32(_p(a), _p(b), _p(g), _p(loss), _f(coef_loss), _f(coef_grad), int(accumulate), n, C.c_long(a.numel() // n), _stream()),
+         "mse_f32")
+
+
 def image_loss_grad(img, ref, gpool, g, loss, coef_loss, coef_grad, k):
     n, _, s, _ = img.shape
     _chk(load().sfk_image_loss_grad(_p(img), _p(ref), _p(gpool), _p(g), _p(loss), _f(coef_loss), _f(coef_grad), n, s, k, _stream()),
@@ -354,9 +360,9 @@ def attack_update_patch(x, x0, patch, mask, gpool, lr, direction, use_sign, lo, 
                                         _p(hi), _f(gscale), _p(stats), n, s, k, _stream()), "attack_update_patch")
 
 
-def attack_update_adam(x, gpool, m, v, lr, t, gscale, k, b1=0.9, b2=0.999, eps=1e-8):
+def attack_update_adam(x, gpool, m, v, lr, t, gscale, k, b1=0.9, b2=0.999, eps=1e-8, gfull=None, gfull_scale=1.0):
     n, _, s, _ = x.shape
-    _chk(load().sfk_attack_update_adam(_p(x), _p(gpool), _p(m), _p(v), _f(lr), _f(b1), _f(b2), _f(eps), int(t), _f(gscale), n, s, k,
+    _chk(load().sfk_attack_update_adam(_p(x), _p(gpool), _p(gfull), _f(gfull_scale), _p(m), _p(v), _f(lr), _f(b1), _f(b2), _f(eps), int(t), _f(gscale), n, s, k,
                                        _stream()), "attack_update_adam")
 
 

@@ -1,0 +1,159 @@
+"""Drop-in for code/style_fusion_simple.py: same constructor, attributes and methods (file:line cited per method).
+The StyleFusion hierarchy of FusionNets (`stylefusion.sf_hierarchy`, un-vendored) is replaced by the documented stand-in of
+SURVEY A.4: parts are blended pairwise in StyleSpace with a learned (here random-init) per-dimension gate, keeping the
+`s_dict` / part-name interface so a real hierarchy can be dropped in later."""
+from __future__ import annotations
+
+import json
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib
+from .generator import Generator
+from .params import make_fusion_params
+
+_PARTS = {   # get_all_active_parts() of the three hierarchies (code/style_fusion_simple.py:62-71, swap lists :89-104)
+    "ffhq": ["all", "bg_hair_clothes", "hair", "face", "eyes", "skin_mouth", "mouth", "skin", "shirt", "background", "background_top",
+             "background_bottom", "bg"],
+    "car": ["all", "wheels", "car", "body", "car_body", "background", "background_top", "background_bottom", "bg"],
+    "church": ["all", "background", "background_top", "background_bottom", "bg"],
+}
+
+
+class _Blender:
+    """stand-in for sf_hierarchy.nodes["all"]"""
+
+    def __init__(self, parts: List[str], s_dim: int, device, seed: int = 2):
+        self.parts, self.device = parts, device
+        self.gates = {p: {k: v.to(device) for k, v in make_fusion_params(s_dim, seed + i).items()} for i, p in enumerate(parts)}
+        self.fusion_net = self
+
+    def get_all_active_parts(self):
+        return list(self.parts)
+
+    def load_fusion_net(self, path, device):      # real FusionNet checkpoints are not loadable by the stand-in
+        return None
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def forward(self, s_dict: Dict[str, list]):
+        cat = lambda s: torch.cat(s, 1).contiguous() if isinstance(s, (list, tuple)) else s
+        out = cat(s_dict[self.parts[0]])
+        for p in self.parts[1:]:
+            if p not in s_dict:
+                continue
+            b = cat(s_dict[p])
+            if b.data_ptr() == out.data_ptr() or torch.equal(b, out):
+                continue
+            g = self.gates[p]
+            res = torch.empty_like(out)
+            lib.fuse_spatial_fwd(out, b, g["alpha"], g["beta"], g["c"], res)
+            out = res
+        return out
+
+
+class _Hierarchy:
+    def __init__(self, blender):
+        self.nodes = {"all": blender}
+
+
+class StyleFusionSimple:
+    def __init__(self, stylegan_type, stylegan_weights, fusion_nets_weights, device, GAN=None):          # style_fusion_simple.py:26
+        self.stylegan_type = stylegan_type
+        self.truncation, self.stylegan_size, self.stylegan_layers = {"ffhq": (0.7, 1024, 18), "car": (0.5, 512, 16),
+                                                                     "church": (0.5, 256, 14)}[stylegan_type]   # :28-39
+        self.device = device
+        if GAN is not None and isinstance(GAN, Generator) and GAN.size == self.stylegan_size:
+            self.original_net = GAN                                                                        # :51 reuses the decoder
+        else:
+            self.original_net = Generator(self.stylegan_size, 512, 8, device=device)
+            if stylegan_weights:
+                self.original_net.load_state_dict(torch.load(stylegan_weights, map_location="cpu")["g_ema"], strict=True)
+        self.original_net.to(self.device)
+        self.mean_latent = self.original_net.mean_latent(4096)                                             # :60
+        blender = _Blender(_PARTS[stylegan_type], self.original_net.spec.s_dim, self.device)
+        self.sf_hierarchy = _Hierarchy(blender)                                                            # :62-71
+        self.base_blender = self.sf_hierarchy.nodes["all"]
+        if fusion_nets_weights:
+            with open(fusion_nets_weights, "r") as f:                                                      # :73-80
+                self.fusion_nets_paths = json.load(f)
+
+    def generate_img(self, base_latent, latents_type="z", hair=None, face=None, background=None, all=None, mouth=None, eyes=None,
+                     wheels=None, car=None, bg_top=None, bg_bottom=None):                                  # :82-108
+        s_dict = dict()
+        for part in self.sf_hierarchy.nodes["all"].get_all_active_parts():
+            s_dict[part] = self.general_latent_to_s(base_latent, latents_type)
+
+        def swap(value, keys):
+            if value is None:
+                return
+            for k in keys:
+                s_dict[k] = self.general_latent_to_s(value, latents_type)
+
+        swap(hair, ["bg_hair_clothes", "hair"])
+        swap(face, ["face", "eyes", "skin_mouth", "mouth", "skin", "shirt"])
+        swap(background, ["background", "background_top", "background_bottom", "bg"])
+        swap(all, ["all"])
+        swap(mouth, ["skin_mouth", "face"])
+        swap(eyes, ["eyes", "face"])
+        swap(wheels, ["wheels"])
+        swap(car, ["car", "body", "wheels", "car_body"])
+        swap(bg_top, ["background_top"])
+        swap(bg_bottom, ["background_bottom"])
+        return self.s_dict_to_image(s_dict)
+
+    def seed_to_z(self, seed):                                                                             # :110-113
+        torch.manual_seed(seed[0])
+        z_regular = torch.randn((seed[1] + 1, 1, 512), device=self.device)
+        return z_regular[seed[1]]
+
+    def z_to_s(self, z):                                                                                   # :115-118
+        return self.original_net([z], truncation=self.truncation, truncation_latent=self.mean_latent, randomize_noise=False,
+                                 return_style_vector=True)
+
+    def z_to_w_plus(self, z):                                                                              # :120-124
+        _, res = self.original_net([z], truncation=self.truncation, truncation_latent=self.mean_latent, randomize_noise=False,
+                                   return_latents=True)
+        return res[0]
+
+    def w_plus_to_s(self, w_plus, truncation):                                                             # :126-129
+        return self.original_net([w_plus], input_is_latent=True, truncation=truncation, truncation_latent=self.mean_latent,
+                                 randomize_noise=False, return_style_vector=True)
+
+    def general_latent_to_s(self, l, latent_type):                                                         # :131-144
+        assert latent_type in ["z", "w", "w+", "s"]
+        if latent_type == "z":
+            assert l.size() == (1, 512)
+            return self.z_to_s(l)
+        elif latent_type == "w" or latent_type == "w+":
+            assert l.size() == (1, 512) or l.size() == (1, self.stylegan_layers, 512)
+            if l.dim() == 2:
+                return self.w_plus_to_s(l.unsqueeze(0).repeat(1, self.stylegan_layers, 1), truncation=1)
+            return self.w_plus_to_s(l, truncation=1)
+        return l
+
+    def s_to_image(self, s):                                                                               # :146-153
+        if torch.is_tensor(s):
+            s = [s[:, l.s_off:l.s_off + l.cin] for l in self.original_net.spec.layers]
+        img, features, _ = self.original_net([torch.zeros(1, 512, device=self.device)], randomize_noise=False, style_vector=s)
+        return img, features
+
+    def w_plus_to_image(self, w_plus):                                                                     # :155-157
+        return self.s_to_image(self.w_plus_to_s(w_plus, truncation=1))
+
+    def z_to_image(self, z):                                                                               # :159-161
+        return self.s_to_image(self.z_to_s(z))
+
+    def s_dict_to_image(self, s_dict):                                                                     # :163-165
+        return self.s_to_image(self.base_blender.forward(s_dict))
+
+    def w_plus_dict_to_image(self, w_plus_dict, truncation=1):                                             # :167-171
+        return self.s_dict_to_image({k: self.w_plus_to_s(v, truncation=truncation) for k, v in w_plus_dict.items()})
+
+    def z_dict_to_image(self, z_dict):                                                                     # :173-177
+        return self.s_dict_to_image({k: self.z_to_s(v) for k, v in z_dict.items()})

@@ -121,6 +121,9 @@ int sfk_mse_tap(const void* f, const void* ref, void* g, float* loss, float coef
                 int accumulate, int relu_mask, int n, long per_sample, sfk_stream_t s);
 /* image term + avg-pool backward of the VGG input gradient:
  *   g[n][c][h][w] = coef_grad*(img-ref) + gpool[n][c][h/k][w/k]/k^2 ; loss[n] += coef_loss*sum((img-ref)^2) */
+/* fp32 variant for latent codes (attack_main2.py:644-645 l_latent_target / l_latent_org) */
+int sfk_mse_f32(const float* a, const float* b, float* g, float* loss, float coef_loss, float coef_grad, int accumulate,
+                int n, long per_sample, sfk_stream_t s);
 int sfk_image_loss_grad(const float* img, const float* ref, const float* gpool, float* g, float* loss,
                         float coef_loss, float coef_grad, int n, int size, int k, sfk_stream_t s);
 
@@ -189,8 +192,9 @@ int sfk_attack_update_linf(float* x, const float* x0, const float* gpool, float 
 int sfk_attack_update_patch(float* x, const float* x0, float* patch, const float* mask, const float* gpool,
                             float lr, float dir, int use_sign, const float* lo, const float* hi, float gscale,
                             float* stats, int n, int size, int k, sfk_stream_t st);
-int sfk_attack_update_adam(float* x, const float* gpool, float* m, float* v, float lr, float b1, float b2,
-                           float eps, int t, float gscale, int n, int size, int k, sfk_stream_t st);
+/* gfull (optional): an additional full-resolution gradient term, g = gscale*gpool[h/k][w/k] + gfull_scale*gfull */
+int sfk_attack_update_adam(float* x, const float* gpool, const float* gfull, float gfull_scale, float* m, float* v, float lr,
+                           float b1, float b2, float eps, int t, float gscale, int n, int size, int k, sfk_stream_t st);
 /* l2: norms[n] = sum g^2 (phase 0); x' = x + dir*alpha*g/|g|, dn[n] = sum (x'-x0)^2 (phase 1);
  *     x = clamp(x0 + (x'-x0)*min(1, eps/|d|), lo, hi) (phase 2) */
 int sfk_attack_update_l2(float* x, const float* x0, const float* gpool, float* norms, float* dn, float alpha,

@@ -261,3 +261,48 @@ def success_metrics(fused_adv, fused_clean, pipe: OraclePipeline):
         fa, fc = pipe.features(fused_adv), pipe.features(fused_clean)
         vg = sum(per_sample_mse(a, c) for a, c in zip(fa, fc))
     return mse, vg
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ReconLossCfg:
+    """weights of optimize_vgg's `inversion_loss` (attack_main2.py:649; variants interpolation.py:818, inter_copy.py:658)"""
+    w_latent_target: float = 10.0
+    w_latent_org: float = -1.0
+    w_img_rec_target: float = 1.0
+    w_img_org: float = 20.0
+    w_lpips_img: float = 1.0
+    w_lpips_rec: float = 0.0
+    lpips_rec_ref: str = "target"
+
+
+def optimize_vgg_oracle(gspec, GP, espec, EP, vgg_sd, img, img_target, cfg: ReconLossCfg, n_iters: int, lr: float,
+                        record=None):
+    """Restatement of the reference's live loop (attack_main2.py:584-671): Adam on the pixels of `img` ([-1,1]) against the
+    encoder->decoder reconstruction; per-sample means (the reference runs batch 1).  No file I/O."""
+    k = gspec.size // espec.in_res
+    pool = (lambda t: F.avg_pool2d(t, k, k)) if k > 1 else (lambda t: t)
+    img_org = img.clone().detach()
+    with torch.no_grad():                                                    # :597-603
+        latent_target = encoder_forward(EP, espec, pool(img_target))
+        latent_org = encoder_forward(EP, espec, pool(img_org))
+        f_target = vgg_forward(vgg_sd, pool(img_target))
+        f_org = vgg_forward(vgg_sd, pool(img_org))
+    x = img.clone().detach().requires_grad_(True)
+    opt = torch.optim.Adam([x], lr=lr)                                       # :606
+    for it in range(n_iters):
+        opt.zero_grad()
+        lat = encoder_forward(EP, espec, pool(x))                            # :619,622 (evaluated once; same value)
+        img_rec = sg.synthesis_from_styles(GP, gspec, sg.styles_from_wplus(GP, gspec, lat))
+        L = cfg.w_latent_target * per_sample_mse(lat, latent_target) + cfg.w_latent_org * per_sample_mse(lat, latent_org)
+        L = L + cfg.w_img_rec_target * per_sample_mse(img_rec, img_target) + cfg.w_img_org * per_sample_mse(x, img_org)
+        if cfg.w_lpips_img != 0.0:
+            L = L + cfg.w_lpips_img * sum(per_sample_mse(a, b) for a, b in zip(vgg_forward(vgg_sd, pool(x)), f_org))
+        if cfg.w_lpips_rec != 0.0:
+            refs = f_target if cfg.lpips_rec_ref == "target" else f_org
+            L = L + cfg.w_lpips_rec * sum(per_sample_mse(a, b) for a, b in zip(vgg_forward(vgg_sd, pool(img_rec)), refs))
+        L.sum().backward()
+        if record is not None:
+            record.append(dict(loss=L.detach().clone(), grad=x.grad.detach().clone(), img_rec=img_rec.detach().clone()))
+        opt.step()
+    return x.detach()

@@ -1,0 +1,106 @@
+"""CPU tests of the host-side logic that feeds the kernels: tap lists (emulated on CPU against torch convs), model tables,
+sharding over ranks with a real 2-process gloo group."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def emulate_igemm(A, Wt, taps, out_hw, num_acc, out_c):
+    """CPU model of the sfk_igemm contract: A (N,P,H,W,C), Wt (rows, C): out[n,acc,h,w,:] += A[n,plane,h+dy,w+dx,:] @ Wt[brow:brow+out_c].T"""
+    N, P, H, W, C = A.shape
+    oh, ow = out_hw
+    out = torch.zeros(N, num_acc, oh, ow, out_c, dtype=A.dtype)
+    Ap = F.pad(A, [0, 0, 4, 4, 4, 4])
+    for dy, dx, plane, acc, brow in taps:
+        win = Ap[:, plane, 4 + dy:4 + dy + oh, 4 + dx:4 + dx + ow, :]
+        if win.shape[1] < oh or win.shape[2] < ow:
+            win = F.pad(win, [0, 0, 0, ow - win.shape[2], 0, oh - win.shape[1]])
+        out[:, acc] += torch.einsum("nhwc,oc->nhwo", win, Wt[brow:brow + out_c])
+    return out
+
+
+def test_tap_lists_reproduce_conv_dgrad_tconv_and_its_transpose():
+    from sfattack import lib
+    g = torch.Generator().manual_seed(0)
+    N, H, Cin, Cout = 2, 6, 5, 4
+    x = torch.randn(N, Cin, H, H, generator=g, dtype=torch.double)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, dtype=torch.double)
+    A = x.permute(0, 2, 3, 1)[:, None]
+    Wf = w.permute(2, 3, 0, 1).reshape(9 * Cout, Cin)
+    got = emulate_igemm(A, Wf, lib.conv3x3_taps(Cout), (H, H), 1, Cout)[:, 0].permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, F.conv2d(x, w, padding=1))
+    gz = torch.randn(N, Cout, H, H, generator=g, dtype=torch.double)
+    Wb = w.permute(2, 3, 1, 0).reshape(9 * Cin, Cout)
+    got = emulate_igemm(gz.permute(0, 2, 3, 1)[:, None], Wb, lib.conv3x3_dgrad_taps(Cin), (H, H), 1, Cin)[:, 0].permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, F.conv_transpose2d(gz, w, padding=1))
+    # stride-2 transposed conv as 4 phase planes of (H+1)^2
+    T = emulate_igemm(A, Wf, lib.tconv_taps(Cout), (H + 1, H + 1), 4, Cout)
+    full = torch.zeros(N, 2 * H + 2, 2 * H + 2, Cout, dtype=torch.double)
+    for a in (0, 1):
+        for b in (0, 1):
+            full[:, a::2, b::2] = T[:, 2 * a + b]
+    ref = F.conv_transpose2d(x, w.permute(1, 0, 2, 3), stride=2)
+    torch.testing.assert_close(full[:, :2 * H + 1, :2 * H + 1].permute(0, 3, 1, 2), ref)
+    # ... and its transpose, read back from the phase planes
+    gT = torch.randn(N, Cout, 2 * H + 1, 2 * H + 1, generator=g, dtype=torch.double)
+    gTp = F.pad(gT, [0, 1, 0, 1]).permute(0, 2, 3, 1)
+    planes = torch.stack([gTp[:, a::2, b::2] for a in (0, 1) for b in (0, 1)], 1)
+    got = emulate_igemm(planes, Wb, lib.tconv_dgrad_taps(Cin), (H, H), 1, Cin)[:, 0].permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, F.conv2d(gT, w.permute(1, 0, 2, 3), stride=2))
+
+
+def test_model_tables_and_flop_accounting():
+    import bench
+    from sfattack.params import EncSpec, gen_spec
+    spec = gen_spec(1024)
+    fl = bench.flops_per_iter_image(spec, EncSpec(n_latent=18))
+    assert abs(fl["generator_fwd"] / 1e9 - 148.52) < 0.5
+    assert abs(fl["vgg_fwd"] / 1e9 - 31.63) < 0.1
+    assert abs(fl["attack"] / 1e9 - 360.3) < 1.0
+    assert [gen_spec(s).n_latent for s in (256, 512, 1024)] == [14, 16, 18]
+    from sfattack.engine import vgg_layers
+    taps = [l.tap for l in vgg_layers() if l.tap >= 0]
+    assert taps == [0, 1, 2, 3] and [l.kind for l in vgg_layers()].count("pool") == 3
+
+
+def test_block_n_and_patch_utils():
+    from sfattack import lib
+    from sfattack.attack.patch.adversarial_patch_util import init_patch_square, square_transform, submatrix
+    assert lib.pick_block_n(512) == 128 and lib.pick_block_n(32) == 32 and lib.pick_block_n(256, 4) == 128 and 4 * lib.pick_block_n(512, 4) <= 512
+    patch, shape = init_patch_square(512, 0.1)
+    assert shape == (1, 3, 161, 161)                            # floor(sqrt(0.1)*512) = 161
+    canvas, mask = square_transform(patch, (2, 3, 512, 512), shape, 512)
+    assert mask.sum() == 2 * 3 * 161 * 161 and canvas.shape == (2, 3, 512, 512)
+    assert submatrix(canvas[0, 0]).shape == (161, 161)
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    from sfattack.parallel import gather_results, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(7, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None] * torch.ones(1, 3)
+    full = gather_results(local, 7)
+    out.put((rank, lo, hi, full[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_final_gather_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    from sfattack.parallel import shard_range
+    assert [shard_range(7, r, 2) for r in range(2)] == [(0, 4), (4, 7)]
+    assert [shard_range(64, r, 8) for r in range(8)][-1] == (56, 64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, 29533, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert res[0][1:3] == (0, 4) and res[1][1:3] == (4, 7)
+    assert res[0][3] == res[1][3] == [float(i) for i in range(7)]
