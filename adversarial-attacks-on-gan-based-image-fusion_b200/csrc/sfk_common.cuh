@@ -55,6 +55,38 @@ __device__ __forceinline__ bf16x8 ldg8(const void* p) { return __ldg(reinterpret
 __device__ __forceinline__ bf16x8 ld8(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg8(void* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// ---- storage-type generic 8-element vectors: activations are bf16 (product path) or fp32 (parity mode, sfk_set_activation_dtype)
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) { unpack8(ldg8(p), f); }
+__device__ __forceinline__ void load8p(const __nv_bfloat16* p, float* f) { unpack8(ld8(p), f); }
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) { stg8(p, pack8(f)); }
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8p(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ void from_f32(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void from_f32(float* p, float v) { *p = v; }
+
+// activation storage mode of the library: 0 = bf16 (default), 1 = fp32 (parity mode; tensor-core conv unavailable)
+int sfk_act_f32();
+#define SFK_ACT_DISPATCH(CALL_BF16, CALL_F32) \
+  do {                                          \
+    if (sfk_act_f32()) {                        \
+      CALL_F32;                                 \
+    } else {                                    \
+      CALL_BF16;                                \
+    }                                           \
+  } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

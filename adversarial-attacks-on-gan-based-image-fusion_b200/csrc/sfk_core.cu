@@ -22,3 +22,11 @@ int sfk_check_launch(const char* what) {
 
 extern "C" int sfk_version(void) { return 100; }
 extern "C" const char* sfk_last_error_string(void) { return g_err; }
+
+static int g_act_f32 = 0;
+int sfk_act_f32() { return g_act_f32; }
+extern "C" int sfk_set_activation_dtype(int f32) {
+  g_act_f32 = f32 ? 1 : 0;
+  return 0;
+}
+extern "C" int sfk_get_activation_dtype(void) { return g_act_f32; }

@@ -28,8 +28,9 @@ __device__ __forceinline__ void flush_channel_acc(float* sacc, const float* acc,
 
 // ============================================================================================
 // first-layer conv (Cin = 3)
+template <typename T>
 __global__ void conv_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                   bf16* __restrict__ out, int N, int H, int W, int Cout, int relu) {
+                                   T* __restrict__ out, int N, int H, int W, int Cout, int relu) {
   extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
     const int co = i % Cout, k = i / Cout;  // k = c*9 + ky*3 + kx
@@ -72,11 +73,12 @@ __global__ void conv_c3_fwd_kernel(const float* __restrict__ x, const float* __r
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
     }
-    stg8(out + ((static_cast<long>(n) * H + hq) * W + wq) * Cout + g * 8, pack8(acc));
+    store8(out + ((static_cast<long>(n) * H + hq) * W + wq) * Cout + g * 8, acc);
   }
 }
 
-__global__ void conv_c3_bwd_kernel(const bf16* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int N,
+template <typename T>
+__global__ void conv_c3_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int N,
                                    int H, int W, int Cout, int LP /* lanes per pixel, power of 2 <= 8 */) {
   extern __shared__ float sw[];  // [9][Cout][3]
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
@@ -105,11 +107,11 @@ __global__ void conv_c3_bwd_kernel(const bf16* __restrict__ g, const float* __re
         for (int kx = 0; kx < 3; ++kx) {
           const int ow = wq - kx + 1;
           if (ow < 0 || ow >= W) continue;
-          const bf16* gp = g + ((static_cast<long>(n) * H + oh) * W + ow) * Cout;
+          const T* gp = g + ((static_cast<long>(n) * H + oh) * W + ow) * Cout;
           const float* wp = sw + (ky * 3 + kx) * Cout * 3;
           for (int v = sub; v < vecs; v += LP) {
             float gv[8];
-            unpack8(ldg8(gp + v * 8), gv);
+            load8(gp + v * 8, gv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float* w3 = wp + (v * 8 + i) * 3;
@@ -157,7 +159,8 @@ __global__ void avgpool_affine_kernel(const float* __restrict__ x, float* __rest
   }
 }
 
-__global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C) {
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, vecs = C / 8;
   const long total = static_cast<long>(N) * Ho * Wo * vecs;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
@@ -178,19 +181,20 @@ __global__ void maxpool2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict
         const int w = 2 * j + dx;
         if (w >= W) continue;
         float t[8];
-        unpack8(ldg8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8), t);
+        load8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8, t);
 #pragma unroll
         for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], t[q]);
       }
     }
-    stg8(y + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8, pack8(m));
+    store8(y + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8, m);
   }
 }
 
 // One thread per pooling window x 8 channels: routes gy to the FIRST maximum in row-major window order
 // (torch's tie-break; ties are common in bf16), adds the optional feature-tap gradient, applies the ReLU mask.
-__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy, bf16* __restrict__ gx,
-                                    const bf16* __restrict__ tap_ref, float tap_coef, int relu_mask, int N, int H, int W, int C) {
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx,
+                                    const T* __restrict__ tap_ref, float tap_coef, int relu_mask, int N, int H, int W, int C) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, vecs = C / 8;
   const long total = static_cast<long>(N) * Ho * Wo * vecs;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
@@ -215,7 +219,7 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
       const int h = 2 * i + (s >> 1), w = 2 * j + (s & 1);
       inb[s] = (h < H) && (w < W);
       if (inb[s]) {
-        unpack8(ldg8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8), xin[s]);
+        load8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8, xin[s]);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (xin[s][q] > m[q]) {
@@ -226,7 +230,7 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
       }
     }
     float g[8];
-    unpack8(ldg8(gy + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8), g);
+    load8(gy + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8, g);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       if (!inb[s]) continue;
@@ -237,7 +241,7 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
       for (int q = 0; q < 8; ++q) o[q] = (am[q] == s) ? g[q] : 0.f;
       if (tap_ref) {
         float r[8];
-        unpack8(ldg8(tap_ref + off), r);
+        load8(tap_ref + off, r);
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] += tap_coef * (xin[s][q] - r[q]);
       }
@@ -245,19 +249,20 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] = xin[s][q] > 0.f ? o[q] : 0.f;
       }
-      stg8(gx + off, pack8(o));
+      store8(gx + off, o);
     }
   }
 }
 
-__global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ y, int HW, int C) {
+template <typename T>
+__global__ void gap_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int HW, int C) {
   // block = (n, channel-vector group); threads stride over HW
   const int n = blockIdx.y, vecs = C / 8;
   const int v = blockIdx.x;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
     float t[8];
-    unpack8(ldg8(x + (static_cast<long>(n) * HW + p) * C + v * 8), t);
+    load8(x + (static_cast<long>(n) * HW + p) * C + v * 8, t);
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] += t[q];
   }
@@ -276,7 +281,8 @@ __global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ y
   (void)vecs;
 }
 
-__global__ void gap_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gy, bf16* __restrict__ gx, int N, int HW, int C) {
+template <typename T>
+__global__ void gap_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gy, T* __restrict__ gx, int N, int HW, int C) {
   const int vecs = C / 8;
   const long total = static_cast<long>(N) * HW * vecs;
   const float inv = 1.f / static_cast<float>(HW);
@@ -286,16 +292,17 @@ __global__ void gap_bwd_kernel(const bf16* __restrict__ x, const float* __restri
     const long p = idx / vecs;
     const int n = p / HW;
     float t[8], o[8];
-    unpack8(ldg8(x + p * C + v * 8), t);
+    load8(x + p * C + v * 8, t);
 #pragma unroll
     for (int q = 0; q < 8; ++q) o[q] = t[q] > 0.f ? gy[static_cast<long>(n) * C + v * 8 + q] * inv : 0.f;
-    stg8(gx + p * C + v * 8, pack8(o));
+    store8(gx + p * C + v * 8, o);
   }
 }
 
 // ============================================================================================
 // losses
-__global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restrict__ ref, bf16* __restrict__ g, float* __restrict__ loss,
+template <typename T>
+__global__ void mse_tap_kernel(const T* __restrict__ f, const T* __restrict__ ref, T* __restrict__ g, float* __restrict__ loss,
                                float coef_loss, float coef_grad, int accumulate, int relu_mask, long per_sample) {
   const int n = blockIdx.y;
   const long vecs = per_sample / 8;
@@ -303,10 +310,10 @@ __global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restric
   float lsum = 0.f;
   for (long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; v < vecs; v += static_cast<long>(gridDim.x) * blockDim.x) {
     float a[8], r[8];
-    unpack8(ldg8(f + base + v * 8), a);
-    unpack8(ldg8(ref + base + v * 8), r);
+    load8(f + base + v * 8, a);
+    load8(ref + base + v * 8, r);
     float o[8];
-    if (g && accumulate) unpack8(ld8(g + base + v * 8), o);
+    if (g && accumulate) load8p(g + base + v * 8, o);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float d = a[q] - r[q];
@@ -315,7 +322,7 @@ __global__ void mse_tap_kernel(const bf16* __restrict__ f, const bf16* __restric
       if (relu_mask && !(a[q] > 0.f)) gq = 0.f;
       o[q] = (g && accumulate) ? o[q] + gq : gq;
     }
-    if (g) stg8(g + base + v * 8, pack8(o));
+    if (g) store8(g + base + v * 8, o);
   }
   lsum = warp_sum(lsum);
   __shared__ float red[kBlock / 32];
@@ -467,7 +474,8 @@ __global__ void demod_bwd_kernel(const float* __restrict__ s, int s_stride, cons
   (void)N;
 }
 
-__global__ void modulate_weights_kernel(const float* __restrict__ wbase, const float* __restrict__ s, int s_stride, bf16* __restrict__ wmod,
+template <typename T>
+__global__ void modulate_weights_kernel(const float* __restrict__ wbase, const float* __restrict__ s, int s_stride, T* __restrict__ wmod,
                                         int N, long rows /* taps*cout */, int Cin) {
   const int vecs = Cin / 8;
   const long total = static_cast<long>(N) * rows * vecs;
@@ -480,7 +488,7 @@ __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const f
     const float4* sp = reinterpret_cast<const float4*>(s + static_cast<long>(n) * s_stride + v * 8);
     const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
     float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
-    stg8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, pack8(o));
+    store8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, o);
   }
 }
 
@@ -544,6 +552,84 @@ __device__ __forceinline__ void blur_block_2x4(int row0, int col0, Load&& ld, fl
 //                  register-blocked FIR above (35 LDS.128 per 8 outputs);
 //   bank layout  : positions are 64 B (CV=4 channel vectors) apart with 64 B of padding after every 4th one, so the two
 //                  column blocks served in one LDS.128 phase fall into different halves of the 32 banks.
+// Straightforward (one thread = one position x 8 channels, 16 taps) versions of the blur and its transpose, generic in the
+// storage type: used by the fp32 parity mode (sfk_set_activation_dtype(1)), where speed is irrelevant.
+template <typename T>
+__global__ void blur_simple_fwd_kernel(const T* __restrict__ Tn_, T* __restrict__ out, const float* __restrict__ d, const float* __restrict__ noise,
+                                       float noise_w, const float* __restrict__ bias, int H, int W, int C) {
+  const int n = blockIdx.y;
+  const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1;
+  const long total = static_cast<long>(Ho) * Wo * vecs;
+  const T* Tn = Tn_ + static_cast<long>(n) * 4 * Hp * Wp * C;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    const long p = idx / vecs;
+    const int pw = p % Wo, po = p / Wo;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < 4; ++t) {
+      const int q = po + t - 1;
+      if (q < 0 || q > 2 * H) continue;
+      for (int u = 0; u < 4; ++u) {
+        const int r = pw + u - 1;
+        if (r < 0 || r > 2 * W) continue;
+        float tv[8];
+        load8(Tn + ((static_cast<long>((q & 1) * 2 + (r & 1)) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + v * 8, tv);
+        const float wgt = blur_w(t) * blur_w(u);
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, tv[i], acc[i]);
+      }
+    }
+    const float nz = noise ? noise_w * noise[static_cast<long>(po) * Wo + pw] : 0.f;
+    float o[8];
+    for (int i = 0; i < 8; ++i) o[i] = lrelu_fwd(fmaf(acc[i], d[static_cast<long>(n) * C + v * 8 + i], nz + bias[v * 8 + i]));
+    store8(out + ((static_cast<long>(n) * Ho + po) * Wo + pw) * C + v * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void blur_simple_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout, T* __restrict__ gT, const float* __restrict__ d,
+                                       const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
+                                       int H, int W, int C) {
+  const int n = blockIdx.y;
+  const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1, Hq = 2 * H + 2, Wq = 2 * W + 2;
+  const long total = static_cast<long>(Hq) * Wq * vecs;
+  const T* on = out + static_cast<long>(n) * Ho * Wo * C;
+  const T* gn = gout + static_cast<long>(n) * Ho * Wo * C;
+  T* gTn = gT + static_cast<long>(n) * 4 * Hp * Wp * C;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    const long p = idx / vecs;
+    const int r = p % Wq, q = p / Wq;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (q <= 2 * H && r <= 2 * W) {
+      for (int t = 0; t < 4; ++t) {
+        const int o = q - t + 1;
+        if (o < 0 || o >= Ho) continue;
+        for (int u = 0; u < 4; ++u) {
+          const int pw = r - u + 1;
+          if (pw < 0 || pw >= Wo) continue;
+          const long off = (static_cast<long>(o) * Wo + pw) * C + v * 8;
+          float ov[8], gv[8];
+          load8(on + off, ov);
+          load8(gn + off, gv);
+          const float wgt = blur_w(t) * blur_w(u);
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt * lrelu_slope(ov[i]), gv[i], acc[i]);
+        }
+      }
+      if (q < Ho && r < Wo) {
+        const long off = (static_cast<long>(q) * Wo + r) * C + v * 8;
+        float ov[8], gv[8];
+        load8(on + off, ov);
+        load8(gn + off, gv);
+        const float nz = noise ? noise_w * noise[static_cast<long>(q) * Wo + r] : 0.f;
+        for (int i = 0; i < 8; ++i)
+          atomicAdd(gdacc + static_cast<long>(n) * C + v * 8 + i, gv[i] * lrelu_slope(ov[i]) * (lrelu_inv(ov[i]) - nz - bias[v * 8 + i]));
+      }
+    }
+    for (int i = 0; i < 8; ++i) acc[i] *= d[static_cast<long>(n) * C + v * 8 + i];
+    store8(gTn + ((static_cast<long>((q & 1) * 2 + (r & 1)) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + v * 8, acc);
+  }
+}
+
 struct BlurGeom {
   int CV, bc, TC, pitch;   // channel vectors per position, column blocks per tile, tile columns, padded positions per row
 };
@@ -603,8 +689,8 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
         if (q >= 0 && q < Ho && rr >= 0 && rr < Wo) {
           const long off = (static_cast<long>(q) * Wo + rr) * C + cvec * 8;
           float ov[8], gv[8];
-          unpack8(ldg8(s0 + off), ov);
-          unpack8(ldg8(s1 + off), gv);
+          load8(s0 + off, ov);
+          load8(s1 + off, gv);
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) gv[cc] *= lrelu_slope(ov[cc]);
           if (r >= 2 && r < 18 && c >= 2 && c < 2 + TC) {   // the tile's own pixels: demodulation reduction
@@ -633,12 +719,12 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
           const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(q) * Wo + rr) : 0.f;
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = lrelu_fwd(fmaf(acc[i][j][c], dv[c], nz + bv[c]));
-          stg8(dn + (static_cast<long>(q) * Wo + rr) * C + cvec * 8, pack8(o));
+          store8(dn + (static_cast<long>(q) * Wo + rr) * C + cvec * 8, o);
         } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = acc[i][j][c] * dv[c];
           const int plane = (q & 1) * 2 + (rr & 1);
-          stg8(dn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (rr >> 1)) * C + cvec * 8, pack8(o));
+          store8(dn + ((static_cast<long>(plane) * Hp + (q >> 1)) * Wp + (rr >> 1)) * C + cvec * 8, o);
         }
       }
     }
@@ -662,7 +748,8 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
   (void)sred;
 }
 
-__global__ void act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restrict__ gout, bf16* __restrict__ gz, const float* __restrict__ d,
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout, T* __restrict__ gz, const float* __restrict__ d,
                                const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc, int HW, int C) {
   extern __shared__ float sacc[];
   const int n = blockIdx.y;
@@ -682,8 +769,8 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restr
     const long p = idx / vecs;
     const long off = base + p * C + cv * 8;
     float ov[8], gv[8], o[8];
-    unpack8(ldg8(out + off), ov);
-    unpack8(ld8(gout + off), gv);   // gz may alias gout (in-place)
+    load8(out + off, ov);
+    load8p(gout + off, gv);   // gz may alias gout (in-place)
     const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -691,7 +778,7 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ out, const bf16* __restr
       racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
       o[i] = gy * dv[i];
     }
-    stg8(gz + off, pack8(o));
+    store8(gz + off, o);
   }
   flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
 }
@@ -714,7 +801,8 @@ __device__ __forceinline__ float skip_up_sample(const float* __restrict__ sk, in
 }
 
 // LP lanes cooperate on one pixel (LP = min(32, C/8)), each lane owns channel vectors lane, lane+LP, ...
-__global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
+template <typename T>
+__global__ void torgb_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
                                  const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ rgb, int H, int W, int C, int LP) {
   extern __shared__ float swm[];  // [3][C] modulated weights of this sample
   const int n = blockIdx.y;
@@ -732,10 +820,10 @@ __global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __rest
     const long p = idx / LP;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (active) {
-      const bf16* xp = x + (static_cast<long>(n) * HW + p) * C;
+      const T* xp = x + (static_cast<long>(n) * HW + p) * C;
       for (int v = sub; v < vecs; v += LP) {
         float xv[8];
-        unpack8(ldg8(xp + v * 8), xv);
+        load8(xp + v * 8, xv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int c = v * 8 + i;
@@ -768,8 +856,9 @@ __global__ void torgb_fwd_kernel(const bf16* __restrict__ x, const float* __rest
   }
 }
 
-__global__ void torgb_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
-                                 const float* __restrict__ grgb, bf16* __restrict__ gx, float* __restrict__ gs, int gs_stride, int HW, int C) {
+template <typename T>
+__global__ void torgb_bwd_kernel(const T* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
+                                 const float* __restrict__ grgb, T* __restrict__ gx, float* __restrict__ gs, int gs_stride, int HW, int C) {
   extern __shared__ float sm[];  // [3][C] weights, then [C] accumulators
   float* sw = sm;
   float* sacc = sm + 3 * C;
@@ -795,14 +884,14 @@ __global__ void torgb_bwd_kernel(const bf16* __restrict__ x, const float* __rest
     const float ga = __ldg(g0 + p), gb = __ldg(g0 + HW + p), gc = __ldg(g0 + 2L * HW + p);
     const long off = (static_cast<long>(n) * HW + p) * C + cv * 8;
     float xv[8], o[8];
-    unpack8(ldg8(x + off), xv);
+    load8(x + off, xv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float gt = w0[i] * ga + w1[i] * gb + w2[i] * gc;
       racc[i] = fmaf(xv[i], gt, racc[i]);
       o[i] = sv[i] * gt;
     }
-    stg8(gx + off, pack8(o));
+    store8(gx + off, o);
   }
   flush_channel_acc(sacc, racc, cv, C, gs + static_cast<long>(n) * gs_stride);
 }
@@ -906,7 +995,8 @@ __global__ void axpby_kernel(const float* x, const float* y, float* out, float a
     out[i] = a * x[i] + (y ? b * y[i] : 0.f);
 }
 
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int N, int C, int H, int W) {
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int H, int W) {
   const long total = static_cast<long>(N) * H * W * C;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
     const int c = idx % C;
@@ -915,10 +1005,11 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restric
     p /= W;
     const int h = p % H;
     const int n = p / H;
-    y[idx] = __float2bfloat16(x[((static_cast<long>(n) * C + c) * H + h) * W + w]);
+    from_f32(&y[idx], x[((static_cast<long>(n) * C + c) * H + h) * W + w]);
   }
 }
-__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W) {
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int H, int W) {
   const long total = static_cast<long>(N) * H * W * C;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
     const int w = idx % W;
@@ -927,7 +1018,7 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restric
     p /= H;
     const int c = p % C;
     const int n = p / C;
-    y[idx] = __bfloat162float(x[((static_cast<long>(n) * H + h) * W + w) * C + c]);
+    y[idx] = to_f32(x[((static_cast<long>(n) * H + h) * W + w) * C + c]);
   }
 }
 
@@ -1112,8 +1203,14 @@ int sfk_conv_c3_fwd(const float* x, const float* w, const float* bias, void* out
   SFK_REQUIRE(x && w && out, SFK_E_ARG, "conv_c3_fwd: null");
   SFK_REQUIRE(cout % 8 == 0 && cout <= 512, SFK_E_SHAPE, "conv_c3_fwd: cout must be a multiple of 8, <= 512");
   const size_t smem = static_cast<size_t>(28 * cout) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  conv_c3_fwd_kernel<<<grid_for(static_cast<long>(n) * h * w_ * (cout / 8)), kBlock, smem, S_(s)>>>(x, w, bias, static_cast<bf16*>(out), n, h, w_, cout, relu);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      conv_c3_fwd_kernel<T><<<grid_for(static_cast<long>(n) * h * w_ * (cout / 8)), kBlock, smem, S_(s)>>>(x, w, bias, static_cast<T*>(out), n, h, w_, cout, relu);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("conv_c3_fwd");
 }
 
@@ -1123,8 +1220,14 @@ int sfk_conv_c3_bwd(const void* g, const float* w, float* gx, int n, int h, int 
   int lp = 1;
   while (lp < 8 && lp * 2 <= cout / 8) lp *= 2;
   const size_t smem = static_cast<size_t>(27 * cout) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  conv_c3_bwd_kernel<<<grid_for(static_cast<long>(n) * h * w_ * lp), kBlock, smem, S_(s)>>>(static_cast<const bf16*>(g), w, gx, n, h, w_, cout, lp);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      conv_c3_bwd_kernel<T><<<grid_for(static_cast<long>(n) * h * w_ * lp), kBlock, smem, S_(s)>>>(static_cast<const T*>(g), w, gx, n, h, w_, cout, lp);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("conv_c3_bwd");
 }
 
@@ -1136,8 +1239,14 @@ int sfk_avgpool_affine_fwd(const float* x, float* y, int n_planes, int h, int w,
 
 int sfk_maxpool2_fwd(const void* x, void* y, int n, int h, int w, int c, sfk_stream_t s) {
   SFK_REQUIRE(x && y && c % 8 == 0, SFK_E_ARG, "maxpool2_fwd: bad args");
-  maxpool2_fwd_kernel<<<grid_for(static_cast<long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), kBlock, 0, S_(s)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(y), n, h, w, c);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      maxpool2_fwd_kernel<T><<<grid_for(static_cast<long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), kBlock, 0, S_(s)>>>(
+      static_cast<const T*>(x), static_cast<T*>(y), n, h, w, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("maxpool2_fwd");
 }
 
@@ -1145,30 +1254,54 @@ int sfk_maxpool2_bwd(const void* x, const void* y, const void* gy, void* gx, con
                      int w, int c, sfk_stream_t s) {
   (void)y;
   SFK_REQUIRE(x && gy && gx && c % 8 == 0, SFK_E_ARG, "maxpool2_bwd: bad args");
-  maxpool2_bwd_kernel<<<grid_for(static_cast<long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), kBlock, 0, S_(s)>>>(
-      static_cast<const bf16*>(x), static_cast<const bf16*>(gy), static_cast<bf16*>(gx), static_cast<const bf16*>(tap_ref), tap_coef, relu_mask,
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      maxpool2_bwd_kernel<T><<<grid_for(static_cast<long>(n) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), kBlock, 0, S_(s)>>>(
+      static_cast<const T*>(x), static_cast<const T*>(gy), static_cast<T*>(gx), static_cast<const T*>(tap_ref), tap_coef, relu_mask,
       n, h, w, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("maxpool2_bwd");
 }
 
 int sfk_gap_fwd(const void* x, float* y, int n, int hw, int c, sfk_stream_t s) {
   SFK_REQUIRE(x && y && c % 8 == 0, SFK_E_ARG, "gap_fwd: bad args");
-  gap_fwd_kernel<<<dim3(c / 8, n), kBlock, 0, S_(s)>>>(static_cast<const bf16*>(x), y, hw, c);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      gap_fwd_kernel<T><<<dim3(c / 8, n), kBlock, 0, S_(s)>>>(static_cast<const T*>(x), y, hw, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("gap_fwd");
 }
 
 int sfk_gap_bwd(const void* x, const float* gy, void* gx, int n, int hw, int c, sfk_stream_t s) {
   SFK_REQUIRE(x && gy && gx && c % 8 == 0, SFK_E_ARG, "gap_bwd: bad args");
-  gap_bwd_kernel<<<grid_for(static_cast<long>(n) * hw * (c / 8)), kBlock, 0, S_(s)>>>(static_cast<const bf16*>(x), gy, static_cast<bf16*>(gx), n, hw, c);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      gap_bwd_kernel<T><<<grid_for(static_cast<long>(n) * hw * (c / 8)), kBlock, 0, S_(s)>>>(static_cast<const T*>(x), gy, static_cast<T*>(gx), n, hw, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("gap_bwd");
 }
 
 int sfk_mse_tap(const void* f, const void* ref, void* g, float* loss, float coef_loss, float coef_grad, int accumulate, int relu_mask, int n,
                 long per_sample, sfk_stream_t s) {
   SFK_REQUIRE(f && ref && per_sample % 8 == 0, SFK_E_ARG, "mse_tap: bad args");
-  mse_tap_kernel<<<dim3(per_sample_blocks(per_sample / 8, n), n), kBlock, 0, S_(s)>>>(static_cast<const bf16*>(f), static_cast<const bf16*>(ref),
-                                                                                      static_cast<bf16*>(g), loss, coef_loss, coef_grad, accumulate,
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      mse_tap_kernel<T><<<dim3(per_sample_blocks(per_sample / 8, n), n), kBlock, 0, S_(s)>>>(static_cast<const T*>(f), static_cast<const T*>(ref),
+                                                                                      static_cast<T*>(g), loss, coef_loss, coef_grad, accumulate,
                                                                                       relu_mask, per_sample);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("mse_tap");
 }
 
@@ -1218,12 +1351,27 @@ int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void
   SFK_REQUIRE(wbase && sv && wmod && cin % 8 == 0 && s_stride % 4 == 0, SFK_E_ARG, "modulate_weights: bad args");
   SFK_REQUIRE(sfk_aligned16(wbase) && sfk_aligned16(sv) && sfk_aligned16(wmod), SFK_E_ALIGN, "modulate_weights: alignment");
   const long rows = static_cast<long>(taps) * cout;
-  modulate_weights_kernel<<<grid_for(static_cast<long>(n) * rows * (cin / 8)), kBlock, 0, S_(st)>>>(wbase, sv, s_stride, static_cast<bf16*>(wmod), n, rows, cin);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      modulate_weights_kernel<T><<<grid_for(static_cast<long>(n) * rows * (cin / 8)), kBlock, 0, S_(st)>>>(wbase, sv, s_stride, static_cast<T*>(wmod), n, rows, cin);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("modulate_weights");
 }
 
 static int blur_launch(bool bwd, const void* a0, const void* a1, void* dst, const float* d, const float* noise, float noise_w, const float* bias,
                        float* gdacc, int n, int h, int w, int c, sfk_stream_t st) {
+  if (sfk_act_f32()) {
+    if (bwd)
+      blur_simple_bwd_kernel<float><<<dim3(per_sample_blocks(static_cast<long>(2 * h + 2) * (2 * w + 2) * (c / 8), n), n), kBlock, 0, S_(st)>>>(
+          static_cast<const float*>(a0), static_cast<const float*>(a1), static_cast<float*>(dst), d, noise, noise_w, bias, gdacc, h, w, c);
+    else
+      blur_simple_fwd_kernel<float><<<dim3(per_sample_blocks(4L * h * w * (c / 8), n), n), kBlock, 0, S_(st)>>>(
+          static_cast<const float*>(a0), static_cast<float*>(dst), d, noise, noise_w, bias, h, w, c);
+    return sfk_check_launch(bwd ? "blur_act_bwd(f32)" : "blur_act_fwd(f32)");
+  }
   const int vecs = c / 8;
   const BlurGeom G = blur_geom(vecs);
   SFK_REQUIRE(vecs % G.CV == 0 && (G.CV == 1 || G.CV == 2 || G.CV == 4), SFK_E_SHAPE, "blur: channel count must be 8, 16 or a multiple of 32");
@@ -1265,8 +1413,14 @@ int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d
 int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w, const float* bias, float* gdacc,
                 int n, int h, int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(out && gout && gz && d && bias && gdacc && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "act_bwd: bad args");
-  act_bwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
-      static_cast<const bf16*>(out), static_cast<const bf16*>(gout), static_cast<bf16*>(gz), d, noise, noise_w, bias, gdacc, h * w, c);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      act_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
+      static_cast<const T*>(out), static_cast<const T*>(gout), static_cast<T*>(gz), d, noise, noise_w, bias, gdacc, h * w, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("act_bwd");
 }
 
@@ -1275,16 +1429,28 @@ int sfk_torgb_fwd(const void* x, const float* wrgb, const float* sv, int s_strid
   SFK_REQUIRE(x && wrgb && sv && bias && rgb && c % 8 == 0, SFK_E_ARG, "torgb_fwd: bad args");
   int lp = 1;
   while (lp < 32 && lp * 16 <= c / 8) lp *= 2;   // C<=64: one thread per pixel (full 64-128 B reads, coalesced planar stores)
-  torgb_fwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * lp, n), n), kBlock, 3 * c * sizeof(float), S_(st)>>>(
-      static_cast<const bf16*>(x), wrgb, sv, s_stride, bias, skip, rgb, h, w, c, lp);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      torgb_fwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * lp, n), n), kBlock, 3 * c * sizeof(float), S_(st)>>>(
+      static_cast<const T*>(x), wrgb, sv, s_stride, bias, skip, rgb, h, w, c, lp);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("torgb_fwd");
 }
 
 int sfk_torgb_bwd(const void* x, const float* wrgb, const float* sv, int s_stride, const float* grgb, void* gx, float* gs, int gs_stride, int n,
                   int h, int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(x && wrgb && sv && grgb && gx && gs && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "torgb_bwd: bad args");
-  torgb_bwd_kernel<<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, 4 * c * sizeof(float), S_(st)>>>(
-      static_cast<const bf16*>(x), wrgb, sv, s_stride, grgb, static_cast<bf16*>(gx), gs, gs_stride, h * w, c);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      torgb_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, 4 * c * sizeof(float), S_(st)>>>(
+      static_cast<const T*>(x), wrgb, sv, s_stride, grgb, static_cast<T*>(gx), gs, gs_stride, h * w, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("torgb_bwd");
 }
 
@@ -1331,13 +1497,25 @@ int sfk_axpby(const float* x, const float* y, float* out, float a, float b, long
 
 int sfk_nchw_to_nhwc_bf16(const float* x, void* y, int n, int c, int h, int w, sfk_stream_t st) {
   SFK_REQUIRE(x && y, SFK_E_ARG, "nchw_to_nhwc: null");
-  nchw_to_nhwc_kernel<<<grid_for(static_cast<long>(n) * c * h * w), kBlock, 0, S_(st)>>>(x, static_cast<bf16*>(y), n, c, h, w);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      nchw_to_nhwc_kernel<T><<<grid_for(static_cast<long>(n) * c * h * w), kBlock, 0, S_(st)>>>(x, static_cast<T*>(y), n, c, h, w);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("nchw_to_nhwc");
 }
 
 int sfk_nhwc_bf16_to_nchw(const void* x, float* y, int n, int c, int h, int w, sfk_stream_t st) {
   SFK_REQUIRE(x && y, SFK_E_ARG, "nhwc_to_nchw: null");
-  nhwc_to_nchw_kernel<<<grid_for(static_cast<long>(n) * c * h * w), kBlock, 0, S_(st)>>>(static_cast<const bf16*>(x), y, n, c, h, w);
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      nhwc_to_nchw_kernel<T><<<grid_for(static_cast<long>(n) * c * h * w), kBlock, 0, S_(st)>>>(static_cast<const T*>(x), y, n, c, h, w);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
   return sfk_check_launch("nhwc_to_nchw");
 }
 

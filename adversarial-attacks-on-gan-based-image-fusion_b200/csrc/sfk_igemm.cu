@@ -192,8 +192,8 @@ __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h,
   if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {
     float x[16];
     if (valid) {
-      unpack8(ldg8(a.xin + off), x);
-      unpack8(ldg8(a.xin + off + 8), x + 8);
+      load8(a.xin + off, x);
+      load8(a.xin + off + 8, x + 8);
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = 0.f;
@@ -214,13 +214,13 @@ __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h,
   if (valid) {
     if (flags & SFK_EP_ACCUM) {
       float o[16];
-      unpack8(ld8(a.out + off), o);
-      unpack8(ld8(a.out + off + 8), o + 8);
+      load8p(a.out + off, o);
+      load8p(a.out + off + 8, o + 8);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += o[i];
     }
-    stg8(a.out + off, pack8(v));
-    stg8(a.out + off + 8, pack8(v + 8));
+    store8(a.out + off, v);
+    store8(a.out + off + 8, v + 8);
   }
 }
 
@@ -758,24 +758,26 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
 
 // ---------------------------------------------------------------------------------------------
 // CUDA-core cross-check with the identical contract (one thread = one position x 16 channels).
+template <typename T>
 struct RefArgs {
-  const __nv_bfloat16* A;
-  const __nv_bfloat16* B;
+  const T* A;
+  const T* B;
   int n_img, a_h, a_w, a_c, a_planes, b_rows, b_per_sample;
   int out_h, out_w, out_c, num_acc, block_n, num_taps, flags;
   int vec_stride;
   float noise_w;
-  __nv_bfloat16* out;
+  T* out;
   const float* dscale;
   const float* bias;
   const float* noise;
-  const __nv_bfloat16* xin;
+  const T* xin;
   const float* colscale;
   float* gs;
   KTap taps[SFK_MAX_TAPS];
 };
 
-__global__ void igemm_ref_kernel(const __grid_constant__ RefArgs a) {
+template <typename T>
+__global__ void igemm_ref_kernel(const __grid_constant__ RefArgs<T> a) {
   const int chunks_per_pos = a.out_c / 16;
   const long total = static_cast<long>(a.n_img) * a.num_acc * a.out_h * a.out_w * chunks_per_pos;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
@@ -799,14 +801,14 @@ __global__ void igemm_ref_kernel(const __grid_constant__ RefArgs a) {
       if (tp.acc != acc) continue;
       const int ih = h + tp.dy, iw = w + tp.dx;
       if (ih < 0 || ih >= a.a_h || iw < 0 || iw >= a.a_w) continue;
-      const __nv_bfloat16* ap = a.A + ((((static_cast<long>(n) * a.a_planes + tp.plane) * a.a_h + ih) * a.a_w + iw) * a.a_c);
+      const T* ap = a.A + ((((static_cast<long>(n) * a.a_planes + tp.plane) * a.a_h + ih) * a.a_w + iw) * a.a_c);
       const long brow0 = static_cast<long>(a.b_per_sample ? n : 0) * a.b_rows + tp.brow + nblk * a.block_n + cin_blk;
       for (int k = 0; k < a.a_c; ++k) {
-        const float av = __bfloat162float(ap[k]);
+        const float av = to_f32(ap[k]);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const long br = brow0 + i;
-          const float bv = (tp.brow + nblk * a.block_n + cin_blk + i < a.b_rows) ? __bfloat162float(a.B[br * a.a_c + k]) : 0.f;
+          const float bv = (tp.brow + nblk * a.block_n + cin_blk + i < a.b_rows) ? to_f32(a.B[br * a.a_c + k]) : 0.f;
           v[i] += av * bv;
         }
       }
@@ -881,6 +883,7 @@ void fill_taps(const sfk_igemm_desc* d, KTap* taps) {
 extern "C" int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream) {
   int rc = validate(d);
   if (rc) return rc;
+  SFK_REQUIRE(!sfk_act_f32(), SFK_E_ARG, "igemm_v1: bf16 activations only");
   EncodeTiledFn enc = get_encode_fn();
   SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
 
@@ -977,9 +980,12 @@ int encode_a_map(EncodeTiledFn enc, CUtensorMap* map, const sfk_igemm_desc* d, i
 }
 }  // namespace
 
+extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream);
+
 extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   int rc = validate(d);
   if (rc) return rc;
+  if (sfk_act_f32()) return sfk_igemm_ref(d, stream);   // fp32 parity mode: exact CUDA-core kernel (tcgen05 path is bf16)
   EncodeTiledFn enc = get_encode_fn();
   SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
 
@@ -1148,25 +1154,30 @@ extern "C" int sfk_role_cycles(unsigned long long* out8, int reset) {
   return 0;
 }
 
-extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
-  int rc = validate(d);
-  if (rc) return rc;
-  RefArgs r;
+template <typename T>
+static int launch_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
+  RefArgs<T> r;
   memset(&r, 0, sizeof(r));
-  r.A = static_cast<const __nv_bfloat16*>(d->a);
-  r.B = static_cast<const __nv_bfloat16*>(d->b);
+  r.A = static_cast<const T*>(d->a);
+  r.B = static_cast<const T*>(d->b);
   r.n_img = d->n_img; r.a_h = d->a_h; r.a_w = d->a_w; r.a_c = d->a_c; r.a_planes = d->a_planes;
   r.b_rows = d->b_rows; r.b_per_sample = d->b_samples > 1 ? 1 : 0;
   r.out_h = d->out_h; r.out_w = d->out_w; r.out_c = d->out_c; r.num_acc = d->num_acc; r.block_n = d->block_n;
   r.num_taps = d->num_taps; r.flags = d->flags; r.noise_w = d->noise_w;
   r.vec_stride = d->vec_stride > 0 ? d->vec_stride : d->out_c;
-  r.out = static_cast<__nv_bfloat16*>(d->out);
+  r.out = static_cast<T*>(d->out);
   r.dscale = d->dscale; r.bias = d->bias; r.noise = d->noise;
-  r.xin = static_cast<const __nv_bfloat16*>(d->xin); r.colscale = d->colscale; r.gs = d->gs;
+  r.xin = static_cast<const T*>(d->xin); r.colscale = d->colscale; r.gs = d->gs;
   fill_taps(d, r.taps);
   const long total = static_cast<long>(d->n_img) * d->num_acc * d->out_h * d->out_w * (d->out_c / 16);
   long blocks = (total + 127) / 128;
   if (blocks > 65535L * 16) blocks = 65535L * 16;
-  igemm_ref_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(r);
+  igemm_ref_kernel<T><<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(r);
   return sfk_check_launch("igemm_ref_kernel");
+}
+
+extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  return sfk_act_f32() ? launch_ref<float>(d, stream) : launch_ref<__nv_bfloat16>(d, stream);
 }

@@ -24,11 +24,13 @@ import torch
 from . import lib
 from .params import EncSpec, GenSpec, VGG_CONVS
 
-BF16 = torch.bfloat16
+def ACT() -> torch.dtype:
+    """activation storage type of the library right now: bf16 (product) or fp32 (parity mode)"""
+    return lib.activation_dtype()
 
 
-def _empty(shape, dev, dtype=BF16):
-    return torch.empty(shape, device=dev, dtype=dtype)
+def _empty(shape, dev, dtype=None):
+    return torch.empty(shape, device=dev, dtype=ACT() if dtype is None else dtype)
 
 
 def _zeros(shape, dev, dtype=torch.float32):
@@ -90,8 +92,8 @@ class ConvStack:
                     self.w_f32[i] = W.to(device=device, dtype=torch.float32).contiguous()
                 else:
                     Wd = W.to(device=device, dtype=torch.float32)
-                    self.w_fwd[i] = Wd.permute(2, 3, 0, 1).reshape(9 * l.cout, l.cin).to(BF16).contiguous()   # [tap][cout][cin]
-                    self.w_bwd[i] = Wd.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(BF16).contiguous()   # [tap][cin][cout]
+                    self.w_fwd[i] = Wd.permute(2, 3, 0, 1).reshape(9 * l.cout, l.cin).to(ACT()).contiguous()   # [tap][cout][cin]
+                    self.w_bwd[i] = Wd.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(ACT()).contiguous()   # [tap][cin][cout]
                 c = l.cout
             l.h, l.w = h, w
             self.out.append(_empty((n, h, w, c), device))
@@ -191,7 +193,7 @@ class SynthesisEngine:
         self.aff_scale = 1.0 / math.sqrt(spec.style_dim)
         c0 = spec.channels[4]
         const = P["input.input"][0].permute(1, 2, 0).contiguous()                      # (4,4,C)
-        self.const = const[None].repeat(B, 1, 1, 1).to(device=device, dtype=BF16).contiguous()
+        self.const = const[None].repeat(B, 1, 1, 1).to(device=device, dtype=ACT()).contiguous()
         self.L: List[dict] = []
         max_w = 0
         max_T = 0
@@ -207,7 +209,7 @@ class SynthesisEngine:
                 scale = 1.0 / math.sqrt(l.cin * 9)
                 Ws = (W * scale).to(device)
                 e["wbase"] = Ws.permute(2, 3, 0, 1).reshape(9, l.cout, l.cin).contiguous()        # fp32 [tap][cout][cin]
-                e["wT"] = Ws.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(BF16).contiguous()  # bf16 [tap][cin][cout], shared
+                e["wT"] = Ws.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(ACT()).contiguous()  # bf16 [tap][cin][cout], shared
                 e["Q"] = (Ws * Ws).sum((2, 3)).contiguous()                                       # (cout,cin)
                 e["bias"] = f32(P[f"{l.name}.activate.bias"])
                 e["noise"] = f32(P[f"noises.noise_{l.noise_idx}"][0, 0])

@@ -47,7 +47,7 @@ class SfkIgemmDesc(C.Structure):
 
 # every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "sfk_version", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
+    "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd",
@@ -73,6 +73,16 @@ def load() -> C.CDLL:
         _lib.sfk_last_error_string.restype = C.c_char_p
         _lib.sfk_version.restype = C.c_int
     return _lib
+
+
+def set_activation_dtype(dtype: torch.dtype):
+    """torch.bfloat16 (default) or torch.float32 (parity mode).  Engines must be built AFTER switching."""
+    assert dtype in (torch.bfloat16, torch.float32)
+    load().sfk_set_activation_dtype(1 if dtype == torch.float32 else 0)
+
+
+def activation_dtype() -> torch.dtype:
+    return torch.float32 if load().sfk_get_activation_dtype() else torch.bfloat16
 
 
 def _stream() -> C.c_void_p:

@@ -28,6 +28,10 @@ typedef void* sfk_stream_t; /* cudaStream_t */
 #define SFK_E_ALIGN (-4)
 
 int sfk_version(void);
+/* Activation storage of every entry point: 0 = bf16 (default, product path), 1 = fp32 (parity mode: the same schedules at fp32
+ * storage; the conv runs the CUDA-core kernel because the tcgen05 path is bf16).  Process-global; set before allocating. */
+int sfk_set_activation_dtype(int f32);
+int sfk_get_activation_dtype(void);
 const char* sfk_last_error_string(void);
 
 /* ---------------------------------------------------------------------------------------------
