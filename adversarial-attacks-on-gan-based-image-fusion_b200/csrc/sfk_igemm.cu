@@ -14,6 +14,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "sfk_common.cuh"
 
 namespace {
@@ -133,6 +135,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Sum each of 16 per-lane values over the 32 lanes with 16 shuffles; afterwards lane l holds the total
@@ -435,7 +453,11 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   __shared__ __align__(16) float col_dscale[256];
   __shared__ __align__(16) float col_bias[256];
   __shared__ __align__(16) float col_scale[256];
-  __shared__ int4 s_tap[kMaxGroups * kMaxGroupTaps];   // per tap: {A offset>>4 (+phase), B offset>>4, TMEM column, first}
+  // ready-made 64-bit operand descriptors, so that issuing a tap is: 2 x LDS.64 -> uniform registers -> tcgen05.mma
+  //   s_adesc[stage][tap]                      s_bdesc[resident ? channel block : stage][tap]
+  __shared__ uint64_t s_adesc[kMaxStages * SFK_MAX_TAPS];
+  __shared__ uint64_t s_bdesc[kMaxStages * SFK_MAX_TAPS];
+  __shared__ int s_colf[SFK_MAX_TAPS];   // (TMEM column << 1) | first-MMA-into-accumulator
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -450,17 +472,23 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   const int bs = a.b_per_sample ? n : 0;
 
   gs_acc[threadIdx.x] = 0.f;
-  if (threadIdx.x < kMaxGroups * kMaxGroupTaps) {
-    const int g = threadIdx.x / kMaxGroupTaps, j = threadIdx.x % kMaxGroupTaps;
-    int4 t = make_int4(0, 0, 0, 0);
-    if (g < a.num_groups && j < a.groups[g].ntaps) {
-      const KGroup& G = a.groups[g];
-      t.x = (G.roff[j] * a.row_bytes) >> 4;
-      t.y = ((a.b_resident ? G.bidx[j] : j) * a.b_tap_bytes) >> 4;
-      t.z = G.acc[j] * a.block_n;
-      t.w = G.first[j];
+  if (threadIdx.x < kMaxStages * SFK_MAX_TAPS) {
+    const int slot = threadIdx.x / SFK_MAX_TAPS, t = threadIdx.x % SFK_MAX_TAPS;
+    const uint32_t base_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t base_b = base_a + a.stages * a.a_stage_bytes;
+    const uint64_t hi = make_smem_desc(0, a.sbo_bytes, a.layout_type);
+    uint64_t da = 0, db = 0;
+    if (t < a.num_taps) {
+      if (slot < a.stages) da = hi | static_cast<uint64_t>(((base_a + slot * a.a_stage_bytes) >> 4) + static_cast<uint32_t>(a.f_a16[t]));
+      if (a.b_resident) {
+        if (slot < a.num_cblk) db = hi | static_cast<uint64_t>(((base_b + slot * a.num_taps * a.b_tap_bytes) >> 4) + static_cast<uint32_t>(a.f_b16[t]));
+      } else if (slot < a.stages) {
+        db = hi | static_cast<uint64_t>(((base_b + slot * a.b_stage_bytes) >> 4) + static_cast<uint32_t>(a.f_b16[t]));
+      }
     }
-    s_tap[threadIdx.x] = t;
+    s_adesc[threadIdx.x] = da;
+    s_bdesc[threadIdx.x] = db;
+    if (slot == 0) s_colf[t] = t < a.num_taps ? ((a.f_col[t] << 1) | (a.f_flags[t] & 1)) : 0;
   }
   if (threadIdx.x < a.block_n) {
     const int c = n0 + threadIdx.x;
@@ -480,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_empty_bar[i], 4);   // one arrival per epilogue warp
     }
     mbar_init(&bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -539,6 +567,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         }
       }
       if (prof) {
+        atomicAdd(&g_role_cycles[0], static_cast<unsigned long long>(t_wait));
         atomicAdd(&g_role_cycles[1], static_cast<unsigned long long>(clock64() - t_start));
       }
     }
@@ -558,15 +587,6 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const int kslices = a.KC / 16;
       const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
       long long t_wd = 0, t_wa = 0;
-      const int nflat = a.num_taps;
-      int A16[SFK_MAX_TAPS], B16[SFK_MAX_TAPS], COL[SFK_MAX_TAPS], FL[SFK_MAX_TAPS];
-#pragma unroll
-      for (int t = 0; t < SFK_MAX_TAPS; ++t) {
-        A16[t] = a.f_a16[t];
-        B16[t] = a.f_b16[t];
-        COL[t] = a.f_col[t];
-        FL[t] = a.f_flags[t];
-      }
       const long long t_start = clock64();
       const uint64_t desc_hi = make_smem_desc(0, a.sbo_bytes, a.layout_type);   // everything but the start address
       bool ok = true;
@@ -584,36 +604,44 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * a.num_acc * a.block_n);
         for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
-          uint32_t a_lo = 0, b_lo = 0;
-          int stage = 0;
+          int t0 = 0;
+          for (int g = 0; g < a.num_groups && ok; ++g, ++ks) {
+            const int nt = a.groups[g].ntaps;
+            const int stage = ks % a.stages;
+            const uint32_t phase = (ks / a.stages) & 1;
+            // gather every descriptor of this load group BEFORE the first MMA: operands of an in-flight tcgen05.mma stay
+            // pinned in their (uniform) registers, so descriptors formed one tap at a time would serialise issue and execution
+            uint64_t AD[kMaxGroupTaps], BD[kMaxGroupTaps];
+            uint32_t TC[kMaxGroupTaps], AF[kMaxGroupTaps];
+            const int a_row = stage * SFK_MAX_TAPS + t0;
+            const int b_row = (a.b_resident ? cb : stage) * SFK_MAX_TAPS + t0;
 #pragma unroll
-          for (int t = 0; t < SFK_MAX_TAPS; ++t) {
-            if (t < nflat && ok) {
-              if (FL[t] & 2) {   // first tap of a load group: wait for its box (and weight tiles)
-                stage = ks % a.stages;
-                const uint32_t phase = (ks / a.stages) & 1;
-                const long long td0 = prof ? clock64() : 0;
-                ok = mbar_wait(&full_bar[stage], phase, a.err);
-                if (prof) t_wd += clock64() - td0;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                a_lo = (smem_a + stage * a.a_stage_bytes) >> 4;
-                b_lo = (a.b_resident ? smem_b + cb * a.num_taps * a.b_tap_bytes : smem_b + stage * a.b_stage_bytes) >> 4;
-              }
-              const uint64_t adesc = desc_hi | static_cast<uint64_t>(a_lo + static_cast<uint32_t>(A16[t]));
-              const uint64_t bdesc = desc_hi | static_cast<uint64_t>(b_lo + static_cast<uint32_t>(B16[t]));
-              const uint32_t tmem_c = tmem_tile + static_cast<uint32_t>(COL[t]);
-              if (leader && ok) {
-                umma_bf16(tmem_c, adesc, bdesc, idesc, (cb == 0 && (FL[t] & 1)) ? 0u : 1u);
-#pragma unroll
-                for (int k = 1; k < 4; ++k)
-                  if (k < kslices) umma_bf16(tmem_c, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, 1u);
-              }
-              if (FL[t] & 4) {   // last tap of the group: the slot is free once these MMAs retire
-                __syncwarp();
-                if (leader) umma_commit(&empty_bar[stage]);
-                ++ks;
+            for (int j = 0; j < kMaxGroupTaps; ++j) {
+              if (j < nt) {
+                AD[j] = s_adesc[a_row + j];
+                BD[j] = s_bdesc[b_row + j];
+                TC[j] = tmem_tile + static_cast<uint32_t>(s_colf[t0 + j] >> 1);
+                AF[j] = (cb == 0 && (s_colf[t0 + j] & 1)) ? 0u : 1u;
               }
             }
+            const long long td0 = prof ? clock64() : 0;
+            ok = mbar_wait(&full_bar[stage], phase, a.err);
+            if (prof) t_wd += clock64() - td0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (leader && ok) {
+#pragma unroll
+              for (int j = 0; j < kMaxGroupTaps; ++j) {
+                if (j < nt) {
+                  umma_bf16(TC[j], AD[j], BD[j], idesc, AF[j]);
+#pragma unroll
+                  for (int k = 1; k < 4; ++k)
+                    if (k < kslices) umma_bf16(TC[j], AD[j] + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                }
+              }
+            }
+            __syncwarp();
+            if (leader) umma_commit(&empty_bar[stage]);
+            t0 += nt;
           }
         }
         __syncwarp();
@@ -642,7 +670,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     int t_h = tile / a.tiles_w, t_w = tile % a.tiles_w;
     const bool use_noise = (flags & SFK_EP_NOISE) != 0;
     auto noise_at = [&](int hh, int ww) -> float {
-      return (use_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) ? a.noise_w * __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;
+      return (use_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
     };
     float nz_next = tile < tiles_per_group ? noise_at(t_h * a.TH + th, t_w * a.TW + tw) : 0.f;
     for (int it = 0; tile < tiles_per_group; ++it) {
@@ -650,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const uint32_t aph = (it / a.acc_stages) & 1;
       const int h = t_h * a.TH + th, w = t_w * a.TW + tw;
       bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
-      const float nz = nz_next;
+      const float nz_raw = nz_next;
       tile += gridDim.x;
       t_w += gridDim.x;
       while (t_w >= a.tiles_w) {
@@ -663,81 +691,94 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       if (prof) t_we += clock64() - te0;
       valid = valid && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int acc = 0; acc < a.num_acc; ++acc) {
-        const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
-        for (int c = 0; c < chunks; ++c) {
-          float v[16];
-          const long off = pix * a.out_c + n0 + c * 16;
-          float x[16];
-          if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {   // start the activation load before the TMEM read completes
-            if (valid) {
-              unpack8(ldg8(a.xin + off), x);
-              unpack8(ldg8(a.xin + off + 8), x + 8);
-            } else {
+      const float nz = a.noise_w * nz_raw;
+      // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
+      auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
+        constexpr int NC = decltype(nc_tag)::value;
+        float v[NC], x[NC];
+        const long off = pix * a.out_c + n0 + c0;
+        if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {   // start the activation load before the TMEM read completes
+          if (valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = 0.f;
-            }
-          }
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                 static_cast<uint32_t>((as * a.num_acc + acc) * a.block_n + c * 16);
-          tmem_ld16(taddr, v);
-          if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
-            const float4* cd = reinterpret_cast<const float4*>(col_dscale + c * 16);
-            const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c * 16);
+            for (int i = 0; i < NC; i += 8) unpack8(ldg8(a.xin + off + i), x + i);
+          } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 dd = cd[i], bb = cb_[i];
-              v[4 * i + 0] = fmaf(v[4 * i + 0], dd.x, nz + bb.x);
-              v[4 * i + 1] = fmaf(v[4 * i + 1], dd.y, nz + bb.y);
-              v[4 * i + 2] = fmaf(v[4 * i + 2], dd.z, nz + bb.z);
-              v[4 * i + 3] = fmaf(v[4 * i + 3], dd.w, nz + bb.w);
-            }
+            for (int i = 0; i < NC; ++i) x[i] = 0.f;
           }
-          if (flags & SFK_EP_RELU) {
+        }
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>((as * a.num_acc + acc) * a.block_n + c0);
+        if (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
+          const float4* cd = reinterpret_cast<const float4*>(col_dscale + c0);
+          const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          for (int i = 0; i < NC / 4; ++i) {
+            const float4 dd = cd[i], bb = cb_[i];
+            v[4 * i + 0] = fmaf(v[4 * i + 0], dd.x, nz + bb.x);
+            v[4 * i + 1] = fmaf(v[4 * i + 1], dd.y, nz + bb.y);
+            v[4 * i + 2] = fmaf(v[4 * i + 2], dd.z, nz + bb.z);
+            v[4 * i + 3] = fmaf(v[4 * i + 3], dd.w, nz + bb.w);
           }
-          if (flags & SFK_EP_LRELU) {
+        }
+        if (flags & SFK_EP_RELU) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = lrelu_fwd(v[i]);
-          }
-          if (flags & SFK_EP_GSDOT) {
+          for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (flags & SFK_EP_LRELU) {
+#pragma unroll
+          for (int i = 0; i < NC; ++i) v[i] = lrelu_fwd(v[i]);
+        }
+        if (flags & SFK_EP_GSDOT) {
+#pragma unroll
+          for (int hlf = 0; hlf < NC / 16; ++hlf) {
             float gsd[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) gsd[i] = x[i] * v[i];
+            for (int i = 0; i < 16; ++i) gsd[i] = x[hlf * 16 + i] * v[hlf * 16 + i];
             const float tot = warp_colsum16(gsd, lane);
-            if (lane < 16) atomicAdd(&gs_acc[c * 16 + mycol], tot);
+            if (lane < 16) atomicAdd(&gs_acc[c0 + hlf * 16 + mycol], tot);
           }
-          if (flags & SFK_EP_XMASK) {
+        }
+        if (flags & SFK_EP_XMASK) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
+          for (int i = 0; i < NC; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
+        }
+        if (flags & SFK_EP_COLSCALE) {
+          const float4* cs = reinterpret_cast<const float4*>(col_scale + c0);
+#pragma unroll
+          for (int i = 0; i < NC / 4; ++i) {
+            const float4 ss = cs[i];
+            v[4 * i + 0] *= ss.x;
+            v[4 * i + 1] *= ss.y;
+            v[4 * i + 2] *= ss.z;
+            v[4 * i + 3] *= ss.w;
           }
-          if (flags & SFK_EP_COLSCALE) {
-            const float4* cs = reinterpret_cast<const float4*>(col_scale + c * 16);
+        }
+        if (valid) {
+          if (flags & SFK_EP_ACCUM) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 ss = cs[i];
-              v[4 * i + 0] *= ss.x;
-              v[4 * i + 1] *= ss.y;
-              v[4 * i + 2] *= ss.z;
-              v[4 * i + 3] *= ss.w;
+            for (int i = 0; i < NC; i += 8) {
+              float o[8];
+              unpack8(ld8(a.out + off + i), o);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[i + e] += o[e];
             }
           }
-          if (valid) {
-            if (flags & SFK_EP_ACCUM) {
-              float o[16];
-              unpack8(ld8(a.out + off), o);
-              unpack8(ld8(a.out + off + 8), o + 8);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += o[i];
-            }
-            stg8(a.out + off, pack8(v));
-            stg8(a.out + off + 8, pack8(v + 8));
-          }
+          for (int i = 0; i < NC; i += 8) stg8(a.out + off + i, pack8(v + i));
+        }
+      };
+      for (int acc = 0; acc < a.num_acc; ++acc) {
+        const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
+        if ((a.block_n & 31) == 0) {
+          for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix);
+        } else {
+          for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (128 arrivals)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (one arrival per warp)
     }
     if (prof) {
       atomicAdd(&g_role_cycles[5], static_cast<unsigned long long>(t_we));

@@ -35,6 +35,8 @@ def main():
         d = lib.make_igemm_desc(x, n, h, w, cin, 1, wt, n, 9 * cout, out, h + 1, w + 1, cout, 4, lib.pick_block_n(cout, 4), lib.tconv_taps(cout), err=err)
         bytes_alg = 2 * n * h * w * (cin + 4 * cout)
     d.stages = stages
+    if os.environ.get('SFK_FLAGS') is not None:
+        d.flags = int(os.environ['SFK_FLAGS'])
     if os.environ.get('SFK_ROLES'):
         d.flags |= lib.EP_PROFILE
         lib.role_cycles(True)
@@ -52,7 +54,7 @@ def main():
     if os.environ.get('SFK_ROLES'):
         rc = lib.role_cycles(True)
         tiles = max(rc[7], 1)
-        names = ['unused', 'prod_total', 'mma_wait_data', 'mma_wait_acc', 'mma_total', 'epi_wait', 'epi_total']
+        names = ['prod_wait', 'prod_total', 'mma_wait_data', 'mma_wait_acc', 'mma_total', 'epi_wait', 'epi_total']
         print('  role cycles per tile: ' + ', '.join(f'{n}={v / tiles:.0f}' for n, v in zip(names, rc[:7])) + f'  (tiles={tiles})')
     print(f"stages={stages} {mode} n={n} {h}x{w} cin={cin} cout={cout}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s  {bytes_alg/ms/1e6:.1f} GB/s (algorithmic)  err={err.item()}")
 
