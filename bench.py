@@ -99,7 +99,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -281,8 +281,12 @@ def run_ours(args):
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     fl = flops_per_iter_image(spec, es)
     step_ms = ms / args.steps
-    roofline = {"bound": "tensor", "kernel": "igemm_tc_kernel", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "igemm_traffic_r1.json")
+    if os.path.exists(tp) and args.size == SIZE and B == PAIRS_PER_GPU:
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # ncu --set full, dram read+write per launch (profiles/igemm_full_r1.md)
+    roofline = {"bound": "tensor", "kernel": "igemm_tc2_kernel", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"] + " (sustained bf16)",
                 "launches_per_step": n_tc, "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / step_ms if step_ms else None,
                 "algorithmic_gflop_per_iter_image": fl["attack"] / 1e9,
                 "step_frac_of_roofline": (fl["attack"] * B / (step_ms * 1e-3)) / (peaks["bf16_tflops"] * 1e12)}
@@ -334,7 +338,7 @@ def main():
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--e2e-calls", type=int, default=2)
-    ap.add_argument("--cpu-iters", type=int, default=2)
+    ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
