@@ -441,6 +441,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// FCT >= 0: the epilogue flag set is a compile-time constant (the six combinations the engines use are instantiated, so untaken
+// epilogue paths and their index arithmetic disappear); FCT < 0: flags are read at run time.
+template <int FCT>
 __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_constant__ Igemm2Args a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
@@ -660,8 +663,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     const int th = row / a.TWB, tw = row % a.TWB;
     const int chunks = a.block_n / 16;
     const int mycol = colsum16_column(lane);
-    const int flags = a.flags;
-    const bool prof = (flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
+    const int flags = FCT >= 0 ? FCT : a.flags;
+    const bool prof = FCT < 0 && (flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
     long long t_we = 0;
     const long long t_start = clock64();
     // tile coordinates advance incrementally (no division per tile); the per-pixel noise value of the NEXT tile is fetched
@@ -1177,12 +1180,32 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + resident + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaSuccess;
+#define SFK_SET_ATTR(F) e = (e == cudaSuccess) ? cudaFuncSetAttribute(igemm_tc2_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) : e
+    SFK_SET_ATTR(-1);
+    SFK_SET_ATTR(0);
+    SFK_SET_ATTR(SFK_EP_BIAS | SFK_EP_RELU);
+    SFK_SET_ATTR(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
+    SFK_SET_ATTR(SFK_EP_XMASK);
+    SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE);
+    SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);
+#undef SFK_SET_ATTR
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   dim3 grid(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
-  igemm_tc2_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(k);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  switch (d->flags) {
+#define SFK_CASE(F) case (F): igemm_tc2_kernel<F><<<grid, kThreads, smem, cs>>>(k); break
+    SFK_CASE(0);
+    SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU);
+    SFK_CASE(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
+    SFK_CASE(SFK_EP_XMASK);
+    SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE);
+    SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);
+#undef SFK_CASE
+    default: igemm_tc2_kernel<-1><<<grid, kThreads, smem, cs>>>(k); break;
+  }
   return sfk_check_launch("igemm_tc2_kernel");
 }
 
