@@ -92,9 +92,12 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvidia-smi needs ~0.1 s to start, so it is launched before the warm-up; only rows stamped inside [mark_begin, mark_end]
+    # (the timed region) are kept.
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -106,7 +109,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -115,7 +124,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.02)]
+        if not rows:
+            rows = [r for _, r in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -218,19 +230,21 @@ def run_ours(args):
         _, g = eng.forward_backward()
         lib.attack_update_linf(eng.x, eng.x0, g, ALPHA, EPS, 1.0, 0.0, 1.0, eng.stats, k)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     eng.check()
-    sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     lib.LAUNCHES = 0
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    sampler.mark_end()
     launches = lib.LAUNCHES
     clocks = sampler.stop()
     eng.check()

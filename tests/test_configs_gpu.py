@@ -1,0 +1,101 @@
+"""BASELINE.json configurations at their real sizes.
+  C1  FGSM, eps = 8/255, one 256x256 pair, StyleGAN2-256 (config-f widths), style (spatial) fusion + VGG loss, batch 1:
+      checked against the CPU oracle -- fp32 parity mode to north_star's 1e-3, bf16 product path to its stated tolerance.
+  C2/C3  1024x1024: size-independent properties (the oracle needs minutes per iteration there): eps-ball and [0,1] invariants,
+      monotone untargeted loss, idempotent projection, linearity of the style-gradient reduction."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _models(size, seed=0):
+    from sfattack.params import (EncSpec, gen_spec, make_encoder_params, make_fusion_params, make_generator_params,
+                                 make_vgg_state_dict)
+    spec = gen_spec(size)
+    GP = make_generator_params(spec, seed)
+    es = EncSpec(n_latent=spec.n_latent)
+    return spec, GP, es, make_encoder_params(es, seed + 1), make_vgg_state_dict(seed + 2), make_fusion_params(spec.s_dim, seed + 3)
+
+
+def _pairs(B, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda: F.avg_pool2d(torch.rand(B, 3, size + 4, size + 4, generator=g), 5, 1)
+    return mk(), mk(), mk(), mk(), g
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_c1_fgsm_256_style_fusion_vs_oracle(mode):
+    from oracle.pipeline import AttackCfg as OCfg, LossCfg as OLoss, OraclePipeline, run_attack as oracle_run
+    from sfattack import lib
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    spec, GP, es, EP, vsd, FP = _models(256)
+    xa, xb, ta, tb, g = _pairs(1, 256, 21)
+    eps = 8 / 255
+    # FGSM = one step of size eps from the clean pair; targeted (the gradient of the untargeted loss is exactly 0 at the clean point)
+    ocfg = OCfg(kind="linf", steps=1, eps=eps, alpha=eps, random_start=False, targeted=True, loss=OLoss(1.0, 1.0))
+    pipe = OraclePipeline(spec, GP, es, EP, vsd, FP, fusion="spatial")
+    rec = []
+    want = oracle_run(pipe, xa, xb, ocfg, target=(ta, tb), record=rec)
+    lib.set_activation_dtype(torch.float32 if mode == "fp32" else torch.bfloat16)
+    try:
+        eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion="spatial", batch=1, device=DEV, loss=LossCfg(1.0, 1.0))
+        got = run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind="linf", steps=1, eps=eps, alpha=eps, random_start=False, targeted=True),
+                         target=(ta.to(DEV), tb.to(DEV)))
+    finally:
+        lib.set_activation_dtype(torch.bfloat16)
+    X0 = torch.cat([xa, xb])
+    x_adv, x_ref = got["x_adv"].cpu(), want["x_adv"]
+    assert (x_adv - X0).abs().max() <= eps + 1e-6 and x_adv.min() >= 0 and x_adv.max() <= 1
+    g_ref = rec[0]["grad"]
+    band = g_ref.abs() > (1e-3 if mode == "fp32" else 5e-2) * g_ref.abs().mean()     # sign tie band
+    within = ((x_adv - x_ref).abs() < 1e-3)
+    frac_band = within[band].float().mean().item()
+    fused_err = (got["fused_adv"].cpu() - want["fused_adv"]).abs().max().item()
+    ref_err = (got["fused_ref"].cpu() - want["fused_ref"]).abs().max().item()
+    loss_rel = ((got["losses"][0].cpu() - want["losses"][0]).abs() / want["losses"][0].abs()).max().item()
+    print(f"[C1 {mode}] perturbation within 1e-3: {frac_band:.4f} (outside tie band, band excludes {(~band).float().mean():.4f}); "
+          f"fused max-abs err {fused_err:.2e}; reference fusion err {ref_err:.2e}; loss rel err {loss_rel:.2e}")
+    if mode == "fp32":
+        assert frac_band > 0.995 and fused_err < 1e-3 and ref_err < 1e-3 and loss_rel < 1e-3
+    else:
+        scale = want["fused_ref"].abs().max().item()     # bf16 activations through 14 layers: a few % of the image range
+        assert frac_band > 0.90 and fused_err < 0.04 * scale and loss_rel < 0.10, (fused_err, scale, loss_rel)
+    # identical attack outcome: targeted attack moved the fusion towards the target by the same amount
+    d_ref = ((want["fused_adv"] - want["fused_ref"]) ** 2).mean().item()
+    d_got = ((got["fused_adv"] - got["fused_ref"]) ** 2).mean().item()
+    assert abs(d_got - d_ref) <= (0.02 if mode == "fp32" else 0.2) * d_ref
+
+
+def test_c2_c3_full_size_properties_1024():
+    from sfattack import lib
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    spec, GP, es, EP, vsd, FP = _models(1024)
+    B = 2
+    xa, xb, _, _, g = _pairs(B, 1024, 31)
+    noise = torch.rand(2, B, 3, 1024, 1024, generator=g) * 2 - 1
+    eps, alpha = 8 / 255, 2 / 255
+    for fusion in ("arithmetic", "spatial"):
+        eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion=fusion, batch=B, device=DEV, loss=LossCfg(1.0, 1.0))
+        out = run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind="linf", steps=4, eps=eps, alpha=alpha), start_noise=noise)
+        X0 = torch.cat([xa, xb]).to(DEV)
+        x = out["x_adv"]
+        assert torch.isfinite(x).all() and torch.isfinite(out["fused_adv"]).all()
+        assert (x - X0).abs().max() <= eps + 1e-6 and x.min() >= 0 and x.max() <= 1          # projection + clamp
+        assert (out["losses"][-1] > out["losses"][0]).all()                                   # untargeted ascent
+        # the projection is idempotent: a zero-size step leaves the iterate unchanged
+        y = x.clone()
+        lib.attack_update_linf(y, X0, eng.g_xin, 0.0, eps, 1.0, 0.0, 1.0, None, eng.k_in)
+        assert torch.equal(y, x)
+        # gradient is piecewise constant over the k x k pooling cells and the style gradient is linear in the image gradient
+        gs1 = eng.syn.backward(eng.g_img).clone()
+        gs2 = eng.syn.backward((2.0 * eng.g_img).contiguous()).clone()
+        rel = ((gs2 - 2 * gs1).norm() / (2 * gs1).norm()).item()
+        assert rel < 2e-2, rel
+        eng.check()
+        del eng
+        torch.cuda.empty_cache()
