@@ -543,28 +543,47 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
       long long t_wait = 0;
       const long long t_start = clock64();
+      // per-group constants live in registers (fully unrolled group loop); tile coordinates advance without divisions
+      int Gdx[kMaxGroups], Gdy[kMaxGroups], Gpl[kMaxGroups], Gby[kMaxGroups], Gnt[kMaxGroups];
+      uint64_t Gmap[kMaxGroups];
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        Gdx[g] = a.groups[g].dx_min;
+        Gdy[g] = a.groups[g].dy_min;
+        Gpl[g] = a.groups[g].plane;
+        Gnt[g] = a.groups[g].ntaps;
+        Gby[g] = a.groups[g].bytes + (a.b_resident ? 0 : a.groups[g].ntaps * a.block_n * a.row_bytes);
+        Gmap[g] = reinterpret_cast<uint64_t>(&a.mapA[a.groups[g].map]);
+      }
+      const int ngroups = a.num_groups;
+      int t_h = static_cast<int>(blockIdx.x) / a.tiles_w, t_w = static_cast<int>(blockIdx.x) % a.tiles_w;
       for (int tile = blockIdx.x; tile < tiles_per_group && ok; tile += gridDim.x) {
-        const int h0 = (tile / a.tiles_w) * a.TH, w0 = (tile % a.tiles_w) * a.TW;
+        const int h0 = t_h * a.TH, w0 = t_w * a.TW;
+        t_w += gridDim.x;
+        while (t_w >= a.tiles_w) {
+          t_w -= a.tiles_w;
+          ++t_h;
+        }
         for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
-          for (int g = 0; g < a.num_groups; ++g, ++ks) {
-            const KGroup& G = a.groups[g];
-            const int stage = ks % a.stages;
-            const uint32_t phase = (ks / a.stages) & 1;
-            const long long tw0 = prof ? clock64() : 0;
-            if (!mbar_wait(&empty_bar[stage], phase ^ 1, a.err)) {
-              ok = false;
-              break;
-            }
-            if (prof) t_wait += clock64() - tw0;
-            uint32_t bytes = static_cast<uint32_t>(G.bytes);
-            if (!a.b_resident) bytes += static_cast<uint32_t>(G.ntaps * a.block_n * a.row_bytes);
-            mbar_expect_tx(&full_bar[stage], bytes);
-            tma_load_5d(smem_a + stage * a.a_stage_bytes, &a.mapA[G.map], &full_bar[stage], cb * a.KC, w0 + G.dx_min, h0 + G.dy_min,
-                        G.plane, n);
-            if (!a.b_resident) {
-              for (int j = 0; j < G.ntaps; ++j)
-                tma_load_3d(smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes, &a.mapB, &full_bar[stage], cb * a.KC,
-                            G.brow[j] + n0, bs);
+#pragma unroll
+          for (int g = 0; g < kMaxGroups; ++g) {
+            if (g < ngroups && ok) {
+              const int stage = ks % a.stages;
+              const uint32_t phase = (ks / a.stages) & 1;
+              const long long tw0 = prof ? clock64() : 0;
+              ok = mbar_wait(&empty_bar[stage], phase ^ 1, a.err);
+              if (prof) t_wait += clock64() - tw0;
+              if (ok) {
+                mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(Gby[g]));
+                tma_load_5d(smem_a + stage * a.a_stage_bytes, reinterpret_cast<const CUtensorMap*>(Gmap[g]), &full_bar[stage], cb * a.KC,
+                            w0 + Gdx[g], h0 + Gdy[g], Gpl[g], n);
+                if (!a.b_resident) {
+                  for (int j = 0; j < Gnt[g]; ++j)
+                    tma_load_3d(smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes, &a.mapB, &full_bar[stage], cb * a.KC,
+                                a.groups[g].brow[j] + n0, bs);
+                }
+              }
+              ++ks;
             }
           }
         }
@@ -664,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     const int chunks = a.block_n / 16;
     const int mycol = colsum16_column(lane);
     const int flags = FCT >= 0 ? FCT : a.flags;
-    const bool prof = FCT < 0 && (flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
+    const bool prof = (a.flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
     long long t_we = 0;
     const long long t_start = clock64();
     // tile coordinates advance incrementally (no division per tile); the per-pixel noise value of the NEXT tile is fetched
@@ -1060,11 +1079,19 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
 
   // ---- group taps that can share ONE activation load
   //   halo mode (row pitch 16): all taps of a plane whose shifts span <= 2 in x and y read one (TH+span_y[+1]) x 16 box;
-  //                             a tap enters it dy*16+dx rows down; the tile keeps TW = 16 - span_x useful columns
+  //                             a tap enters it dy*16+dx rows down (the swizzle is a function of the absolute smem address,
+  //                             so an operand may start at any row; the descriptor's base-offset field stays 0);
+  //                             the tile keeps TW = 16 - span_x useful columns
   //   dy mode (otherwise):      taps that differ only in dy share a box TH+span rows tall (row offsets are multiples of 8)
-  static int halo_env = -1;
-  if (halo_env < 0) { const char* e = getenv("SFK_HALO"); halo_env = e ? atoi(e) : 0; }   // experimental, off: results differ
-  const bool halo = halo_env && k.TW == 16;
+  // Halo mode pays off where the layer is bound by activation loads (small channel counts: the whole weight set is resident in
+  // smem); for wide layers the 16->14 useful columns cost more tensor time than the saved loads.  SFK_HALO=0/1 forces it.
+  static int halo_env = -2;
+  if (halo_env == -2) { const char* e = getenv("SFK_HALO"); halo_env = e ? atoi(e) : -1; }
+  const int b_total_est = (d->a_c / KC) * d->num_taps * (((d->block_n * KC * 2 + 1023) / 1024) * 1024);
+  // (measured: forward convs at 1024^2 / 512^2 gain 15-20 %; the data-gradient launches are bound by their heavier epilogue and
+  //  lose ~8 % to the narrower tile, so they keep the dy-shared mode)
+  const bool light_epilogue = (d->flags & (SFK_EP_GSDOT | SFK_EP_XMASK)) == 0;
+  const bool halo = k.TW == 16 && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= 72 * 1024 && light_epilogue));
   const bool share = k.TW >= 8;
   int ng = 0;
   int dymin[kMaxGroups], dymax[kMaxGroups], dxmin[kMaxGroups], dxmax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps], tdx[kMaxGroups][kMaxGroupTaps];
@@ -1195,7 +1222,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   }
   dim3 grid(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  switch (d->flags) {
+  switch (d->flags & ~SFK_EP_PROFILE) {
 #define SFK_CASE(F) case (F): igemm_tc2_kernel<F><<<grid, kThreads, smem, cs>>>(k); break
     SFK_CASE(0);
     SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU);
