@@ -688,6 +688,14 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     const long long t_start = clock64();
     // tile coordinates advance incrementally (no division per tile); the per-pixel noise value of the NEXT tile is fetched
     // before blocking on the accumulator of the current one, so its latency is off the critical path
+    // style-gradient partial sums: for narrow accumulators (block_n <= 32) every thread keeps its row's x*gx~ products in
+    // registers across ALL tiles of the CTA and the cross-row reduction happens once at the end; wider ones use the per-tile
+    // butterfly (more registers would spill at 2 CTAs per SM)
+    constexpr int kRegGs = 32;
+    const bool reg_gs = (flags & SFK_EP_GSDOT) && a.block_n <= kRegGs;
+    float gsr[kRegGs];
+#pragma unroll
+    for (int i = 0; i < kRegGs; ++i) gsr[i] = 0.f;
     int tile = blockIdx.x;
     int t_h = tile / a.tiles_w, t_w = tile % a.tiles_w;
     const bool use_noise = (flags & SFK_EP_NOISE) != 0;
@@ -751,7 +759,16 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < NC; ++i) v[i] = lrelu_fwd(v[i]);
         }
-        if (flags & SFK_EP_GSDOT) {
+        if ((flags & SFK_EP_GSDOT) && reg_gs) {
+          // c0 is 0 or 32 here (block_n <= 64, NC == 32 or the 16-wide path with c0 in {0,16,32,48})
+#pragma unroll
+          for (int base = 0; base < kRegGs; base += NC) {
+            if (base == c0) {
+#pragma unroll
+              for (int i = 0; i < NC; ++i) gsr[base + i] = fmaf(x[i], v[i], gsr[base + i]);
+            }
+          }
+        } else if (flags & SFK_EP_GSDOT) {
 #pragma unroll
           for (int hlf = 0; hlf < NC / 16; ++hlf) {
             float gsd[16];
@@ -801,6 +818,15 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (one arrival per warp)
+    }
+    if (reg_gs) {
+#pragma unroll
+      for (int i = 0; i < kRegGs; ++i) {
+        if (i < a.block_n) {
+          const float tot = warp_sum(gsr[i]);
+          if (lane == 0) atomicAdd(&gs_acc[i], tot);
+        }
+      }
     }
     if (prof) {
       atomicAdd(&g_role_cycles[5], static_cast<unsigned long long>(t_we));

@@ -180,3 +180,28 @@ def make_fusion_params(s_dim: int, seed: int = 2) -> Dict[str, torch.Tensor]:
 def blur_kernel_1d() -> List[float]:
     """[1,3,3,1] normalised to sum 1 (make_kernel); 2-D kernel is the outer product."""
     return [0.125, 0.375, 0.375, 0.125]
+
+
+def fused_up_base_weights(w: torch.Tensor) -> torch.Tensor:
+    """(Cout,Cin,3,3) -> (3,3,4,Cout,Cin): `upfirdn2d([1,3,3,1]*4, pad (1,1)) o conv_transpose2d(stride 2)` (upsample=True)
+    collapsed into four 3x3 convolutions over the INPUT grid, one per output phase p = 2a+b:
+        out[2m+a][2n+b] = sum_{dy,dx} Weff[dy][dx][p] . x[m+dy-1][n+dx-1]
+    (tests/test_kernel_math.py::test_fused_upsample_conv_equals_tconv_plus_blur).  The blur is linear and per-channel, so style
+    modulation still acts on the input-channel axis of Weff and demodulation coefficients are those of the original weights."""
+    k = torch.tensor(blur_kernel_1d(), dtype=w.dtype, device=w.device) * 2
+    cout, cin = w.shape[:2]
+    W = torch.zeros(3, 3, 4, cout, cin, dtype=w.dtype, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for t in range(4):
+                for ky in range(3):
+                    if (a + t - 1 - ky) % 2 or not (-1 <= (a + t - 1 - ky) // 2 <= 1):
+                        continue
+                    dy = (a + t - 1 - ky) // 2
+                    for u in range(4):
+                        for kx in range(3):
+                            if (b + u - 1 - kx) % 2 or not (-1 <= (b + u - 1 - kx) // 2 <= 1):
+                                continue
+                            dx = (b + u - 1 - kx) // 2
+                            W[dy + 1, dx + 1, 2 * a + b] += w[:, :, ky, kx] * k[t] * k[u]
+    return W

@@ -174,3 +174,64 @@ def test_torgb_and_skip_upsample_algebra():
     # skip-upsample transpose: up=2 pad (2,1)  ->  down=2 pad (1,2) with the same (symmetric) kernel
     gsk = sg.upfirdn2d(grgb, (sg.make_kernel_2d() * 4).double(), down=2, pad=(1, 2))
     torch.testing.assert_close(gsk, gsk_r)
+
+
+def fused_up_weights(w):
+    """(Cout,Cin,3,3) -> phase weights (3,3,4,Cout,Cin): blur([1,3,3,1]*2 per axis, pad (1,1)) o conv_transpose(stride 2) collapses to
+    four 3x3 convolutions over the INPUT grid, one per output phase (a,b):  out[2m+a][2n+b] = sum_{dy,dx} Weff[dy][dx][2a+b] x[m+dy-1][n+dx-1]."""
+    k = torch.tensor(blur_kernel_1d(), dtype=w.dtype) * 2
+    Cout, Cin = w.shape[:2]
+    W = torch.zeros(3, 3, 4, Cout, Cin, dtype=w.dtype)
+    for a in (0, 1):
+        for b in (0, 1):
+            for t in range(4):
+                for ky in range(3):
+                    if (a + t - 1 - ky) % 2:
+                        continue
+                    dy = (a + t - 1 - ky) // 2
+                    if dy < -1 or dy > 1:
+                        continue
+                    for u in range(4):
+                        for kx in range(3):
+                            if (b + u - 1 - kx) % 2:
+                                continue
+                            dx = (b + u - 1 - kx) // 2
+                            if dx < -1 or dx > 1:
+                                continue
+                            W[dy + 1, dx + 1, 2 * a + b] += w[:, :, ky, kx] * k[t] * k[u]
+    return W
+
+
+def test_fused_upsample_conv_equals_tconv_plus_blur():
+    from sfattack.params import fused_up_base_weights
+    g = torch.Generator().manual_seed(4)
+    B, Cin, Cout, H = 2, 5, 3, 6
+    x = torch.randn(B, Cin, H, H, generator=g, dtype=torch.double)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, dtype=torch.double)
+    ref = sg.upfirdn2d(F.conv_transpose2d(x, w.permute(1, 0, 2, 3), stride=2), (sg.make_kernel_2d() * 4).double(), pad=(1, 1))
+    We = fused_up_weights(w)
+    torch.testing.assert_close(fused_up_base_weights(w), We)
+    out = torch.zeros(B, Cout, 2 * H, 2 * H, dtype=torch.double)
+    xp = F.pad(x, [1, 1, 1, 1])
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = 0
+            for dy in range(3):
+                for dx in range(3):
+                    acc = acc + torch.einsum("oi,bihw->bohw", We[dy, dx, 2 * a + b], xp[:, :, dy:dy + H, dx:dx + H])
+            out[:, :, a::2, b::2] = acc
+    torch.testing.assert_close(out, ref)
+    # transpose: gx[i] = sum_{dy,dx,phase} Weff^T g[2(i-dy+1)+a][...]  == conv3x3^T over the space-to-depth view of g
+    gz = torch.randn(B, Cout, 2 * H, 2 * H, generator=g, dtype=torch.double)
+    xr = x.clone().requires_grad_(True)
+    r2 = sg.upfirdn2d(F.conv_transpose2d(xr, w.permute(1, 0, 2, 3), stride=2), (sg.make_kernel_2d() * 4).double(), pad=(1, 1))
+    (gx_ref,) = torch.autograd.grad((r2 * gz).sum(), xr)
+    s2d = torch.stack([gz[:, :, a::2, b::2] for a in (0, 1) for b in (0, 1)], 1)          # (B,4,Cout,H,H)
+    s2dp = F.pad(s2d, [1, 1, 1, 1])
+    gx = 0
+    for dy in range(3):
+        for dx in range(3):
+            # dgrad tap: gx[p] += W[dy][dx]^T g[p - (d - 1)]
+            win = s2dp[:, :, :, 2 - dy:2 - dy + H, 2 - dx:2 - dx + H]
+            gx = gx + torch.einsum("poi,bpohw->bihw", We[dy, dx], win)
+    torch.testing.assert_close(gx, gx_ref)
