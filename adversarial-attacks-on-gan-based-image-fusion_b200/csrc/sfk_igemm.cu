@@ -41,6 +41,7 @@ struct __align__(64) IgemmKArgs {
   int tmem_cols;
   int flags;
   int vec_stride;
+  int out_d2s;
   float noise_w;
   __nv_bfloat16* out;
   const float* dscale;
@@ -182,22 +183,33 @@ template <typename Args>
 __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h, int w, int col0, bool valid, float* v,
                                            float* gsdot /* 16 products for the style-gradient reduction */) {
   const int flags = a.flags;
-  const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
-  const long off = pix * a.out_c + col0;
-  const long vec = static_cast<long>(n) * a.out_c + col0;
+  long off, vec, noise_idx = static_cast<long>(h) * a.out_w + w;
+  int bias0 = col0;
+  if (a.out_d2s) {   // depth-to-space: column block -> output phase
+    const int Cq = a.out_c / 4, ph = col0 / Cq, ch = col0 % Cq;
+    const long fh = 2L * h + (ph >> 1), fw = 2L * w + (ph & 1);
+    off = ((static_cast<long>(n) * 2 * a.out_h + fh) * (2 * a.out_w) + fw) * Cq + ch;
+    vec = static_cast<long>(n) * Cq + ch;
+    bias0 = ch;
+    noise_idx = fh * (2 * a.out_w) + fw;
+  } else {
+    const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
+    off = pix * a.out_c + col0;
+    vec = static_cast<long>(n) * a.out_c + col0;
+  }
   const long svec = static_cast<long>(n) * a.vec_stride + col0;  // colscale / gs rows may live inside a wider [n][s_dim] array
   if (flags & SFK_EP_DSCALE) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= __ldg(a.dscale + vec + i);
   }
   if ((flags & SFK_EP_NOISE) && valid) {
-    const float nz = a.noise_w * __ldg(a.noise + static_cast<long>(h) * a.out_w + w);
+    const float nz = a.noise_w * __ldg(a.noise + noise_idx);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += nz;
   }
   if (flags & SFK_EP_BIAS) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + col0 + i);
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + bias0 + i);
   }
   if (flags & SFK_EP_RELU) {
 #pragma unroll
@@ -408,6 +420,7 @@ struct __align__(64) Igemm2Args {
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
   int b_per_sample, b_resident, dual_issue;
+  int out_d2s, a_s2d, cpa;   // fused resampling (see sfk.h); cpa = k-blocks per row phase of the space-to-depth input
   int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
   int layout_type, sbo_bytes, tmem_cols, flags, vec_stride;
   float noise_w;
@@ -495,8 +508,9 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   }
   if (threadIdx.x < a.block_n) {
     const int c = n0 + threadIdx.x;
-    col_dscale[threadIdx.x] = (a.flags & SFK_EP_DSCALE) ? a.dscale[static_cast<long>(n) * a.out_c + c] : 1.f;
-    col_bias[threadIdx.x] = (a.flags & SFK_EP_BIAS) ? a.bias[c] : 0.f;
+    const int cw = a.out_d2s ? a.out_c / 4 : a.out_c;   // depth-to-space: the 4 phases share the per-channel vectors
+    col_dscale[threadIdx.x] = (a.flags & SFK_EP_DSCALE) ? a.dscale[static_cast<long>(n) * cw + c % cw] : 1.f;
+    col_bias[threadIdx.x] = (a.flags & SFK_EP_BIAS) ? a.bias[c % cw] : 0.f;
     col_scale[threadIdx.x] = (a.flags & SFK_EP_COLSCALE) ? a.colscale[static_cast<long>(n) * a.vec_stride + c] : 1.f;
   }
   if (warp == 0 && lane == 0) {
@@ -575,8 +589,12 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
               if (prof) t_wait += clock64() - tw0;
               if (ok) {
                 mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(Gby[g]));
-                tma_load_5d(smem_a + stage * a.a_stage_bytes, reinterpret_cast<const CUtensorMap*>(Gmap[g]), &full_bar[stage], cb * a.KC,
-                            w0 + Gdx[g], h0 + Gdy[g], Gpl[g], n);
+                if (a.a_s2d)   // dims {2Cq, W, row phase, H, N}: k-block cb = (row phase, part of the pixel pair)
+                  tma_load_5d(smem_a + stage * a.a_stage_bytes, reinterpret_cast<const CUtensorMap*>(Gmap[g]), &full_bar[stage],
+                              (cb % a.cpa) * a.KC, w0 + Gdx[g], cb / a.cpa, h0 + Gdy[g], n);
+                else
+                  tma_load_5d(smem_a + stage * a.a_stage_bytes, reinterpret_cast<const CUtensorMap*>(Gmap[g]), &full_bar[stage], cb * a.KC,
+                              w0 + Gdx[g], h0 + Gdy[g], Gpl[g], n);
                 if (!a.b_resident) {
                   for (int j = 0; j < Gnt[g]; ++j)
                     tma_load_3d(smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes, &a.mapB, &full_bar[stage], cb * a.KC,
@@ -700,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     int t_h = tile / a.tiles_w, t_w = tile % a.tiles_w;
     const bool use_noise = (flags & SFK_EP_NOISE) != 0;
     auto noise_at = [&](int hh, int ww) -> float {
-      return (use_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
+      return (use_noise && !a.out_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
     };
     float nz_next = tile < tiles_per_group ? noise_at(t_h * a.TH + th, t_w * a.TW + tw) : 0.f;
     for (int it = 0; tile < tiles_per_group; ++it) {
@@ -721,12 +739,23 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       if (prof) t_we += clock64() - te0;
       valid = valid && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float nz = a.noise_w * nz_raw;
+      float nz = a.noise_w * nz_raw;
+      float nz4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.out_d2s && use_noise && valid) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+          nz4[ph] = a.noise_w * __ldg(a.noise + (2L * h + (ph >> 1)) * (2 * a.out_w) + 2 * w + (ph & 1));
+      }
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;
         float v[NC], x[NC];
-        const long off = pix * a.out_c + n0 + c0;
+        long off = pix * a.out_c + n0 + c0;
+        if (a.out_d2s) {   // this column block is one output phase: pixel (2h + ph/2, 2w + ph%2) of the fine grid
+          const int Cq = a.out_c >> 2, ph = (n0 + c0) / Cq, ch = (n0 + c0) % Cq;
+          off = ((static_cast<long>(n) * 2 * a.out_h + 2 * h + (ph >> 1)) * (2 * a.out_w) + 2 * w + (ph & 1)) * Cq + ch;
+          nz = nz4[ph];
+        }
         if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {   // start the activation load before the TMEM read completes
           if (valid) {
 #pragma unroll
@@ -809,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       };
       for (int acc = 0; acc < a.num_acc; ++acc) {
         const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
-        if ((a.block_n & 31) == 0) {
+        if ((a.block_n & 31) == 0 && (!a.out_d2s || ((a.out_c >> 2) & 31) == 0)) {
           for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix);
         } else {
           for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix);
@@ -854,6 +883,7 @@ struct RefArgs {
   int n_img, a_h, a_w, a_c, a_planes, b_rows, b_per_sample;
   int out_h, out_w, out_c, num_acc, block_n, num_taps, flags;
   int vec_stride;
+  int out_d2s, a_s2d;
   float noise_w;
   T* out;
   const float* dscale;
@@ -891,9 +921,16 @@ __global__ void igemm_ref_kernel(const __grid_constant__ RefArgs<T> a) {
       const int ih = h + tp.dy, iw = w + tp.dx;
       if (ih < 0 || ih >= a.a_h || iw < 0 || iw >= a.a_w) continue;
       const T* ap = a.A + ((((static_cast<long>(n) * a.a_planes + tp.plane) * a.a_h + ih) * a.a_w + iw) * a.a_c);
+      const int Cq = a.a_c / 4;
       const long brow0 = static_cast<long>(a.b_per_sample ? n : 0) * a.b_rows + tp.brow + nblk * a.block_n + cin_blk;
       for (int k = 0; k < a.a_c; ++k) {
-        const float av = to_f32(ap[k]);
+        float av;
+        if (a.a_s2d) {   // K index = phase*Cq + c of fine pixel (2ih + phase/2, 2iw + phase%2)
+          const int ph = k / Cq, c = k % Cq;
+          av = to_f32(a.A[((static_cast<long>(n) * 2 * a.a_h + 2 * ih + (ph >> 1)) * (2 * a.a_w) + 2 * iw + (ph & 1)) * Cq + c]);
+        } else {
+          av = to_f32(ap[k]);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const long br = brow0 + i;
@@ -945,6 +982,9 @@ int validate(const sfk_igemm_desc* d) {
     SFK_REQUIRE(d->taps[t].plane >= 0 && d->taps[t].plane < d->a_planes, SFK_E_SHAPE, "igemm: tap plane out of range");
     SFK_REQUIRE(d->taps[t].brow >= 0 && d->taps[t].brow + d->out_c <= d->b_rows, SFK_E_SHAPE, "igemm: tap weight rows out of range");
   }
+  if (d->out_d2s) SFK_REQUIRE(d->num_acc == 1 && d->out_c % 64 == 0 && !(d->flags & (SFK_EP_XMASK | SFK_EP_GSDOT | SFK_EP_ACCUM | SFK_EP_COLSCALE)),
+                              SFK_E_SHAPE, "igemm: depth-to-space output needs one accumulator, out_c % 64 == 0 and a forward epilogue");
+  if (d->a_s2d) SFK_REQUIRE(d->a_planes == 1 && d->a_c % 64 == 0, SFK_E_SHAPE, "igemm: space-to-depth input needs a_c % 64 == 0");
   if (d->flags & SFK_EP_DSCALE) SFK_REQUIRE(d->dscale, SFK_E_ARG, "igemm: dscale missing");
   if (d->flags & SFK_EP_BIAS) SFK_REQUIRE(d->bias, SFK_E_ARG, "igemm: bias missing");
   if (d->flags & SFK_EP_NOISE) SFK_REQUIRE(d->noise, SFK_E_ARG, "igemm: noise missing");
@@ -973,6 +1013,7 @@ extern "C" int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream) {
   int rc = validate(d);
   if (rc) return rc;
   SFK_REQUIRE(!sfk_act_f32(), SFK_E_ARG, "igemm_v1: bf16 activations only");
+  SFK_REQUIRE(!d->out_d2s && !d->a_s2d, SFK_E_ARG, "igemm_v1: fused resampling is only implemented by sfk_igemm / sfk_igemm_ref");
   EncodeTiledFn enc = get_encode_fn();
   SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
 
@@ -1058,6 +1099,16 @@ extern "C" int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream) {
 
 namespace {
 int encode_a_map(EncodeTiledFn enc, CUtensorMap* map, const sfk_igemm_desc* d, int KC, int TW, int rows, CUtensorMapSwizzle swz) {
+  if (d->a_s2d) {   // [n][2*a_h][2*a_w][Cq] viewed as {pixel pair (2Cq), W, row phase, H, N}
+    const cuuint64_t cq = (cuuint64_t)d->a_c / 4, frow = 2 * (cuuint64_t)d->a_w * cq * 2;   // bytes of one fine row
+    cuuint64_t dims[5] = {2 * cq, (cuuint64_t)d->a_w, 2, (cuuint64_t)d->a_h, (cuuint64_t)d->n_img};
+    cuuint64_t strides[4] = {2 * cq * 2, frow, 2 * frow, 2 * (cuuint64_t)d->a_h * frow};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)TW, 1, (cuuint32_t)rows, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+  }
   cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_w, (cuuint64_t)d->a_h, (cuuint64_t)d->a_planes, (cuuint64_t)d->n_img};
   cuuint64_t strides[4] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->a_w * d->a_c * 2, (cuuint64_t)d->a_h * d->a_w * d->a_c * 2,
                            (cuuint64_t)d->a_planes * d->a_h * d->a_w * d->a_c * 2};
@@ -1080,10 +1131,14 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
 
   static Igemm2Args k;   // large POD; sfk_igemm is not re-entrant across host threads (documented in sfk.h)
   memset(&k, 0, sizeof(k));
-  const int KC = (d->a_c % 64 == 0) ? 64 : (d->a_c % 32 == 0 ? 32 : 16);
+  const int kdim = d->a_s2d ? d->a_c / 2 : d->a_c;   // contiguous K extent in memory (space-to-depth: one pixel pair = 2*Cq)
+  const int KC = (kdim % 64 == 0) ? 64 : (kdim % 32 == 0 ? 32 : 16);
   const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   k.KC = KC;
   k.num_cblk = d->a_c / KC;
+  k.out_d2s = d->out_d2s;
+  k.a_s2d = d->a_s2d;
+  k.cpa = d->a_s2d ? kdim / KC : 1;
   k.row_bytes = KC * 2;
   k.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   k.sbo_bytes = 8 * k.row_bytes;
@@ -1117,7 +1172,9 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   // (measured: forward convs at 1024^2 / 512^2 gain 15-20 %; the data-gradient launches are bound by their heavier epilogue and
   //  lose ~8 % to the narrower tile, so they keep the dy-shared mode)
   const bool light_epilogue = (d->flags & (SFK_EP_GSDOT | SFK_EP_XMASK)) == 0;
-  const bool halo = k.TW == 16 && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= 72 * 1024 && light_epilogue));
+  // the fused-resampling launches (4 phases of weights) keep their whole weight set resident at one CTA per SM
+  const int resident_limit = (d->out_d2s || d->a_s2d) ? 150 * 1024 : 72 * 1024;
+  const bool halo = k.TW == 16 && !d->a_s2d && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= resident_limit && light_epilogue));
   const bool share = k.TW >= 8;
   int ng = 0;
   int dymin[kMaxGroups], dymax[kMaxGroups], dxmin[kMaxGroups], dxmax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps], tdx[kMaxGroups][kMaxGroupTaps];
@@ -1175,7 +1232,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   // ---- shared memory plan
   k.b_tap_bytes = ((d->block_n * k.row_bytes + 1023) / 1024) * 1024;
   const int b_total = k.num_cblk * k.num_taps * k.b_tap_bytes;
-  k.b_resident = b_total <= 72 * 1024 ? 1 : 0;
+  k.b_resident = b_total <= resident_limit ? 1 : 0;
   for (int g = 0; g < ng; ++g)
     for (int j = 0; j < k.groups[g].ntaps; ++j) {
       k.groups[g].a16[j] = (k.groups[g].roff[j] * k.row_bytes) >> 4;
@@ -1282,6 +1339,8 @@ static int launch_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
   r.out_h = d->out_h; r.out_w = d->out_w; r.out_c = d->out_c; r.num_acc = d->num_acc; r.block_n = d->block_n;
   r.num_taps = d->num_taps; r.flags = d->flags; r.noise_w = d->noise_w;
   r.vec_stride = d->vec_stride > 0 ? d->vec_stride : d->out_c;
+  r.out_d2s = d->out_d2s;
+  r.a_s2d = d->a_s2d;
   r.out = static_cast<T*>(d->out);
   r.dscale = d->dscale; r.bias = d->bias; r.noise = d->noise;
   r.xin = static_cast<const T*>(d->xin); r.colscale = d->colscale; r.gs = d->gs;

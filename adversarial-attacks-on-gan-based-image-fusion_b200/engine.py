@@ -16,13 +16,14 @@ Layouts: activations NHWC bf16, images NCHW fp32, style ve
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import lib
-from .params import EncSpec, GenSpec, VGG_CONVS
+from .params import EncSpec, GenSpec, VGG_CONVS, fused_up_base_weights
 
 def ACT() -> torch.dtype:
     """activation storage type of the library right now: bf16 (product) or fp32 (parity mode)"""
@@ -177,6 +178,13 @@ class ConvStack:
 
 
 # =================================================================================================
+def _fused_up_min_res() -> int:
+    """Up-layers at or above this output resolution run as ONE fused upsample-conv launch (2.25x the tensor FLOPs, but no
+    phase-plane round trip and no separate blur kernels); below it the 4-accumulator transposed conv + blur kernels are
+    cheaper because those layers are tensor-bound.  SFK_FUSED_UP_RES overrides (0 = all layers, large = none)."""
+    return int(os.environ.get("SFK_FUSED_UP_RES", "1024"))
+
+
 class SynthesisEngine:
     """StyleGAN2 synthesis from a concatenated StyleSpace vector s (B, s_dim)."""
 
@@ -208,8 +216,16 @@ class SynthesisEngine:
                 W = P[f"{l.name}.conv.weight"][0].to(torch.float32)                              # (cout,cin,3,3)
                 scale = 1.0 / math.sqrt(l.cin * 9)
                 Ws = (W * scale).to(device)
-                e["wbase"] = Ws.permute(2, 3, 0, 1).reshape(9, l.cout, l.cin).contiguous()        # fp32 [tap][cout][cin]
-                e["wT"] = Ws.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(ACT()).contiguous()  # bf16 [tap][cin][cout], shared
+                e["fused_up"] = l.kind == "up" and l.res >= _fused_up_min_res() and l.cout % 16 == 0 and l.cin % 16 == 0
+                if e["fused_up"]:
+                    # upsample conv = blur o transposed conv collapsed into four 3x3 phase convs over the input grid
+                    # (params.fused_up_base_weights): one launch each way, no phase-plane round trip through HBM
+                    We = fused_up_base_weights(Ws).reshape(3, 3, 4 * l.cout, l.cin)
+                    e["wbase"] = We.reshape(9, 4 * l.cout, l.cin).contiguous()                    # fp32 [tap][phase*cout][cin]
+                    e["wT"] = We.permute(0, 1, 3, 2).reshape(9 * l.cin, 4 * l.cout).to(ACT()).contiguous()
+                else:
+                    e["wbase"] = Ws.permute(2, 3, 0, 1).reshape(9, l.cout, l.cin).contiguous()        # fp32 [tap][cout][cin]
+                    e["wT"] = Ws.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(ACT()).contiguous()  # [tap][cin][cout], shared
                 e["Q"] = (Ws * Ws).sum((2, 3)).contiguous()                                       # (cout,cin)
                 e["bias"] = f32(P[f"{l.name}.activate.bias"])
                 e["noise"] = f32(P[f"noises.noise_{l.noise_idx}"][0, 0])
@@ -218,8 +234,8 @@ class SynthesisEngine:
                 e["gdacc"] = _zeros((B, l.cout), device)
                 e["out"] = _empty((B, l.res, l.res, l.cout), device)
                 e["gout"] = _empty((B, l.res, l.res, l.cout), device)
-                max_w = max(max_w, 9 * l.cout * l.cin)
-                if l.kind == "up":
+                max_w = max(max_w, 9 * l.cout * l.cin * (4 if e["fused_up"] else 1))
+                if l.kind == "up" and not e["fused_up"]:
                     hp = l.res // 2 + 1
                     max_T = max(max_T, 4 * hp * hp * l.cout)
             self.L.append(e)
@@ -254,6 +270,18 @@ class SynthesisEngine:
                     e["gout"], B, l.res, l.res, l.cout, 1, e["wT"], 1, 9 * l.cin, gx_dst, l.res, l.res, l.cin, 1,
                     lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=x,
                     colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
+            elif e["fused_up"]:
+                h = l.res // 2
+                wmod = self.wmod[: B * 36 * l.cout * l.cin].view(B, 36 * l.cout, l.cin)
+                e["wmod"] = wmod
+                e["fwd"] = lib.make_igemm_desc(
+                    x, B, h, h, l.cin, 1, wmod, B, 36 * l.cout, e["out"], h, h, 4 * l.cout, 1, lib.pick_block_n(4 * l.cout),
+                    lib.conv3x3_taps(4 * l.cout), flags=lib.EP_DSCALE | lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU, dscale=e["d"],
+                    bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err, out_d2s=1)
+                e["bwd"] = lib.make_igemm_desc(
+                    e["gout"], B, h, h, 4 * l.cout, 1, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1,
+                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM,
+                    xin=x, colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err, a_s2d=1)
             else:  # up
                 h = l.res // 2
                 wmod = self.wmod[: B * 9 * l.cout * l.cin].view(B, 9 * l.cout, l.cin)
@@ -295,7 +323,7 @@ class SynthesisEngine:
             lib.demod_fwd(s, l.s_off, e["Q"], e["d"])
             lib.modulate_weights(e["wbase"], s, l.s_off, e["wmod"])
             lib.igemm(e["fwd"])
-            if l.kind == "up":
+            if l.kind == "up" and not e["fused_up"]:
                 lib.blur_act_fwd(e["T"], e["out"], e["d"], e["noise"], e["noise_w"], e["bias"])
         return skip
 
@@ -329,7 +357,10 @@ class SynthesisEngine:
             up, conv = L[2 + 3 * k], L[3 + 3 * k]
             below_conv, below_rgb = (L[3 + 3 * (k - 1)], L[4 + 3 * (k - 1)]) if k > 0 else (L[0], L[1])
             conv_backward(conv)                        # writes up["gout"]
-            lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
+            if up["fused_up"]:
+                lib.act_bwd(up["out"], up["gout"], up["gout"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
+            else:
+                lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
             lib.rgb_down(grgb, below_rgb["grgb"])
             grgb = below_rgb["grgb"]
             lib.torgb_bwd(below_conv["out"], below_rgb["wrgb"], s, below_rgb["l"].s_off, grgb, below_conv["gout"], self.gs)

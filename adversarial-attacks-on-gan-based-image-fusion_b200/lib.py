@@ -42,6 +42,7 @@ class SfkIgemmDesc(C.Structure):
         ("vec_stride", C.c_int32),
         ("err", C.c_void_p),
         ("stages", C.c_int32),
+        ("out_d2s", C.c_int32), ("a_s2d", C.c_int32),
     ]
 
 
@@ -114,7 +115,7 @@ def _f(v) -> C.c_float:
 # ------------------------------------------------------------------------------------------------
 def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out, out_h, out_w, out_c, num_acc, block_n,
                     taps: Sequence[tuple], flags=0, dscale=None, bias=None, noise=None, noise_w=0.0, xin=None,
-                    colscale=None, gs=None, err=None, stages=0, vec_stride=0, vec_off=0) -> SfkIgemmDesc:
+                    colscale=None, gs=None, err=None, stages=0, vec_stride=0, vec_off=0, out_d2s=0, a_s2d=0) -> SfkIgemmDesc:
     d = SfkIgemmDesc()
     d.a, d.n_img, d.a_h, d.a_w, d.a_c, d.a_planes = _p(a), n_img, a_h, a_w, a_c, a_planes
     d.b, d.b_samples, d.b_rows = _p(b), b_samples, b_rows
@@ -126,6 +127,7 @@ def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out
     d.flags = flags
     d.dscale, d.bias, d.noise, d.noise_w = _p(dscale), _p(bias), _p(noise), float(noise_w)
     d.xin, d.err, d.stages, d.vec_stride = _p(xin), _p(err), stages, vec_stride
+    d.out_d2s, d.a_s2d = out_d2s, a_s2d
     d.colscale = _sub(colscale, vec_off) if colscale is not None else C.c_void_p(0)
     d.gs = _sub(gs, vec_off) if gs is not None else C.c_void_p(0)
     # keep the tensors alive as long as the descriptor
@@ -135,7 +137,9 @@ def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out
 
 def igemm_flops(d: SfkIgemmDesc) -> float:
     """algorithmic FLOPs of one launch: every tap is an (out_c x a_c) MAC block per output position"""
-    return 2.0 * d.n_img * d.out_h * d.out_w * d.num_taps * d.out_c * d.a_c
+    f = 2.0 * d.n_img * d.out_h * d.out_w * d.num_taps * d.out_c * d.a_c
+    # fused upsample conv: the four phase convs execute 4x the MACs of the transposed conv they replace; count the latter
+    return f / 4 if (d.out_d2s or d.a_s2d) else f
 
 
 def igemm(desc: SfkIgemmDesc, ref: bool = False, v1: bool = False):

@@ -88,6 +88,13 @@ typedef struct {
   int32_t vec_stride;        /* row stride (floats) of colscale and gs; 0 = out_c */
   int32_t* err;              /* device int, set non-zero on an internal timeout */
   int32_t stages;            /* 0 = auto */
+  /* Resample fused into the conv (upsampling StyledConv = 4 phase convs over the INPUT grid):
+   * out_d2s: the out_c = 4*Cq columns are the 4 output phases; column p*Cq+c of position (h,w) is stored to pixel
+   *          (2h + p/2, 2w + p%2), channel c of an [n][2*out_h][2*out_w][Cq] tensor; dscale/bias are indexed by c, noise by the
+   *          fine pixel.  (depth-to-space epilogue)
+   * a_s2d:   A is physically [n][2*a_h][2*a_w][a_c/4]; its K index is p*Cq+c for fine pixel (2h+p/2, 2w+p%2) (space-to-depth
+   *          view, used by the data gradient of the fused op). */
+  int32_t out_d2s, a_s2d;
 } sfk_igemm_desc;
 
 int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);   /* persistent kernel; call from one host thread at a time */

@@ -167,6 +167,67 @@ def test_tconv_blur_act_fwd_bwd(n, h, cin, cout):
     _close(gdacc, (gy * y).sum((2, 3)), rtol=2e-3, what="gdacc")
 
 
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 64, 32), (1, 24, 64, 16), (2, 32, 32, 32), (1, 8, 128, 64)])
+def test_fused_upsample_conv_fwd_bwd(n, h, cin, cout):
+    """blur(tconv(x)) as ONE launch: four 3x3 phase convs with a depth-to-space epilogue (forward) and the 3x3 data gradient
+    reading the fine-grid gradient through a space-to-depth view (backward), against autograd through conv_transpose2d + upfirdn2d."""
+    from oracle import stylegan2 as sg
+    from sfattack import lib
+    from sfattack.params import fused_up_base_weights
+    g = _gen(7)
+    x = _rb(n, cin, h, h, g=g).requires_grad_(True)
+    w0 = _rb(cout, cin, 3, 3, g=g, scale=1.0 / math.sqrt(cin * 9))
+    sty = torch.rand(n, cin, generator=g, device=_dev()) + 0.5
+    dsc = torch.rand(n, cout, generator=g, device=_dev()) + 0.5
+    noise = torch.randn(2 * h, 2 * h, generator=g, device=_dev())
+    bias = torch.randn(cout, generator=g, device=_dev()) * 0.1
+    nw = 0.3
+    weff = fused_up_base_weights(w0)                                   # (3,3,4,Cout,Cin)
+    wmod = (weff[None] * sty[:, None, None, None, None, :]).bfloat16()  # per-sample modulated, rounded as the kernel sees them
+    # reference from the SAME rounded phase weights: out[2m+a][2n+b] = sum W[dy][dx][2a+b] x[m+dy-1][n+dx-1]
+    ys = []
+    for i in range(n):
+        wi = wmod[i].float().reshape(3, 3, 4 * cout, cin).permute(2, 3, 0, 1)
+        y = F.conv2d(x[i:i + 1], wi, padding=1).view(1, 2, 2, cout, h, h)          # (1,a,b,co,m,n)
+        ys.append(y.permute(0, 3, 4, 1, 5, 2).reshape(1, cout, 2 * h, 2 * h))
+    z = torch.cat(ys)
+    ref = F.leaky_relu(z * dsc[:, :, None, None] + nw * noise + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    # and the phase weights really are tconv + blur (fp32 weights, looser tolerance: bf16 rounding of W_eff vs of W)
+    k2 = (sg.make_kernel_2d() * 4).to(_dev())
+    t = F.conv_transpose2d(x.detach(), (w0[None] * sty[:, None, :, None, None])[0].transpose(0, 1), stride=2)
+    z0 = sg.upfirdn2d(t[:1], k2, pad=(1, 1))
+    _close(z[:1].detach(), z0, rtol=2 ** -6, what="phase weights vs tconv+blur")
+
+    gz = _rb(n, cout, 2 * h, 2 * h, g=g)
+    (gx_ref,) = torch.autograd.grad((z * gz).sum(), x)
+    xin = _rb(n, cin, h, h, g=g)
+    prev = _rb(n, cin, h, h, g=g)
+    ref_gs = (xin * gx_ref).sum((2, 3))
+    ref_gx = prev + sty[:, :, None, None] * gx_ref
+
+    xb = _nhwc(x.detach())
+    wb = wmod.reshape(n, 9 * 4 * cout, cin).contiguous()
+    wT = wmod.reshape(n, 3, 3, 4 * cout, cin).permute(0, 1, 2, 4, 3).reshape(n, 9 * cin, 4 * cout).contiguous()
+    for use_ref in ("ref", "v2"):
+        err = torch.zeros(1, dtype=torch.int32, device=_dev())
+        out = torch.full((n, 2 * h, 2 * h, cout), float("nan"), device=_dev(), dtype=torch.bfloat16)
+        d = lib.make_igemm_desc(xb, n, h, h, cin, 1, wb, n, 9 * 4 * cout, out, h, h, 4 * cout, 1, lib.pick_block_n(4 * cout),
+                                lib.conv3x3_taps(4 * cout), flags=lib.EP_DSCALE | lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,
+                                dscale=dsc, bias=bias, noise=noise, noise_w=nw, err=err, out_d2s=1)
+        lib.igemm(d, ref=use_ref == "ref")
+        gx = _nhwc(prev).clone()
+        gs = torch.zeros(n, cin, device=_dev())
+        d2 = lib.make_igemm_desc(_nhwc(gz), n, h, h, 4 * cout, 1, wT, n, 9 * cin, gx, h, h, cin, 1, lib.pick_block_n(cin),
+                                 lib.conv3x3_dgrad_taps(cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM,
+                                 xin=_nhwc(xin), colscale=sty, gs=gs, err=err, a_s2d=1)
+        lib.igemm(d2, ref=use_ref == "ref")
+        torch.cuda.synchronize()
+        assert err.item() == 0
+        _close(_nchw(out), ref.detach(), what=f"fused up fwd {use_ref}")
+        _close(_nchw(gx), ref_gx, what=f"fused up dgrad {use_ref}")
+        _close(gs, ref_gs, rtol=2e-3, what=f"fused up gs {use_ref}")
+
+
 def test_conv_c3_fwd_bwd():
     from sfattack import lib
     g = _gen(4)
