@@ -476,7 +476,7 @@ __global__ void demod_bwd_kernel(const float* __restrict__ s, int s_stride, cons
 
 template <typename T>
 __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const float* __restrict__ s, int s_stride, T* __restrict__ wmod,
-                                        int N, long rows /* taps*cout */, int Cin) {
+                                        int N, long rows /* taps*cout */, int Cin, const float* __restrict__ d, int cout, int d_cols) {
   const int vecs = Cin / 8;
   const long total = static_cast<long>(N) * rows * vecs;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
@@ -488,6 +488,11 @@ __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const f
     const float4* sp = reinterpret_cast<const float4*>(s + static_cast<long>(n) * s_stride + v * 8);
     const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
     float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
+    if (d != nullptr) {   // demodulation folded into the weights: the conv epilogue then has no per-column scale to fetch
+      const float dv = __ldg(d + static_cast<long>(n) * d_cols + (r % cout) % d_cols);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] *= dv;
+    }
     store8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, o);
   }
 }
@@ -1347,14 +1352,16 @@ int sfk_demod_bwd(const float* sv, int s_stride, const float* Q, const float* d,
   return sfk_check_launch("demod_bwd");
 }
 
-int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void* wmod, int n, int taps, int cout, int cin, sfk_stream_t st) {
+int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void* wmod, int n, int taps, int cout, int cin, const float* d,
+                         int d_cols, sfk_stream_t st) {
   SFK_REQUIRE(wbase && sv && wmod && cin % 8 == 0 && s_stride % 4 == 0, SFK_E_ARG, "modulate_weights: bad args");
+  SFK_REQUIRE(d == nullptr || (d_cols > 0 && cout % d_cols == 0), SFK_E_ARG, "modulate_weights: d_cols must divide cout");
   SFK_REQUIRE(sfk_aligned16(wbase) && sfk_aligned16(sv) && sfk_aligned16(wmod), SFK_E_ALIGN, "modulate_weights: alignment");
   const long rows = static_cast<long>(taps) * cout;
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);
-      modulate_weights_kernel<T><<<grid_for(static_cast<long>(n) * rows * (cin / 8)), kBlock, 0, S_(st)>>>(wbase, sv, s_stride, static_cast<T*>(wmod), n, rows, cin);
+      modulate_weights_kernel<T><<<grid_for(static_cast<long>(n) * rows * (cin / 8)), kBlock, 0, S_(st)>>>(wbase, sv, s_stride, static_cast<T*>(wmod), n, rows, cin, d, cout, d_cols > 0 ? d_cols : cout);
     };
     if (sfk_act_f32()) run(float{}); else run(bf16{});
   }

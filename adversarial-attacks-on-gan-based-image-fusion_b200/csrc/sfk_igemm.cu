@@ -420,7 +420,7 @@ struct __align__(64) Igemm2Args {
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
   int b_per_sample, b_resident, dual_issue;
-  int out_d2s, a_s2d, cpa;   // fused resampling (see sfk.h); cpa = k-blocks per row phase of the space-to-depth input
+  int out_d2s, a_s2d, cpa, cq_log2;   // fused resampling (see sfk.h); cpa = k-blocks per row phase of the space-to-depth input
   int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
   int layout_type, sbo_bytes, tmem_cols, flags, vec_stride;
   float noise_w;
@@ -721,40 +721,49 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       return (use_noise && !a.out_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
     };
     float nz_next = tile < tiles_per_group ? noise_at(t_h * a.TH + th, t_w * a.TW + tw) : 0.f;
+    // depth-to-space output: one raw noise value per output phase of this thread's coarse pixel
+    const bool d2s_noise = use_noise && a.out_d2s;
+    float nq0 = 0.f, nq1 = 0.f, nq2 = 0.f, nq3 = 0.f;
+    auto noise4_at = [&](int hh, int ww) {
+      if (d2s_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) {
+        const float2* r0 = reinterpret_cast<const float2*>(a.noise + (2L * hh) * (2 * a.out_w) + 2 * ww);
+        const float2 u = __ldg(r0), l = __ldg(r0 + a.out_w);
+        nq0 = u.x; nq1 = u.y; nq2 = l.x; nq3 = l.y;
+      }
+    };
+    if (tile < tiles_per_group) noise4_at(t_h * a.TH + th, t_w * a.TW + tw);
     for (int it = 0; tile < tiles_per_group; ++it) {
       const int as = it % a.acc_stages;
       const uint32_t aph = (it / a.acc_stages) & 1;
       const int h = t_h * a.TH + th, w = t_w * a.TW + tw;
       bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
       const float nz_raw = nz_next;
+      const float nz4[4] = {nq0, nq1, nq2, nq3};
       tile += gridDim.x;
       t_w += gridDim.x;
       while (t_w >= a.tiles_w) {
         t_w -= a.tiles_w;
         ++t_h;
       }
-      if (tile < tiles_per_group) nz_next = noise_at(t_h * a.TH + th, t_w * a.TW + tw);
+      if (tile < tiles_per_group) {
+        nz_next = noise_at(t_h * a.TH + th, t_w * a.TW + tw);
+        noise4_at(t_h * a.TH + th, t_w * a.TW + tw);
+      }
       const long long te0 = prof ? clock64() : 0;
       const bool ok = mbar_wait(&tmem_full_bar[as], aph, a.err);
       if (prof) t_we += clock64() - te0;
       valid = valid && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float nz = a.noise_w * nz_raw;
-      float nz4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (a.out_d2s && use_noise && valid) {
-#pragma unroll
-        for (int ph = 0; ph < 4; ++ph)
-          nz4[ph] = a.noise_w * __ldg(a.noise + (2L * h + (ph >> 1)) * (2 * a.out_w) + 2 * w + (ph & 1));
-      }
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;
         float v[NC], x[NC];
         long off = pix * a.out_c + n0 + c0;
         if (a.out_d2s) {   // this column block is one output phase: pixel (2h + ph/2, 2w + ph%2) of the fine grid
-          const int Cq = a.out_c >> 2, ph = (n0 + c0) / Cq, ch = (n0 + c0) % Cq;
-          off = ((static_cast<long>(n) * 2 * a.out_h + 2 * h + (ph >> 1)) * (2 * a.out_w) + 2 * w + (ph & 1)) * Cq + ch;
-          nz = nz4[ph];
+          const int ph = (n0 + c0) >> a.cq_log2, ch = (n0 + c0) & ((1 << a.cq_log2) - 1);   // Cq is a power of two (validate)
+          off = (((static_cast<long>(n) * 2 * a.out_h + 2 * h + (ph >> 1)) * (2 * a.out_w) + 2 * w + (ph & 1)) << a.cq_log2) + ch;
+          nz = a.noise_w * (ph == 0 ? nz4[0] : ph == 1 ? nz4[1] : ph == 2 ? nz4[2] : nz4[3]);
         }
         if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {   // start the activation load before the TMEM read completes
           if (valid) {
@@ -768,7 +777,17 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>((as * a.num_acc + acc) * a.block_n + c0);
         if (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
+        if (!(flags & SFK_EP_DSCALE) && (flags & (SFK_EP_NOISE | SFK_EP_BIAS))) {
+          const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
+#pragma unroll
+          for (int i = 0; i < NC / 4; ++i) {
+            const float4 bb = (flags & SFK_EP_BIAS) ? cb_[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * i + 0] += nz + bb.x;
+            v[4 * i + 1] += nz + bb.y;
+            v[4 * i + 2] += nz + bb.z;
+            v[4 * i + 3] += nz + bb.w;
+          }
+        } else if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
           const float4* cd = reinterpret_cast<const float4*>(col_dscale + c0);
           const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
 #pragma unroll
@@ -982,8 +1001,8 @@ int validate(const sfk_igemm_desc* d) {
     SFK_REQUIRE(d->taps[t].plane >= 0 && d->taps[t].plane < d->a_planes, SFK_E_SHAPE, "igemm: tap plane out of range");
     SFK_REQUIRE(d->taps[t].brow >= 0 && d->taps[t].brow + d->out_c <= d->b_rows, SFK_E_SHAPE, "igemm: tap weight rows out of range");
   }
-  if (d->out_d2s) SFK_REQUIRE(d->num_acc == 1 && d->out_c % 64 == 0 && !(d->flags & (SFK_EP_XMASK | SFK_EP_GSDOT | SFK_EP_ACCUM | SFK_EP_COLSCALE)),
-                              SFK_E_SHAPE, "igemm: depth-to-space output needs one accumulator, out_c % 64 == 0 and a forward epilogue");
+  if (d->out_d2s) SFK_REQUIRE(d->num_acc == 1 && d->out_c % 64 == 0 && (d->out_c & (d->out_c - 1)) == 0 && !(d->flags & (SFK_EP_XMASK | SFK_EP_GSDOT | SFK_EP_ACCUM | SFK_EP_COLSCALE)),
+                              SFK_E_SHAPE, "igemm: depth-to-space output needs one accumulator, out_c a power of two >= 64 and a forward epilogue");
   if (d->a_s2d) SFK_REQUIRE(d->a_planes == 1 && d->a_c % 64 == 0, SFK_E_SHAPE, "igemm: space-to-depth input needs a_c % 64 == 0");
   if (d->flags & SFK_EP_DSCALE) SFK_REQUIRE(d->dscale, SFK_E_ARG, "igemm: dscale missing");
   if (d->flags & SFK_EP_BIAS) SFK_REQUIRE(d->bias, SFK_E_ARG, "igemm: bias missing");
@@ -1139,6 +1158,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   k.out_d2s = d->out_d2s;
   k.a_s2d = d->a_s2d;
   k.cpa = d->a_s2d ? kdim / KC : 1;
+  for (k.cq_log2 = 0; (4 << k.cq_log2) < d->out_c; ++k.cq_log2) {}
   k.row_bytes = KC * 2;
   k.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   k.sbo_bytes = 8 * k.row_bytes;
@@ -1174,7 +1194,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   const bool light_epilogue = (d->flags & (SFK_EP_GSDOT | SFK_EP_XMASK)) == 0;
   // the fused-resampling launches (4 phases of weights) keep their whole weight set resident at one CTA per SM
   const int resident_limit = (d->out_d2s || d->a_s2d) ? 150 * 1024 : 72 * 1024;
-  const bool halo = k.TW == 16 && !d->a_s2d && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= resident_limit && light_epilogue));
+  const bool halo = k.TW == 16 && !d->a_s2d && !d->out_d2s && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= resident_limit && light_epilogue));
   const bool share = k.TW >= 8;
   int ng = 0;
   int dymin[kMaxGroups], dymax[kMaxGroups], dxmin[kMaxGroups], dxmax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps], tdx[kMaxGroups][kMaxGroupTaps];
@@ -1296,6 +1316,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
     SFK_SET_ATTR(0);
     SFK_SET_ATTR(SFK_EP_BIAS | SFK_EP_RELU);
     SFK_SET_ATTR(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
+    SFK_SET_ATTR(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
     SFK_SET_ATTR(SFK_EP_XMASK);
     SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE);
     SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);
@@ -1310,6 +1331,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
     SFK_CASE(0);
     SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU);
     SFK_CASE(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
+    SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
     SFK_CASE(SFK_EP_XMASK);
     SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE);
     SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);

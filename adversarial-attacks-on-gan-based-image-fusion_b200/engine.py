@@ -181,8 +181,9 @@ class ConvStack:
 def _fused_up_min_res() -> int:
     """Up-layers at or above this output resolution run as ONE fused upsample-conv launch (2.25x the tensor FLOPs, but no
     phase-plane round trip and no separate blur kernels); below it the 4-accumulator transposed conv + blur kernels are
-    cheaper because those layers are tensor-bound.  SFK_FUSED_UP_RES overrides (0 = all layers, large = none)."""
-    return int(os.environ.get("SFK_FUSED_UP_RES", "1024"))
+    cheaper because those layers are tensor-bound.  Measured on the 1024 model, 8 pairs (ms/step): none 14.0, >=1024 13.28,
+    >=512 12.79, >=256 12.63, >=128 12.75.  SFK_FUSED_UP_RES overrides (0 = all layers, large = none)."""
+    return int(os.environ.get("SFK_FUSED_UP_RES", "256"))
 
 
 class SynthesisEngine:
@@ -263,7 +264,7 @@ class SynthesisEngine:
                 e["wmod"] = wmod
                 e["fwd"] = lib.make_igemm_desc(
                     x, B, l.res, l.res, l.cin, 1, wmod, B, 9 * l.cout, e["out"], l.res, l.res, l.cout, 1, lib.pick_block_n(l.cout),
-                    lib.conv3x3_taps(l.cout), flags=lib.EP_DSCALE | lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU, dscale=e["d"],
+                    lib.conv3x3_taps(l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,   # demod is folded into wmod
                     bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err)
                 gx_dst = prev_conv["gout"] if prev_conv is not None else self.gx_scratch
                 e["bwd"] = lib.make_igemm_desc(
@@ -276,7 +277,7 @@ class SynthesisEngine:
                 e["wmod"] = wmod
                 e["fwd"] = lib.make_igemm_desc(
                     x, B, h, h, l.cin, 1, wmod, B, 36 * l.cout, e["out"], h, h, 4 * l.cout, 1, lib.pick_block_n(4 * l.cout),
-                    lib.conv3x3_taps(4 * l.cout), flags=lib.EP_DSCALE | lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU, dscale=e["d"],
+                    lib.conv3x3_taps(4 * l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,
                     bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err, out_d2s=1)
                 e["bwd"] = lib.make_igemm_desc(
                     e["gout"], B, h, h, 4 * l.cout, 1, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1,
@@ -321,7 +322,9 @@ class SynthesisEngine:
                 skip = e["rgb"]
                 continue
             lib.demod_fwd(s, l.s_off, e["Q"], e["d"])
-            lib.modulate_weights(e["wbase"], s, l.s_off, e["wmod"])
+            # demodulation rides on the weights wherever the conv epilogue would apply it (the blur kernel of the unfused
+            # up-layers applies it itself, after the FIR)
+            lib.modulate_weights(e["wbase"], s, l.s_off, e["wmod"], None if (l.kind == "up" and not e["fused_up"]) else e["d"])
             lib.igemm(e["fwd"])
             if l.kind == "up" and not e["fused_up"]:
                 lib.blur_act_fwd(e["T"], e["out"], e["d"], e["noise"], e["noise_w"], e["bias"])

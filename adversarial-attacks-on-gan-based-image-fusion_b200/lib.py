@@ -290,10 +290,11 @@ def demod_bwd(s, s_off, Q, d, gdacc, gs):
          "demod_bwd")
 
 
-def modulate_weights(wbase, s, s_off, wmod):
+def modulate_weights(wbase, s, s_off, wmod, d=None):
     n, sd = s.shape
     taps, cout, cin = wbase.shape
-    _chk(load().sfk_modulate_weights(_p(wbase), _sub(s, s_off), sd, _p(wmod), n, taps, cout, cin, _stream()), "modulate_weights")
+    _chk(load().sfk_modulate_weights(_p(wbase), _sub(s, s_off), sd, _p(wmod), n, taps, cout, cin, _p(d),
+                                     d.shape[1] if d is not None else 0, _stream()), "modulate_weights")
 
 
 def blur_act_fwd(T, out, d, noise, noise_w, bias):

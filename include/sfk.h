@@ -152,9 +152,11 @@ int sfk_demod_fwd(const float* s, int s_stride, const float* Q, float* d, int n,
 /* gs[n][i] -= s[n][i] * sum_j gdacc[n][j] d[n][j]^2 Q[j][i] */
 int sfk_demod_bwd(const float* s, int s_stride, const float* Q, const float* d, const float* gdacc, float* gs,
                   int gs_stride, int n, int cin, int cout, sfk_stream_t st);
-/* wmod[n][t][j][i] = bf16(wbase[t][j][i] * s[n][i])    (wbase already carries 1/sqrt(cin*k*k)) */
+/* wmod[n][t][j][i] = bf16(wbase[t][j][i] * s[n][i] * (d ? d[n][j % d_cols] : 1))   (wbase already carries 1/sqrt(cin*k*k)).
+ * d (optional, [n][d_cols]) folds the demodulation of ModulatedConv2d into the weights so the conv epilogue has no
+ * per-column scale; d_cols divides cout (the fused upsample conv stacks 4 phases of d_cols output channels in one tap). */
 int sfk_modulate_weights(const float* wbase, const float* s, int s_stride, void* wmod, int n, int taps, int cout,
-                         int cin, sfk_stream_t st);
+                         int cin, const float* d, int d_cols, sfk_stream_t st);
 /* upfirdn2d([1,3,3,1] blur, pad (1,1)) of the phase-planar transposed-conv output, fused with
  * demod * . + noise + bias, leaky_relu*sqrt2.  T: [n][4][h+1][w+1][c] -> out [n][2h][2w][c]. */
 int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias,

@@ -29,6 +29,23 @@ def main():
         d = lib.make_igemm_desc(x, n, h, w, cin, 1, wt, 1, 9 * cout, out, h, w, cout, 1, lib.pick_block_n(cout), lib.conv3x3_dgrad_taps(cout),
                                 flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=xin, colscale=torch.ones(n, cout, device=dev), gs=gs, err=err)
         bytes_alg = 2 * n * h * w * (cin + 2 * cout)
+    elif mode == "fup":      # fused upsample conv forward: x (h,w,cin) -> (2h,2w,cout)
+        wt = (torch.randn(n, 36 * cout, cin, generator=g, device=dev) / math.sqrt(9 * cin)).bfloat16()
+        out = torch.empty(n, 2 * h, 2 * w, cout, device=dev, dtype=torch.bfloat16)
+        d = lib.make_igemm_desc(x, n, h, w, cin, 1, wt, n, 36 * cout, out, h, w, 4 * cout, 1, lib.pick_block_n(4 * cout), lib.conv3x3_taps(4 * cout),
+                                flags=lib.EP_DSCALE | lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU, dscale=torch.ones(n, cout, device=dev),
+                                bias=torch.zeros(cout, device=dev), noise=torch.randn(2 * h, 2 * w, device=dev), noise_w=0.1, err=err, out_d2s=1)
+        bytes_alg = 2 * n * h * w * (cin + 4 * cout)
+    elif mode == "fupb":     # its data gradient: g (2h,2w,cin) -> (h,w,cout) ; here cin = channels of the FINE gradient
+        x = torch.randn(n, 2 * h, 2 * w, cin, generator=g, device=dev).bfloat16()
+        wt = (torch.randn(9 * cout, 4 * cin, generator=g, device=dev) / math.sqrt(9 * cin)).bfloat16()
+        out = torch.zeros(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+        xin = torch.randn(n, h, w, cout, generator=g, device=dev).bfloat16()
+        gs = torch.zeros(n, cout, device=dev)
+        d = lib.make_igemm_desc(x, n, h, w, 4 * cin, 1, wt, 1, 9 * cout, out, h, w, cout, 1, lib.pick_block_n(cout), lib.conv3x3_dgrad_taps(cout),
+                                flags=lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM, xin=xin, colscale=torch.ones(n, cout, device=dev), gs=gs,
+                                err=err, a_s2d=1)
+        bytes_alg = 2 * n * h * w * (4 * cin + 3 * cout)
     else:
         wt = (torch.randn(n, 9 * cout, cin, generator=g, device=dev) / math.sqrt(9 * cin)).bfloat16()
         out = torch.empty(n, 4, h + 1, w + 1, cout, device=dev, dtype=torch.bfloat16)

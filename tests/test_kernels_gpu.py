@@ -352,6 +352,12 @@ def test_style_space_kernels():
     wmod = torch.empty(n, 9, cout, cin, device=_dev(), dtype=torch.bfloat16)
     lib.modulate_weights(wbase, s, 0, wmod)
     _close(wmod, wbase[None] * s[:, None, None, :cin], what="modulate")
+    lib.modulate_weights(wbase, s, 0, wmod, d)       # demodulation folded in
+    _close(wmod, wbase[None] * s[:, None, None, :cin] * d[:, None, :, None], what="modulate*demod")
+    if cout % 4 == 0:                                # four phases of cout/4 channels share d (fused upsample conv)
+        d4 = d[:, :cout // 4].contiguous()
+        lib.modulate_weights(wbase, s, 0, wmod, d4)
+        _close(wmod, wbase[None] * s[:, None, None, :cin] * d4.repeat(1, 4)[:, None, :, None], what="modulate*demod (4 phases)")
     # spatial fusion gate
     sa, sb = torch.randn(n, SD, generator=g, device=_dev(), requires_grad=True), torch.randn(n, SD, generator=g, device=_dev(), requires_grad=True)
     al, be, cc = (torch.randn(SD, generator=g, device=_dev()) for _ in range(3))
