@@ -27,30 +27,38 @@ __device__ __forceinline__ void flush_channel_acc(float* sacc, const float* acc,
 }
 
 // ============================================================================================
-// first-layer conv (Cin = 3)
+// first-layer conv (Cin = 3).  CUDA-core kernels, register-blocked so that they are bound by FMA issue and not by the
+// shared-memory weight fetches: one thread owns 4 horizontally adjacent pixels x 8 output channels, so every weight vector
+// read from shared memory feeds 32 FMAs (forward) / 96 FMAs (backward).
 template <typename T>
-__global__ void conv_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                   T* __restrict__ out, int N, int H, int W, int Cout, int relu) {
-  extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
+__global__ void __launch_bounds__(kBlock) conv_c3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                             T* __restrict__ out, int N, int H, int W, int Cout, int relu) {
+  extern __shared__ __align__(16) float sw[];  // [27][Cout] then bias[Cout]
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
     const int co = i % Cout, k = i / Cout;  // k = c*9 + ky*3 + kx
     sw[i] = w[co * 27 + k];
   }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int groups = Cout / 8;
-  const long total = static_cast<long>(N) * H * W * groups;
+  const int groups = Cout / 8, W4 = (W + 3) / 4;
+  const long total = static_cast<long>(N) * H * W4 * groups;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
     const int g = idx % groups;
     long p = idx / groups;
-    const int wq = p % W;
-    p /= W;
+    const int w0 = (p % W4) * 4;
+    p /= W4;
     const int hq = p % H;
     const int n = p / H;
-    float acc[8];
+    float acc[4][8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(sw + 27 * Cout + g * 8), b1 = *reinterpret_cast<const float4*>(sw + 27 * Cout + g * 8 + 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = sw[27 * Cout + g * 8 + i];
+      for (int j = 0; j < 4; ++j) {
+        acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b0.z; acc[j][3] = b0.w;
+        acc[j][4] = b1.x; acc[j][5] = b1.y; acc[j][6] = b1.z; acc[j][7] = b1.w;
+      }
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* xp = x + (static_cast<long>(n) * 3 + c) * H * W;
@@ -58,36 +66,50 @@ __global__ void conv_c3_fwd_kernel(const float* __restrict__ x, const float* __r
       for (int ky = 0; ky < 3; ++ky) {
         const int ih = hq + ky - 1;
         if (ih < 0 || ih >= H) continue;
+        float xr[6];   // input columns w0-1 .. w0+4 of this row
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int iw = w0 + q - 1;
+          xr[q] = (iw >= 0 && iw < W) ? __ldg(xp + static_cast<long>(ih) * W + iw) : 0.f;
+        }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int iw = wq + kx - 1;
-          if (iw < 0 || iw >= W) continue;
-          const float xv = __ldg(xp + static_cast<long>(ih) * W + iw);
           const float* wp = sw + (c * 9 + ky * 3 + kx) * Cout + g * 8;
+          const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 4);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wp[i], acc[i]);
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(xr[j + kx], wv[i], acc[j][i]);
+          }
         }
       }
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    for (int j = 0; j < 4; ++j) {
+      if (w0 + j >= W) break;
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = fmaxf(acc[j][i], 0.f);
+      }
+      store8(out + ((static_cast<long>(n) * H + hq) * W + w0 + j) * Cout + g * 8, acc[j]);
     }
-    store8(out + ((static_cast<long>(n) * H + hq) * W + wq) * Cout + g * 8, acc);
   }
 }
 
 template <typename T>
-__global__ void conv_c3_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int N,
-                                   int H, int W, int Cout, int LP /* lanes per pixel, power of 2 <= 8 */) {
-  extern __shared__ float sw[];  // [9][Cout][3]
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
-    const int c = i % 3, co = (i / 3) % Cout, k = i / (3 * Cout);
-    sw[i] = w[co * 27 + c * 9 + k];
+__global__ void __launch_bounds__(kBlock) conv_c3_bwd_kernel(const T* __restrict__ g, const float* __restrict__ w, float* __restrict__ gx, int N,
+                                                             int H, int W, int Cout, int LP /* lanes per pixel quad, power of 2 <= 8 */) {
+  // [9][Cout/8][8*4 + 4]: input channel padded to 4 (one LDS.128 per output channel); each 8-channel vector padded by 4 floats so
+  // that the lanes of a pixel quad (one vector each) read from distinct banks
+  extern __shared__ __align__(16) float sw[];
+  const int vecs = Cout / 8, W4 = (W + 3) / 4;
+  for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) {
+    const int c = i % 4, co = (i / 4) % Cout, k = i / (4 * Cout);
+    sw[(k * vecs + co / 8) * 36 + (co % 8) * 4 + c] = c < 3 ? w[co * 27 + c * 9 + k] : 0.f;
   }
   __syncthreads();
-  const int vecs = Cout / 8;
-  const long total = static_cast<long>(N) * H * W * LP;
+  const long total = static_cast<long>(N) * H * W4 * LP;
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   const long rounds = (total + stride - 1) / stride;
   for (long rr = 0; rr < rounds; ++rr) {
@@ -95,45 +117,66 @@ __global__ void conv_c3_bwd_kernel(const T* __restrict__ g, const float* __restr
     const bool active = idx < total;
     const int sub = idx % LP;
     long p = idx / LP;
-    const int wq = p % W;
-    p /= W;
+    const int w0 = (p % W4) * 4;
+    p /= W4;
     const int hq = p % H;
     const int n = p / H;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float a[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j][0] = a[j][1] = a[j][2] = 0.f;
     if (active) {
       for (int ky = 0; ky < 3; ++ky) {
         const int oh = hq - ky + 1;
         if (oh < 0 || oh >= H) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ow = wq - kx + 1;
-          if (ow < 0 || ow >= W) continue;
-          const T* gp = g + ((static_cast<long>(n) * H + oh) * W + ow) * Cout;
-          const float* wp = sw + (ky * 3 + kx) * Cout * 3;
-          for (int v = sub; v < vecs; v += LP) {
-            float gv[8];
-            load8(gp + v * 8, gv);
+        const T* grow = g + (static_cast<long>(n) * H + oh) * W * Cout;
+        for (int v = sub; v < vecs; v += LP) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float* w3 = wp + (v * 8 + i) * 3;
-              a0 = fmaf(gv[i], w3[0], a0);
-              a1 = fmaf(gv[i], w3[1], a1);
-              a2 = fmaf(gv[i], w3[2], a2);
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * vecs + v) * 36);
+            float4 wv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wv[i] = wp[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ow = w0 + j - kx + 1;
+              if (ow < 0 || ow >= W) continue;
+              float gv[8];
+              load8(grow + static_cast<long>(ow) * Cout + v * 8, gv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                a[j][0] = fmaf(gv[i], wv[i].x, a[j][0]);
+                a[j][1] = fmaf(gv[i], wv[i].y, a[j][1]);
+                a[j][2] = fmaf(gv[i], wv[i].z, a[j][2]);
+              }
             }
           }
         }
       }
     }
     for (int o = LP >> 1; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j][0] += __shfl_xor_sync(0xffffffffu, a[j][0], o);
+        a[j][1] += __shfl_xor_sync(0xffffffffu, a[j][1], o);
+        a[j][2] += __shfl_xor_sync(0xffffffffu, a[j][2], o);
+      }
     }
     if (active && sub == 0) {
       const long hw = static_cast<long>(H) * W;
-      float* o = gx + static_cast<long>(n) * 3 * hw + static_cast<long>(hq) * W + wq;
-      o[0] = a0;
-      o[hw] = a1;
-      o[2 * hw] = a2;
+      float* o = gx + static_cast<long>(n) * 3 * hw + static_cast<long>(hq) * W + w0;
+      if ((W & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(o + c * hw) = make_float4(a[0][c], a[1][c], a[2][c], a[3][c]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (w0 + j < W) {
+            o[j] = a[j][0];
+            o[hw + j] = a[j][1];
+            o[2 * hw + j] = a[j][2];
+          }
+        }
+      }
     }
   }
 }
@@ -414,22 +457,39 @@ __global__ void style_affine_fwd_kernel(const float* __restrict__ w, const float
   }
 }
 
+// gw[n][l][k] = scale * sum over the rows r of every layer driven by latent l of gs[n][r] * A[r][k].
+// block = (layer, slice of its rows, group of 8 samples): A is streamed once per sample group, coalesced along k; partial sums
+// are merged with atomics (gw is zeroed by the launcher).
+constexpr int kAffRows = 32;
 __global__ void style_affine_bwd_kernel(const float* __restrict__ gs, const float* __restrict__ A, const int* __restrict__ layer_row_start,
-                                        const int* __restrict__ layer_widx, int n_layers, float* __restrict__ gw, int N, int L, int D, int SD,
-                                        float scale) {
-  const long total = static_cast<long>(N) * L * D;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int k = idx % D;
-    const int l = (idx / D) % L;
-    const int n = idx / (static_cast<long>(D) * L);
-    float acc = 0.f;
-    for (int ly = 0; ly < n_layers; ++ly) {
-      if (layer_widx[ly] != l) continue;
-      for (int r = layer_row_start[ly]; r < layer_row_start[ly + 1]; ++r)
-        acc = fmaf(__ldg(gs + static_cast<long>(n) * SD + r), __ldg(A + static_cast<long>(r) * D + k), acc);
+                                        const int* __restrict__ layer_widx, float* __restrict__ gw, int N, int L, int D, int SD, float scale) {
+  __shared__ float sg[8][kAffRows];
+  const int ly = blockIdx.x;
+  const int l = layer_widx[ly];
+  const int n0 = blockIdx.z * 8;
+  const int rend = layer_row_start[ly + 1];
+  for (int r0 = layer_row_start[ly] + blockIdx.y * kAffRows; r0 < rend; r0 += gridDim.y * kAffRows) {
+  const int r1 = min(rend, r0 + kAffRows);
+  __syncthreads();
+  for (int t = threadIdx.x; t < 8 * kAffRows; t += blockDim.x) {
+    const int q = t / kAffRows, r = r0 + t % kAffRows;
+    sg[q][t % kAffRows] = (n0 + q < N && r < r1) ? __ldg(gs + static_cast<long>(n0 + q) * SD + r) : 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) {
+      const float a = __ldg(A + static_cast<long>(r) * D + k);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fmaf(sg[q][r - r0], a, acc[q]);
     }
-    gw[idx] = scale * acc;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (n0 + q < N) atomicAdd(gw + (static_cast<long>(n0 + q) * L + l) * D + k, scale * acc[q]);
+  }
   }
 }
 
@@ -805,13 +865,18 @@ __device__ __forceinline__ float skip_up_sample(const float* __restrict__ sk, in
   return r;
 }
 
-// LP lanes cooperate on one pixel (LP = min(32, C/8)), each lane owns channel vectors lane, lane+LP, ...
+// LP lanes cooperate on one pixel (LP = max(1, C/128)), each lane owns channel vectors lane, lane+LP, ...; per-pixel work (index
+// math, skip upsample, planar stores) is done once, so few lanes per pixel is right for the narrow high-resolution layers.
+// Modulated weights sit in shared memory as [vector][colour][8]: six broadcast LDS.128 feed the 24 FMAs of one 16-byte load.
 template <typename T>
 __global__ void torgb_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride,
                                  const float* __restrict__ bias, const float* __restrict__ skip, float* __restrict__ rgb, int H, int W, int C, int LP) {
-  extern __shared__ float swm[];  // [3][C] modulated weights of this sample
+  extern __shared__ __align__(16) float swm[];  // [C/8][3][8] modulated weights of this sample
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) swm[i] = wrgb[i] * s[static_cast<long>(n) * s_stride + (i % C)];
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int col = i / C, c = i % C;
+    swm[((c >> 3) * 3 + col) * 8 + (c & 7)] = wrgb[i] * s[static_cast<long>(n) * s_stride + c];
+  }
   __syncthreads();
   const int vecs = C / 8;
   const long HW = static_cast<long>(H) * W;
@@ -829,13 +894,14 @@ __global__ void torgb_fwd_kernel(const T* __restrict__ x, const float* __restric
       for (int v = sub; v < vecs; v += LP) {
         float xv[8];
         load8(xp + v * 8, xv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = v * 8 + i;
-          a0 = fmaf(xv[i], swm[c], a0);
-          a1 = fmaf(xv[i], swm[C + c], a1);
-          a2 = fmaf(xv[i], swm[2 * C + c], a2);
-        }
+        const float4* wp = reinterpret_cast<const float4*>(swm + v * 24);
+        const float4 r0 = wp[0], r1 = wp[1], g0 = wp[2], g1 = wp[3], b0 = wp[4], b1 = wp[5];
+        a0 = fmaf(xv[0], r0.x, a0); a0 = fmaf(xv[1], r0.y, a0); a0 = fmaf(xv[2], r0.z, a0); a0 = fmaf(xv[3], r0.w, a0);
+        a0 = fmaf(xv[4], r1.x, a0); a0 = fmaf(xv[5], r1.y, a0); a0 = fmaf(xv[6], r1.z, a0); a0 = fmaf(xv[7], r1.w, a0);
+        a1 = fmaf(xv[0], g0.x, a1); a1 = fmaf(xv[1], g0.y, a1); a1 = fmaf(xv[2], g0.z, a1); a1 = fmaf(xv[3], g0.w, a1);
+        a1 = fmaf(xv[4], g1.x, a1); a1 = fmaf(xv[5], g1.y, a1); a1 = fmaf(xv[6], g1.z, a1); a1 = fmaf(xv[7], g1.w, a1);
+        a2 = fmaf(xv[0], b0.x, a2); a2 = fmaf(xv[1], b0.y, a2); a2 = fmaf(xv[2], b0.z, a2); a2 = fmaf(xv[3], b0.w, a2);
+        a2 = fmaf(xv[4], b1.x, a2); a2 = fmaf(xv[5], b1.y, a2); a2 = fmaf(xv[6], b1.z, a2); a2 = fmaf(xv[7], b1.w, a2);
       }
     }
     for (int o = LP >> 1; o > 0; o >>= 1) {
@@ -901,6 +967,64 @@ __global__ void torgb_bwd_kernel(const T* __restrict__ x, const float* __restric
   flush_channel_acc(sacc, racc, cv, C, gs + static_cast<long>(n) * gs_stride);
 }
 
+// ToRGB backward + activation backward of the conv that feeds it, in one pass over the conv's output / gradient buffers:
+//   g   = gin (gradient already written by the next resolution's upsample conv; absent at the top) + s_rgb * (wrgb^T grgb)
+//   gs_rgb[n][i] += sum_hw out * (wrgb^T grgb)                      (ToRGB style gradient)
+//   gy  = g * act'(out);  gdacc[n][j] += sum_hw gy * y;  gz = gy * d      (as act_bwd)
+template <typename T>
+__global__ void act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T* gz, const float* __restrict__ d,
+                                     const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
+                                     const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride, const float* __restrict__ grgb,
+                                     float* __restrict__ gs, int gs_stride, int HW, int C) {
+  extern __shared__ float sacc[];   // [C]
+  const int n = blockIdx.y;
+  const int vecs = C / 8;
+  const int cv = threadIdx.x % vecs;
+  float sv[8], dv[8], bv[8], w0[8], w1[8], w2[8], racc[8], rrgb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cv * 8 + i;
+    sv[i] = s[static_cast<long>(n) * s_stride + c];
+    dv[i] = d[static_cast<long>(n) * C + c];
+    bv[i] = bias[c];
+    w0[i] = wrgb[c];
+    w1[i] = wrgb[C + c];
+    w2[i] = wrgb[2 * C + c];
+    racc[i] = 0.f;
+    rrgb[i] = 0.f;
+  }
+  const long total = static_cast<long>(HW) * vecs;
+  const long base = static_cast<long>(n) * HW * C;
+  const float* g0 = grgb + static_cast<long>(n) * 3 * HW;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = idx / vecs;
+    const long off = base + p * C + cv * 8;
+    const float ga = __ldg(g0 + p), gb = __ldg(g0 + HW + p), gc = __ldg(g0 + 2L * HW + p);
+    float ov[8], gv[8], o[8];
+    load8(out + off, ov);
+    if (gin != nullptr) {
+      load8p(gin + off, gv);   // gz may alias gin (in-place)
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gv[i] = 0.f;
+    }
+    const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gt = w0[i] * ga + w1[i] * gb + w2[i] * gc;
+      rrgb[i] = fmaf(ov[i], gt, rrgb[i]);
+      const float gy = fmaf(sv[i], gt, gv[i]) * lrelu_slope(ov[i]);
+      racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
+      o[i] = gy * dv[i];
+    }
+    store8(gz + off, o);
+  }
+  flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
+  __syncthreads();
+  flush_channel_acc(sacc, rrgb, cv, C, gs + static_cast<long>(n) * gs_stride);
+}
+
 __global__ void rgb_down_kernel(const float* __restrict__ g, float* __restrict__ gs, long planes, int H, int W) {
   // gskip[i][j] = sum_{t,u} g[2i+t-1][2j+u-1] k'[t] k'[u]
   const int hs = H / 2, ws = W / 2;
@@ -944,23 +1068,31 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
-// split over the output dimension: block (x = chunk of 256 inputs, y = slice of outputs) reads its W rows ONCE and
-// serves every sample from registers; partial sums are merged with atomics (gx is zeroed by the launcher).
-__global__ void linear_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx, int N, int In, int Out,
-                                  int o_per_slice) {
+// split over the output dimension: block (x = chunk of 128 inputs, y = slice of 32 outputs) reads its W rows ONCE and serves
+// every sample from registers (the slice of gy sits in shared memory); partial sums are merged with atomics (gx is zeroed by the
+// launcher).  Many small slices: the kernel is a single pass over W and needs the whole GPU's load parallelism.
+constexpr int kLinSlice = 32;
+__global__ void linear_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ Wt, float* __restrict__ gx, int N, int In, int Out) {
+  __shared__ float sg[16][kLinSlice];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int o0 = blockIdx.y * o_per_slice;
-  const int o1 = min(Out, o0 + o_per_slice);
-  if (i >= In) return;
+  const int o0 = blockIdx.y * kLinSlice;
+  const int no = min(kLinSlice, Out - o0);
   for (int nb = 0; nb < N; nb += 16) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 16 * kLinSlice; t += blockDim.x) {
+      const int q = t / kLinSlice, o = t % kLinSlice;
+      sg[q][o] = (nb + q < N && o < no) ? __ldg(gy + static_cast<long>(nb + q) * Out + o0 + o) : 0.f;
+    }
+    __syncthreads();
+    if (i >= In) continue;
     float acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-    for (int o = o0; o < o1; ++o) {
-      const float wv = __ldg(Wt + static_cast<long>(o) * In + i);
+#pragma unroll 4
+    for (int o = 0; o < no; ++o) {
+      const float wv = __ldg(Wt + static_cast<long>(o0 + o) * In + i);
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if (nb + q < N) acc[q] = fmaf(__ldg(gy + static_cast<long>(nb + q) * Out + o), wv, acc[q]);
+      for (int q = 0; q < 16; ++q) acc[q] = fmaf(sg[q][o], wv, acc[q]);
     }
 #pragma unroll
     for (int q = 0; q < 16; ++q)
@@ -1208,11 +1340,14 @@ int sfk_conv_c3_fwd(const float* x, const float* w, const float* bias, void* out
   SFK_REQUIRE(x && w && out, SFK_E_ARG, "conv_c3_fwd: null");
   SFK_REQUIRE(cout % 8 == 0 && cout <= 512, SFK_E_SHAPE, "conv_c3_fwd: cout must be a multiple of 8, <= 512");
   const size_t smem = static_cast<size_t>(28 * cout) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(conv_c3_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(conv_c3_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);
-      conv_c3_fwd_kernel<T><<<grid_for(static_cast<long>(n) * h * w_ * (cout / 8)), kBlock, smem, S_(s)>>>(x, w, bias, static_cast<T*>(out), n, h, w_, cout, relu);
+      conv_c3_fwd_kernel<T><<<grid_for(static_cast<long>(n) * h * ((w_ + 3) / 4) * (cout / 8)), kBlock, smem, S_(s)>>>(x, w, bias, static_cast<T*>(out), n, h, w_, cout, relu);
     };
     if (sfk_act_f32()) run(float{}); else run(bf16{});
   }
@@ -1224,12 +1359,15 @@ int sfk_conv_c3_bwd(const void* g, const float* w, float* gx, int n, int h, int 
   SFK_REQUIRE(cout % 8 == 0 && cout <= 512, SFK_E_SHAPE, "conv_c3_bwd: cout must be a multiple of 8, <= 512");
   int lp = 1;
   while (lp < 8 && lp * 2 <= cout / 8) lp *= 2;
-  const size_t smem = static_cast<size_t>(27 * cout) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(conv_c3_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const size_t smem = static_cast<size_t>(9 * (cout / 8) * 36) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(conv_c3_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(conv_c3_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);
-      conv_c3_bwd_kernel<T><<<grid_for(static_cast<long>(n) * h * w_ * lp), kBlock, smem, S_(s)>>>(static_cast<const T*>(g), w, gx, n, h, w_, cout, lp);
+      conv_c3_bwd_kernel<T><<<grid_for(static_cast<long>(n) * h * ((w_ + 3) / 4) * lp), kBlock, smem, S_(s)>>>(static_cast<const T*>(g), w, gx, n, h, w_, cout, lp);
     };
     if (sfk_act_f32()) run(float{}); else run(bf16{});
   }
@@ -1334,8 +1472,9 @@ int sfk_style_affine_fwd(const float* w, const float* A, const float* bias, cons
 int sfk_style_affine_bwd(const float* gs, const float* A, const int32_t* layer_row_start, const int32_t* layer_widx, int n_layers, float* gw, int n,
                          int n_latent, int style_dim, int s_dim, float scale, sfk_stream_t st) {
   SFK_REQUIRE(gs && A && layer_row_start && layer_widx && gw, SFK_E_ARG, "style_affine_bwd: null");
-  style_affine_bwd_kernel<<<grid_for(static_cast<long>(n) * n_latent * style_dim), kBlock, 0, S_(st)>>>(gs, A, layer_row_start, layer_widx, n_layers, gw,
-                                                                                                        n, n_latent, style_dim, s_dim, scale);
+  zero_kernel<<<grid_for(static_cast<long>(n) * n_latent * style_dim), kBlock, 0, S_(st)>>>(gw, static_cast<long>(n) * n_latent * style_dim);
+  style_affine_bwd_kernel<<<dim3(n_layers, 16, (n + 7) / 8), kBlock, 0, S_(st)>>>(gs, A, layer_row_start, layer_widx, gw, n, n_latent, style_dim, s_dim,
+                                                                                   scale);
   return sfk_check_launch("style_affine_bwd");
 }
 
@@ -1435,7 +1574,7 @@ int sfk_torgb_fwd(const void* x, const float* wrgb, const float* sv, int s_strid
                   int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(x && wrgb && sv && bias && rgb && c % 8 == 0, SFK_E_ARG, "torgb_fwd: bad args");
   int lp = 1;
-  while (lp < 32 && lp * 16 <= c / 8) lp *= 2;   // C<=64: one thread per pixel (full 64-128 B reads, coalesced planar stores)
+  while (lp < 32 && lp * 16 <= c / 8) lp *= 2;   // C<=128: one thread per pixel (full 64-256 B reads, coalesced planar stores)
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);
@@ -1461,6 +1600,23 @@ int sfk_torgb_bwd(const void* x, const float* wrgb, const float* sv, int s_strid
   return sfk_check_launch("torgb_bwd");
 }
 
+int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d, const float* noise, float noise_w, const float* bias,
+                      float* gdacc, const float* wrgb, const float* sv, int s_stride, const float* grgb, float* gs, int gs_stride, int n, int h,
+                      int w, int c, sfk_stream_t st) {
+  SFK_REQUIRE(out && gz && d && bias && gdacc && wrgb && sv && grgb && gs && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG,
+              "act_torgb_bwd: bad args");
+  {
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      act_torgb_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
+          static_cast<const T*>(out), static_cast<const T*>(gin), static_cast<T*>(gz), d, noise, noise_w, bias, gdacc, wrgb, sv, s_stride, grgb, gs,
+          gs_stride, h * w, c);
+    };
+    if (sfk_act_f32()) run(float{}); else run(bf16{});
+  }
+  return sfk_check_launch("act_torgb_bwd");
+}
+
 int sfk_rgb_down(const float* g, float* gskip, int planes, int h, int w, sfk_stream_t st) {
   SFK_REQUIRE(g && gskip && h % 2 == 0 && w % 2 == 0, SFK_E_ARG, "rgb_down: bad args");
   rgb_down_kernel<<<grid_for(static_cast<long>(planes) * (h / 2) * (w / 2)), kBlock, 0, S_(st)>>>(g, gskip, planes, h, w);
@@ -1476,10 +1632,7 @@ int sfk_linear_fwd(const float* x, const float* W, const float* bias, float* y, 
 int sfk_linear_bwd(const float* gy, const float* W, float* gx, int n, int in, int out, sfk_stream_t st) {
   SFK_REQUIRE(gy && W && gx, SFK_E_ARG, "linear_bwd: null");
   zero_kernel<<<grid_for(static_cast<long>(n) * in), kBlock, 0, S_(st)>>>(gx, static_cast<long>(n) * in);
-  int slices = out >= 64 ? 64 : 1;
-  const int per = (out + slices - 1) / slices;
-  slices = (out + per - 1) / per;
-  linear_bwd_kernel<<<dim3((in + 127) / 128, slices), 128, 0, S_(st)>>>(gy, W, gx, n, in, out, per);
+  linear_bwd_kernel<<<dim3((in + 127) / 128, (out + kLinSlice - 1) / kLinSlice), 128, 0, S_(st)>>>(gy, W, gx, n, in, out);
   return sfk_check_launch("linear_bwd");
 }
 

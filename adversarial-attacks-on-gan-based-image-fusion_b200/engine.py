@@ -281,7 +281,7 @@ class SynthesisEngine:
                     bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err, out_d2s=1)
                 e["bwd"] = lib.make_igemm_desc(
                     e["gout"], B, h, h, 4 * l.cout, 1, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1,
-                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM,
+                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE,
                     xin=x, colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err, a_s2d=1)
             else:  # up
                 h = l.res // 2
@@ -291,10 +291,10 @@ class SynthesisEngine:
                 e["T"] = T
                 e["fwd"] = lib.make_igemm_desc(x, B, h, h, l.cin, 1, wmod, B, 9 * l.cout, T, h + 1, h + 1, l.cout, 4,
                                                lib.pick_block_n(l.cout, 4), lib.tconv_taps(l.cout), err=self.err)
-                # data gradient accumulates into the gradient buffer of the previous resolution's conv
+                # data gradient is the first writer of the gradient buffer of the previous resolution's conv
                 e["bwd"] = lib.make_igemm_desc(
                     T, B, h + 1, h + 1, l.cout, 4, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1, lib.pick_block_n(l.cin),
-                    lib.tconv_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE | lib.EP_ACCUM, xin=x, colscale=self.s,
+                    lib.tconv_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=x, colscale=self.s,
                     gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
             x = e["out"]
             prev_conv = e
@@ -338,8 +338,8 @@ class SynthesisEngine:
         """g_img (B,3,size,size) fp32 -> gs (B, s_dim) fp32 (owned).  Must follow forward() with the same s.
 
         Layer list is [conv1, rgb1, (up, conv, rgb) per resolution].  Every conv output feeds ToRGB and (except at the
-        top) the next up-conv: ToRGB's backward is the first writer of the conv's gradient buffer, the up-conv's data
-        gradient accumulates into it (SFK_EP_ACCUM)."""
+        top) the next up-conv: the up-conv's data gradient is the first writer of the conv's gradient buffer, then ONE
+        kernel adds ToRGB's backward and applies the conv's activation backward in place (sfk_act_torgb_bwd)."""
         s = self.s
         self.gs.zero_()
         for g in self._gd_all:
@@ -347,29 +347,31 @@ class SynthesisEngine:
         L = self.L
         nb = (len(L) - 2) // 3
 
-        def conv_backward(e):
-            l = e["l"]
-            lib.act_bwd(e["out"], e["gout"], e["gout"], e["d"], e["noise"], e["noise_w"], e["bias"], e["gdacc"])
+        def conv_tail(e):
             lib.igemm(e["bwd"])                       # -> gradient of the producer of x, + fused style gradient
-            lib.demod_bwd(s, l.s_off, e["Q"], e["d"], e["gdacc"], self.gs)
+            lib.demod_bwd(s, e["l"].s_off, e["Q"], e["d"], e["gdacc"], self.gs)
+
+        def conv_act_rgb(conv, rgb, grgb, have_gin):
+            # ToRGB backward and the conv's activation backward in one pass over conv["out"] / conv["gout"]
+            lib.act_torgb_bwd(conv["out"], conv["gout"] if have_gin else None, conv["gout"], conv["d"], conv["noise"], conv["noise_w"],
+                              conv["bias"], conv["gdacc"], rgb["wrgb"], s, rgb["l"].s_off, grgb, self.gs)
 
         conv, rgb = (L[3 + 3 * (nb - 1)], L[4 + 3 * (nb - 1)]) if nb > 0 else (L[0], L[1])
         grgb = g_img
-        lib.torgb_bwd(conv["out"], rgb["wrgb"], s, rgb["l"].s_off, grgb, conv["gout"], self.gs)
+        conv_act_rgb(conv, rgb, grgb, False)
         for k in range(nb - 1, -1, -1):
             up, conv = L[2 + 3 * k], L[3 + 3 * k]
             below_conv, below_rgb = (L[3 + 3 * (k - 1)], L[4 + 3 * (k - 1)]) if k > 0 else (L[0], L[1])
-            conv_backward(conv)                        # writes up["gout"]
+            conv_tail(conv)                            # writes up["gout"]
             if up["fused_up"]:
                 lib.act_bwd(up["out"], up["gout"], up["gout"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
             else:
                 lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
             lib.rgb_down(grgb, below_rgb["grgb"])
             grgb = below_rgb["grgb"]
-            lib.torgb_bwd(below_conv["out"], below_rgb["wrgb"], s, below_rgb["l"].s_off, grgb, below_conv["gout"], self.gs)
-            lib.igemm(up["bwd"])                       # accumulates into below_conv["gout"]
-            lib.demod_bwd(s, up["l"].s_off, up["Q"], up["d"], up["gdacc"], self.gs)
-        conv_backward(L[0])
+            conv_tail(up)                              # first writer of below_conv["gout"]
+            conv_act_rgb(below_conv, below_rgb, grgb, True)
+        conv_tail(L[0])
         return self.gs
 
 

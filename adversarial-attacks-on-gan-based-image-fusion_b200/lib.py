@@ -51,7 +51,7 @@ EXPORTS = [
     "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
-    "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd",
+    "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
     "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_update_patch",
     "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample",
@@ -325,6 +325,12 @@ def torgb_bwd(x, wrgb, s, s_off, grgb, gx, gs):
     n, h, w, c = x.shape
     _chk(load().sfk_torgb_bwd(_p(x), _p(wrgb), _sub(s, s_off), s.shape[1], _p(grgb), _p(gx), _sub(gs, s_off), gs.shape[1], n, h, w,
                               c, _stream()), "torgb_bwd")
+
+
+def act_torgb_bwd(out, gin, gz, d, noise, noise_w, bias, gdacc, wrgb, s, s_off, grgb, gs):
+    n, h, w, c = out.shape
+    _chk(load().sfk_act_torgb_bwd(_p(out), _p(gin), _p(gz), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc), _p(wrgb), _sub(s, s_off),
+                                  s.shape[1], _p(grgb), _sub(gs, s_off), gs.shape[1], n, h, w, c, _stream()), "act_torgb_bwd")
 
 
 def rgb_down(g, gskip):

@@ -173,6 +173,12 @@ int sfk_torgb_fwd(const void* x, const float* wrgb, const float* s, int s_stride
 /* gx[n][h][w][i] = s[n][i]*sum_c wrgb[c][i] grgb[n][c][h][w];  gs[n][i] += sum_hw x*gx~ */
 int sfk_torgb_bwd(const void* x, const float* wrgb, const float* s, int s_stride, const float* grgb, void* gx,
                   float* gs, int gs_stride, int n, int h, int w, int c, sfk_stream_t st);
+/* sfk_torgb_bwd + sfk_act_bwd of the conv feeding the ToRGB in ONE pass (StyledConv -> ToRGB):
+ *   g = (gin ? gin : 0) + s_rgb * (wrgb^T grgb);  gs_rgb += sum_hw out * (wrgb^T grgb);  gz = d * g * act'(out);  gdacc += sum_hw gy*y
+ * gin may be NULL (top resolution) and may alias gz. */
+int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d, const float* noise, float noise_w,
+                      const float* bias, float* gdacc, const float* wrgb, const float* s_rgb, int s_stride,
+                      const float* grgb, float* gs_rgb, int gs_stride, int n, int h, int w, int c, sfk_stream_t st);
 /* transpose of the skip upsample: gskip = upfirdn2d(g, k*4, down=2, pad=(1,2)); planes = n*3 */
 int sfk_rgb_down(const float* g, float* gskip, int planes, int h, int w, sfk_stream_t st);
 

@@ -17,6 +17,30 @@ def main():
         _, g = eng.forward_backward()
         lib.attack_update_linf(eng.x, eng.x0, g, bench.ALPHA, bench.EPS, 1.0, 0.0, 1.0, eng.stats, eng.k_in)
     for _ in range(3): step()
+    if os.environ.get("SFK_PROF_ALL"):
+        # CUDA-event timing of EVERY wrapper call of one step, summed per entry point
+        import collections, types
+        rec = []
+        names = [k for k, v in vars(lib).items() if isinstance(v, types.FunctionType) and not k.startswith("_") and k not in
+                 ("load", "make_igemm_desc", "igemm_flops", "profile_igemm", "role_cycles", "pick_block_n", "conv3x3_taps",
+                  "conv3x3_dgrad_taps", "tconv_taps", "tconv_dgrad_taps", "set_activation_dtype", "activation_dtype", "version")]
+        orig = {k: getattr(lib, k) for k in names}
+        def wrap(k, f):
+            def g(*a, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); r = f(*a, **kw); e1.record(); rec.append((k, e0, e1)); return r
+            return g
+        for k in names: setattr(lib, k, wrap(k, orig[k]))
+        step(); torch.cuda.synchronize()
+        for k in names: setattr(lib, k, orig[k])
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for k, e0, e1 in rec:
+            agg[k][0] += 1; agg[k][1] += e0.elapsed_time(e1) * 1e3
+        tot = sum(v for _, v in agg.values())
+        print(f"{len(rec)} calls, {tot:.0f} us")
+        for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            print(f"  {k:24s} {c:3d} {v:8.1f} us {100 * v / tot:5.1f}%")
+        return
     prof = lib.profile_igemm(step)
     tot = prof["ms"]
     print(f"{prof['launches']} conv launches, {tot:.3f} ms, {prof['flops']/tot/1e9:.1f} TFLOP/s")

@@ -228,10 +228,10 @@ def test_fused_upsample_conv_fwd_bwd(n, h, cin, cout):
         _close(gs, ref_gs, rtol=2e-3, what=f"fused up gs {use_ref}")
 
 
-def test_conv_c3_fwd_bwd():
+@pytest.mark.parametrize("n,h,w,cout", [(2, 20, 24, 64), (1, 9, 7, 32), (3, 5, 18, 8)])
+def test_conv_c3_fwd_bwd(n, h, w, cout):
     from sfattack import lib
     g = _gen(4)
-    n, h, w, cout = 2, 20, 24, 64
     x = torch.randn(n, 3, h, w, generator=g, device=_dev()).requires_grad_(True)
     wt = torch.randn(cout, 3, 3, 3, generator=g, device=_dev()) * 0.2
     b = torch.randn(cout, generator=g, device=_dev()) * 0.1
@@ -410,6 +410,19 @@ def test_act_bwd_and_torgb():
     lib.torgb_bwd(_nhwc(x.detach()), wr, s.detach(), 0, grgb, gx, gs)
     _close(_nchw(gx), gx_ref, what="torgb bwd gx")
     _close(gs, gs_ref, rtol=1e-3, what="torgb bwd gs")
+    # fused: ToRGB backward + activation backward of the conv feeding it, with and without an incoming gradient
+    gt = torch.einsum("ci,bchw->bihw", wr, grgb)
+    for have_gin in (True, False):
+        gin = gout if have_gin else torch.zeros_like(gout)
+        gtot = gin + s.detach()[:, :, None, None] * gt
+        gy2 = gtot * math.sqrt(2) * torch.where(out > 0, 1.0, 0.2)
+        buf = _nhwc(gin).clone()
+        gd2 = torch.zeros(n, c, device=_dev())
+        gs2 = torch.zeros(n, c, device=_dev())
+        lib.act_torgb_bwd(_nhwc(out), buf if have_gin else None, buf, dsc, noise, nw, bias, gd2, wr, s.detach(), 0, grgb, gs2)
+        _close(_nchw(buf), gy2 * dsc[:, :, None, None], what=f"act_torgb_bwd gz gin={have_gin}")
+        _close(gd2, (gy2 * y).sum((2, 3)), rtol=2e-3, what="act_torgb_bwd gdacc")
+        _close(gs2, (out * gt).sum((2, 3)), rtol=1e-3, what="act_torgb_bwd gs_rgb")
     gsk = torch.empty(n, 3, h // 2, h // 2, device=_dev())
     lib.rgb_down(grgb, gsk)
     _close(gsk, gsk_ref, rtol=1e-4, what="rgb_down")
