@@ -815,19 +815,22 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
 
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout, T* __restrict__ gz, const float* __restrict__ d,
-                               const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc, int HW, int C) {
+                               const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
+                               const float* __restrict__ s_in, float* __restrict__ gs_in, int vec_stride, int HW, int C) {
   extern __shared__ float sacc[];
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const long total = static_cast<long>(HW) * vecs;
   const long base = static_cast<long>(n) * HW * C;
   const int cv = threadIdx.x % vecs;
-  float dv[8], bv[8], racc[8];
+  float dv[8], bv[8], racc[8], si[8], rin[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     dv[i] = d[static_cast<long>(n) * C + cv * 8 + i];
     bv[i] = bias[cv * 8 + i];
     racc[i] = 0.f;
+    si[i] = s_in ? s_in[static_cast<long>(n) * vec_stride + cv * 8 + i] : 1.f;
+    rin[i] = 0.f;
   }
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -839,13 +842,18 @@ __global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ 
     const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float gy = gv[i] * lrelu_slope(ov[i]);
+      rin[i] = fmaf(ov[i], gv[i], rin[i]);            // style gradient of the consumer conv: sum out * (unscaled data gradient)
+      const float gy = gv[i] * si[i] * lrelu_slope(ov[i]);
       racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
       o[i] = gy * dv[i];
     }
     store8(gz + off, o);
   }
   flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
+  if (gs_in != nullptr) {
+    __syncthreads();
+    flush_channel_acc(sacc, rin, cv, C, gs_in + static_cast<long>(n) * vec_stride);
+  }
 }
 
 // ============================================================================================
@@ -975,12 +983,12 @@ template <typename T>
 __global__ void act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T* gz, const float* __restrict__ d,
                                      const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
                                      const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride, const float* __restrict__ grgb,
-                                     float* __restrict__ gs, int gs_stride, int HW, int C) {
+                                     float* __restrict__ gs, int gs_stride, const float* __restrict__ s_in, float* __restrict__ gs_in, int HW, int C) {
   extern __shared__ float sacc[];   // [C]
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int cv = threadIdx.x % vecs;
-  float sv[8], dv[8], bv[8], w0[8], w1[8], w2[8], racc[8], rrgb[8];
+  float sv[8], dv[8], bv[8], w0[8], w1[8], w2[8], racc[8], rrgb[8], si[8], rin[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cv * 8 + i;
@@ -992,6 +1000,8 @@ __global__ void act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T*
     w2[i] = wrgb[2 * C + c];
     racc[i] = 0.f;
     rrgb[i] = 0.f;
+    si[i] = s_in ? s_in[static_cast<long>(n) * s_stride + c] : 1.f;
+    rin[i] = 0.f;
   }
   const long total = static_cast<long>(HW) * vecs;
   const long base = static_cast<long>(n) * HW * C;
@@ -1014,7 +1024,8 @@ __global__ void act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T*
     for (int i = 0; i < 8; ++i) {
       const float gt = w0[i] * ga + w1[i] * gb + w2[i] * gc;
       rrgb[i] = fmaf(ov[i], gt, rrgb[i]);
-      const float gy = fmaf(sv[i], gt, gv[i]) * lrelu_slope(ov[i]);
+      rin[i] = fmaf(ov[i], gv[i], rin[i]);
+      const float gy = fmaf(sv[i], gt, gv[i] * si[i]) * lrelu_slope(ov[i]);
       racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
       o[i] = gy * dv[i];
     }
@@ -1023,6 +1034,10 @@ __global__ void act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T*
   flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
   __syncthreads();
   flush_channel_acc(sacc, rrgb, cv, C, gs + static_cast<long>(n) * gs_stride);
+  if (gs_in != nullptr) {
+    __syncthreads();
+    flush_channel_acc(sacc, rin, cv, C, gs_in + static_cast<long>(n) * gs_stride);
+  }
 }
 
 __global__ void rgb_down_kernel(const float* __restrict__ g, float* __restrict__ gs, long planes, int H, int W) {
@@ -1557,13 +1572,13 @@ int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d
 }
 
 int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w, const float* bias, float* gdacc,
-                int n, int h, int w, int c, sfk_stream_t st) {
+                const float* s_in, float* gs_in, int vec_stride, int n, int h, int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(out && gout && gz && d && bias && gdacc && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "act_bwd: bad args");
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);
       act_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
-      static_cast<const T*>(out), static_cast<const T*>(gout), static_cast<T*>(gz), d, noise, noise_w, bias, gdacc, h * w, c);
+      static_cast<const T*>(out), static_cast<const T*>(gout), static_cast<T*>(gz), d, noise, noise_w, bias, gdacc, s_in, gs_in, vec_stride, h * w, c);
     };
     if (sfk_act_f32()) run(float{}); else run(bf16{});
   }
@@ -1601,8 +1616,8 @@ int sfk_torgb_bwd(const void* x, const float* wrgb, const float* sv, int s_strid
 }
 
 int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d, const float* noise, float noise_w, const float* bias,
-                      float* gdacc, const float* wrgb, const float* sv, int s_stride, const float* grgb, float* gs, int gs_stride, int n, int h,
-                      int w, int c, sfk_stream_t st) {
+                      float* gdacc, const float* wrgb, const float* sv, int s_stride, const float* grgb, float* gs, int gs_stride,
+                      const float* s_in, float* gs_in, int n, int h, int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(out && gz && d && bias && gdacc && wrgb && sv && grgb && gs && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG,
               "act_torgb_bwd: bad args");
   {
@@ -1610,7 +1625,7 @@ int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d
       using T = decltype(tag);
       act_torgb_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
           static_cast<const T*>(out), static_cast<const T*>(gin), static_cast<T*>(gz), d, noise, noise_w, bias, gdacc, wrgb, sv, s_stride, grgb, gs,
-          gs_stride, h * w, c);
+          gs_stride, s_in, gs_in, h * w, c);
     };
     if (sfk_act_f32()) run(float{}); else run(bf16{});
   }

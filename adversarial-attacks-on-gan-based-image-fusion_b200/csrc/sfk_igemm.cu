@@ -1193,7 +1193,9 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   //  lose ~8 % to the narrower tile, so they keep the dy-shared mode)
   const bool light_epilogue = (d->flags & (SFK_EP_GSDOT | SFK_EP_XMASK)) == 0;
   // the fused-resampling launches (4 phases of weights) keep their whole weight set resident at one CTA per SM
-  const int resident_limit = (d->out_d2s || d->a_s2d) ? 150 * 1024 : 72 * 1024;
+  static int rl_env = -2;
+  if (rl_env == -2) { const char* e = getenv("SFK_S2D_RESIDENT"); rl_env = e ? atoi(e) : 0; }   // measured at 1024^2: streamed weights at 2 CTAs/SM 455 us, resident at 1 CTA/SM 571 us
+  const int resident_limit = (d->out_d2s || (d->a_s2d && rl_env)) ? 150 * 1024 : 72 * 1024;
   const bool halo = k.TW == 16 && !d->a_s2d && !d->out_d2s && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= resident_limit && light_epilogue));
   const bool share = k.TW >= 8;
   int ng = 0;

@@ -267,10 +267,20 @@ class SynthesisEngine:
                     lib.conv3x3_taps(l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,   # demod is folded into wmod
                     bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err)
                 gx_dst = prev_conv["gout"] if prev_conv is not None else self.gx_scratch
-                e["bwd"] = lib.make_igemm_desc(
-                    e["gout"], B, l.res, l.res, l.cout, 1, e["wT"], 1, 9 * l.cin, gx_dst, l.res, l.res, l.cin, 1,
-                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=x,
-                    colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
+                # The style modulation (x s) and style gradient (sum x*gx~) of a data gradient are finished by the kernel that
+                # consumes it (act_bwd / act_torgb_bwd stream both tensors anyway) wherever such a consumer exists; the launch
+                # itself then has the plain epilogue.  Exceptions: conv1 (no consumer) and convs fed by an unfused up-layer
+                # (consumer is the blur kernel).
+                e["deferred"] = prev_conv is not None and prev_conv["fused_up"]
+                if e["deferred"]:
+                    e["bwd"] = lib.make_igemm_desc(
+                        e["gout"], B, l.res, l.res, l.cout, 1, e["wT"], 1, 9 * l.cin, gx_dst, l.res, l.res, l.cin, 1,
+                        lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), err=self.err)
+                else:
+                    e["bwd"] = lib.make_igemm_desc(
+                        e["gout"], B, l.res, l.res, l.cout, 1, e["wT"], 1, 9 * l.cin, gx_dst, l.res, l.res, l.cin, 1,
+                        lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=x,
+                        colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
             elif e["fused_up"]:
                 h = l.res // 2
                 wmod = self.wmod[: B * 36 * l.cout * l.cin].view(B, 36 * l.cout, l.cin)
@@ -281,8 +291,8 @@ class SynthesisEngine:
                     bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err, out_d2s=1)
                 e["bwd"] = lib.make_igemm_desc(
                     e["gout"], B, h, h, 4 * l.cout, 1, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1,
-                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE,
-                    xin=x, colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err, a_s2d=1)
+                    lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), err=self.err, a_s2d=1)   # finished by act_torgb_bwd
+                e["deferred"] = True
             else:  # up
                 h = l.res // 2
                 wmod = self.wmod[: B * 9 * l.cout * l.cin].view(B, 9 * l.cout, l.cin)
@@ -294,8 +304,8 @@ class SynthesisEngine:
                 # data gradient is the first writer of the gradient buffer of the previous resolution's conv
                 e["bwd"] = lib.make_igemm_desc(
                     T, B, h + 1, h + 1, l.cout, 4, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1, lib.pick_block_n(l.cin),
-                    lib.tconv_dgrad_taps(l.cin), flags=lib.EP_GSDOT | lib.EP_COLSCALE, xin=x, colscale=self.s,
-                    gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
+                    lib.tconv_dgrad_taps(l.cin), err=self.err)                                         # finished by act_torgb_bwd
+                e["deferred"] = True
             x = e["out"]
             prev_conv = e
 
@@ -351,26 +361,29 @@ class SynthesisEngine:
             lib.igemm(e["bwd"])                       # -> gradient of the producer of x, + fused style gradient
             lib.demod_bwd(s, e["l"].s_off, e["Q"], e["d"], e["gdacc"], self.gs)
 
-        def conv_act_rgb(conv, rgb, grgb, have_gin):
-            # ToRGB backward and the conv's activation backward in one pass over conv["out"] / conv["gout"]
-            lib.act_torgb_bwd(conv["out"], conv["gout"] if have_gin else None, conv["gout"], conv["d"], conv["noise"], conv["noise_w"],
-                              conv["bias"], conv["gdacc"], rgb["wrgb"], s, rgb["l"].s_off, grgb, self.gs)
+        def conv_act_rgb(conv, rgb, grgb, producer):
+            # ToRGB backward and the conv's activation backward in one pass over conv["out"] / conv["gout"]; `producer` is the
+            # up-layer whose plain data gradient already sits in conv["gout"] (its modulation + style gradient are finished here)
+            lib.act_torgb_bwd(conv["out"], conv["gout"] if producer is not None else None, conv["gout"], conv["d"], conv["noise"],
+                              conv["noise_w"], conv["bias"], conv["gdacc"], rgb["wrgb"], s, rgb["l"].s_off, grgb, self.gs,
+                              in_off=producer["l"].s_off if producer is not None else None)
 
         conv, rgb = (L[3 + 3 * (nb - 1)], L[4 + 3 * (nb - 1)]) if nb > 0 else (L[0], L[1])
         grgb = g_img
-        conv_act_rgb(conv, rgb, grgb, False)
+        conv_act_rgb(conv, rgb, grgb, None)
         for k in range(nb - 1, -1, -1):
             up, conv = L[2 + 3 * k], L[3 + 3 * k]
             below_conv, below_rgb = (L[3 + 3 * (k - 1)], L[4 + 3 * (k - 1)]) if k > 0 else (L[0], L[1])
             conv_tail(conv)                            # writes up["gout"]
             if up["fused_up"]:
-                lib.act_bwd(up["out"], up["gout"], up["gout"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
+                lib.act_bwd(up["out"], up["gout"], up["gout"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"],
+                            s_in=s, gs_in=self.gs, in_off=conv["l"].s_off)
             else:
                 lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
             lib.rgb_down(grgb, below_rgb["grgb"])
             grgb = below_rgb["grgb"]
             conv_tail(up)                              # first writer of below_conv["gout"]
-            conv_act_rgb(below_conv, below_rgb, grgb, True)
+            conv_act_rgb(below_conv, below_rgb, grgb, up)
         conv_tail(L[0])
         return self.gs
 

@@ -309,10 +309,13 @@ def blur_act_bwd(out, gout, gT, d, noise, noise_w, bias, gdacc):
                                  c, _stream()), "blur_act_bwd")
 
 
-def act_bwd(out, gout, gz, d, noise, noise_w, bias, gdacc):
+def act_bwd(out, gout, gz, d, noise, noise_w, bias, gdacc, s_in=None, gs_in=None, in_off=0):
+    """s_in / gs_in (B, s_dim) + in_off: finish a flags-0 data gradient of the conv that consumes `out` (see sfk.h)."""
     n, h, w, c = out.shape
-    _chk(load().sfk_act_bwd(_p(out), _p(gout), _p(gz), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc), n, h, w, c, _stream()),
-         "act_bwd")
+    _chk(load().sfk_act_bwd(_p(out), _p(gout), _p(gz), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc),
+                            _sub(s_in, in_off) if s_in is not None else C.c_void_p(0),
+                            _sub(gs_in, in_off) if gs_in is not None else C.c_void_p(0),
+                            s_in.shape[1] if s_in is not None else 0, n, h, w, c, _stream()), "act_bwd")
 
 
 def torgb_fwd(x, wrgb, s, s_off, bias, skip, rgb):
@@ -327,10 +330,13 @@ def torgb_bwd(x, wrgb, s, s_off, grgb, gx, gs):
                               c, _stream()), "torgb_bwd")
 
 
-def act_torgb_bwd(out, gin, gz, d, noise, noise_w, bias, gdacc, wrgb, s, s_off, grgb, gs):
+def act_torgb_bwd(out, gin, gz, d, noise, noise_w, bias, gdacc, wrgb, s, s_off, grgb, gs, in_off=None):
+    """in_off: s_off of the conv whose flags-0 data gradient wrote `gin` (its modulation and style gradient are finished here)."""
     n, h, w, c = out.shape
+    fin = in_off is not None and gin is not None
     _chk(load().sfk_act_torgb_bwd(_p(out), _p(gin), _p(gz), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc), _p(wrgb), _sub(s, s_off),
-                                  s.shape[1], _p(grgb), _sub(gs, s_off), gs.shape[1], n, h, w, c, _stream()), "act_torgb_bwd")
+                                  s.shape[1], _p(grgb), _sub(gs, s_off), gs.shape[1], _sub(s, in_off) if fin else C.c_void_p(0),
+                                  _sub(gs, in_off) if fin else C.c_void_p(0), n, h, w, c, _stream()), "act_torgb_bwd")
 
 
 def rgb_down(g, gskip):

@@ -166,19 +166,25 @@ int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d
                      const float* bias, float* gdacc, int n, int h, int w, int c, sfk_stream_t st);
 /* backward of FusedLeakyReLU+noise+demod for non-upsampling layers: gz = d*act'(out)*gout (in place ok) */
 int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w,
-                const float* bias, float* gdacc, int n, int h, int w, int c, sfk_stream_t st);
+                const float* bias, float* gdacc, const float* s_in, float* gs_in, int vec_stride, int n, int h, int w, int c,
+                sfk_stream_t st);
 /* ToRGB: rgb[n][c][h][w] = sum_i wrgb[c][i] s[n][i] x[n][h][w][i] + bias[c] + upsample2(skip) */
 int sfk_torgb_fwd(const void* x, const float* wrgb, const float* s, int s_stride, const float* bias, const float* skip,
                   float* rgb, int n, int h, int w, int c, sfk_stream_t st);
 /* gx[n][h][w][i] = s[n][i]*sum_c wrgb[c][i] grgb[n][c][h][w];  gs[n][i] += sum_hw x*gx~ */
 int sfk_torgb_bwd(const void* x, const float* wrgb, const float* s, int s_stride, const float* grgb, void* gx,
                   float* gs, int gs_stride, int n, int h, int w, int c, sfk_stream_t st);
+/* s_in / gs_in (both optional, in sfk_act_bwd and sfk_act_torgb_bwd): when the incoming gradient was written by a data-gradient
+ * launch WITHOUT its style epilogue (flags 0), the consumer finishes it while it streams the two tensors anyway:
+ *   gs_in[n][c] += sum_hw out * gin   (style gradient of the consuming conv; its input IS this layer's output)
+ *   gin <- s_in[n][c] * gin           (modulation of that conv).  Strides: vec_stride (act_bwd) / s_stride, gs_stride (act_torgb_bwd). */
 /* sfk_torgb_bwd + sfk_act_bwd of the conv feeding the ToRGB in ONE pass (StyledConv -> ToRGB):
  *   g = (gin ? gin : 0) + s_rgb * (wrgb^T grgb);  gs_rgb += sum_hw out * (wrgb^T grgb);  gz = d * g * act'(out);  gdacc += sum_hw gy*y
  * gin may be NULL (top resolution) and may alias gz. */
 int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d, const float* noise, float noise_w,
                       const float* bias, float* gdacc, const float* wrgb, const float* s_rgb, int s_stride,
-                      const float* grgb, float* gs_rgb, int gs_stride, int n, int h, int w, int c, sfk_stream_t st);
+                      const float* grgb, float* gs_rgb, int gs_stride, const float* s_in, float* gs_in, int n, int h, int w,
+                      int c, sfk_stream_t st);
 /* transpose of the skip upsample: gskip = upfirdn2d(g, k*4, down=2, pad=(1,2)); planes = n*3 */
 int sfk_rgb_down(const float* g, float* gskip, int planes, int h, int w, sfk_stream_t st);
 

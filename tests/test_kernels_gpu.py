@@ -392,6 +392,18 @@ def test_act_bwd_and_torgb():
     y = torch.where(out > 0, out / math.sqrt(2), out / (0.2 * math.sqrt(2))) - nw * noise - bias.view(1, -1, 1, 1)
     _close(_nchw(gz), gy * dsc[:, :, None, None], what="act_bwd gz")
     _close(gd, (gy * y).sum((2, 3)), rtol=2e-3, what="act_bwd gdacc")
+    # ... finishing a plain (flags 0) data gradient of the consumer conv: gout <- s_in * gout, gs_in += sum out * gout
+    SD, off = 3 * c, c
+    s_all = torch.randn(n, SD, generator=g, device=_dev()) + 1
+    gs_all = torch.zeros(n, SD, device=_dev())
+    gd.zero_()
+    lib.act_bwd(_nhwc(out), _nhwc(gout), gz, dsc, noise, nw, bias, gd, s_in=s_all, gs_in=gs_all, in_off=off)
+    sin = s_all[:, off:off + c]
+    gy_s = gout * sin[:, :, None, None] * math.sqrt(2) * torch.where(out > 0, 1.0, 0.2)
+    _close(_nchw(gz), gy_s * dsc[:, :, None, None], what="act_bwd(s_in) gz")
+    _close(gd, (gy_s * y).sum((2, 3)), rtol=2e-3, what="act_bwd(s_in) gdacc")
+    _close(gs_all[:, off:off + c], (out * gout).sum((2, 3)), rtol=1e-3, what="act_bwd gs_in")
+    assert gs_all[:, :off].abs().max() == 0 and gs_all[:, off + c:].abs().max() == 0
     # ToRGB forward / backward with skip upsample
     x = _rb(n, c, h, h, g=g).requires_grad_(True)
     wr = torch.randn(3, c, generator=g, device=_dev()) / math.sqrt(c)
@@ -423,6 +435,20 @@ def test_act_bwd_and_torgb():
         _close(_nchw(buf), gy2 * dsc[:, :, None, None], what=f"act_torgb_bwd gz gin={have_gin}")
         _close(gd2, (gy2 * y).sum((2, 3)), rtol=2e-3, what="act_torgb_bwd gdacc")
         _close(gs2, (out * gt).sum((2, 3)), rtol=1e-3, what="act_torgb_bwd gs_rgb")
+    # and with the producer's modulation / style gradient finished in the same pass (styles live in one (n, SD) vector)
+    s3 = torch.randn(n, SD, generator=g, device=_dev()) + 1
+    gs3 = torch.zeros(n, SD, device=_dev())
+    s_rgb, s_prod = s3[:, :c], s3[:, 2 * c:]
+    gtot = gout * s_prod[:, :, None, None] + s_rgb[:, :, None, None] * gt
+    gy3 = gtot * math.sqrt(2) * torch.where(out > 0, 1.0, 0.2)
+    buf = _nhwc(gout).clone()
+    gd3 = torch.zeros(n, c, device=_dev())
+    lib.act_torgb_bwd(_nhwc(out), buf, buf, dsc, noise, nw, bias, gd3, wr, s3, 0, grgb, gs3, in_off=2 * c)
+    _close(_nchw(buf), gy3 * dsc[:, :, None, None], what="act_torgb_bwd(s_in) gz")
+    _close(gd3, (gy3 * y).sum((2, 3)), rtol=2e-3, what="act_torgb_bwd(s_in) gdacc")
+    _close(gs3[:, :c], (out * gt).sum((2, 3)), rtol=1e-3, what="act_torgb_bwd(s_in) gs_rgb")
+    _close(gs3[:, 2 * c:], (out * gout).sum((2, 3)), rtol=1e-3, what="act_torgb_bwd gs_in")
+    assert gs3[:, c:2 * c].abs().max() == 0
     gsk = torch.empty(n, 3, h // 2, h // 2, device=_dev())
     lib.rgb_down(grgb, gsk)
     _close(gsk, gsk_ref, rtol=1e-4, what="rgb_down")
