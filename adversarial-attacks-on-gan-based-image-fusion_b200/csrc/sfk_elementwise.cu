@@ -813,6 +813,10 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
   (void)sred;
 }
 
+// The activation is piecewise linear through 0, so with m = act'(out) the pre-activation is out / m and
+//   gy * y = (g m)(out/m - nz - b) = g*out - gy (nz + b):
+// the first term is the same sum the consumer conv's style gradient needs (rin), the second is accumulated on the OUTPUT value
+// gz = gy d and divided by d (> 0) once at the end.  Six ALU ops per element instead of eleven.
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout, T* __restrict__ gz, const float* __restrict__ d,
                                const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
@@ -823,7 +827,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ 
   const long total = static_cast<long>(HW) * vecs;
   const long base = static_cast<long>(n) * HW * C;
   const int cv = threadIdx.x % vecs;
-  float dv[8], bv[8], racc[8], si[8], rin[8];
+  float dv[8], bv[8], racc[8], si[8], rin[8], kp[8], kn[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     dv[i] = d[static_cast<long>(n) * C + cv * 8 + i];
@@ -831,24 +835,46 @@ __global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ 
     racc[i] = 0.f;
     si[i] = s_in ? s_in[static_cast<long>(n) * vec_stride + cv * 8 + i] : 1.f;
     rin[i] = 0.f;
+    kp[i] = si[i] * dv[i] * SFK_SQRT2;          // gz = g * (out > 0 ? kp : kn)
+    kn[i] = kp[i] * 0.2f;
   }
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = idx / vecs;
-    const long off = base + p * C + cv * 8;
-    float ov[8], gv[8], o[8];
-    load8(out + off, ov);
-    load8p(gout + off, gv);   // gz may alias gout (in-place)
-    const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
+  // two pixels per iteration: both loads are in flight before the first is consumed (the kernel is bound by memory latency x
+  // occupancy, not by bandwidth, at one 32-byte request per thread)
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += 2 * stride) {
+    const long pA = idx / vecs, pB = (idx + stride) / vecs;
+    const bool hasB = idx + stride < total;
+    const long offA = base + pA * C + cv * 8, offB = base + pB * C + cv * 8;
+    float ovA[8], gvA[8], ovB[8], gvB[8], o[8];
+    load8(out + offA, ovA);
+    load8p(gout + offA, gvA);   // gz may alias gout (in-place)
+    float nzA = noise ? __ldg(noise + pA) : 0.f, nzB = 0.f;
+    if (hasB) {
+      load8(out + offB, ovB);
+      load8p(gout + offB, gvB);
+      nzB = noise ? __ldg(noise + pB) : 0.f;
+    }
+    nzA *= noise_w;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      rin[i] = fmaf(ov[i], gv[i], rin[i]);            // style gradient of the consumer conv: sum out * (unscaled data gradient)
-      const float gy = gv[i] * si[i] * lrelu_slope(ov[i]);
-      racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
-      o[i] = gy * dv[i];
+      rin[i] = fmaf(ovA[i], gvA[i], rin[i]);
+      o[i] = gvA[i] * (ovA[i] > 0.f ? kp[i] : kn[i]);
+      racc[i] = fmaf(o[i], nzA + bv[i], racc[i]);
     }
-    store8(gz + off, o);
+    store8(gz + offA, o);
+    if (hasB) {
+      nzB *= noise_w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rin[i] = fmaf(ovB[i], gvB[i], rin[i]);
+        o[i] = gvB[i] * (ovB[i] > 0.f ? kp[i] : kn[i]);
+        racc[i] = fmaf(o[i], nzB + bv[i], racc[i]);
+      }
+      store8(gz + offB, o);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) racc[i] = si[i] * rin[i] - racc[i] / dv[i];
   flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
   if (gs_in != nullptr) {
     __syncthreads();
@@ -980,57 +1006,89 @@ __global__ void torgb_bwd_kernel(const T* __restrict__ x, const float* __restric
 //   gs_rgb[n][i] += sum_hw out * (wrgb^T grgb)                      (ToRGB style gradient)
 //   gy  = g * act'(out);  gdacc[n][j] += sum_hw gy * y;  gz = gy * d      (as act_bwd)
 template <typename T>
-__global__ void act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T* gz, const float* __restrict__ d,
-                                     const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
-                                     const float* __restrict__ wrgb, const float* __restrict__ s, int s_stride, const float* __restrict__ grgb,
-                                     float* __restrict__ gs, int gs_stride, const float* __restrict__ s_in, float* __restrict__ gs_in, int HW, int C) {
-  extern __shared__ float sacc[];   // [C]
+__global__ void __launch_bounds__(kBlock, 2)
+act_torgb_bwd_kernel(const T* __restrict__ out, const T* gin, T* gz, const float* __restrict__ d, const float* __restrict__ noise, float noise_w,
+                     const float* __restrict__ bias, float* __restrict__ gdacc, const float* __restrict__ wrgb, const float* __restrict__ s,
+                     int s_stride, const float* __restrict__ grgb, float* __restrict__ gs, int gs_stride, const float* __restrict__ s_in,
+                     float* __restrict__ gs_in, int HW, int C) {
+  extern __shared__ __align__(16) float sm[];   // [C] accumulator scratch, then ToRGB weights as [C/8][3][8]
+  float* sacc = sm;
+  float* sw = sm + C;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    const int col = i / C, c = i % C;
+    sw[((c >> 3) * 3 + col) * 8 + (c & 7)] = wrgb[i];
+  }
+  __syncthreads();
   const int n = blockIdx.y;
   const int vecs = C / 8;
   const int cv = threadIdx.x % vecs;
-  float sv[8], dv[8], bv[8], w0[8], w1[8], w2[8], racc[8], rrgb[8], si[8], rin[8];
+  const float4* wq = reinterpret_cast<const float4*>(sw + cv * 24);
+  float sv[8], bv[8], racc[8], rrgb[8], si[8], rin[8], kp[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cv * 8 + i;
     sv[i] = s[static_cast<long>(n) * s_stride + c];
-    dv[i] = d[static_cast<long>(n) * C + c];
     bv[i] = bias[c];
-    w0[i] = wrgb[c];
-    w1[i] = wrgb[C + c];
-    w2[i] = wrgb[2 * C + c];
     racc[i] = 0.f;
     rrgb[i] = 0.f;
     si[i] = s_in ? s_in[static_cast<long>(n) * s_stride + c] : 1.f;
     rin[i] = 0.f;
+    kp[i] = d[static_cast<long>(n) * C + c] * SFK_SQRT2;      // gz = g * kp * (out > 0 ? 1 : 0.2)
   }
   const long total = static_cast<long>(HW) * vecs;
   const long base = static_cast<long>(n) * HW * C;
   const float* g0 = grgb + static_cast<long>(n) * 3 * HW;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long p = idx / vecs;
-    const long off = base + p * C + cv * 8;
-    const float ga = __ldg(g0 + p), gb = __ldg(g0 + HW + p), gc = __ldg(g0 + 2L * HW + p);
-    float ov[8], gv[8], o[8];
-    load8(out + off, ov);
-    if (gin != nullptr) {
-      load8p(gin + off, gv);   // gz may alias gin (in-place)
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) gv[i] = 0.f;
-    }
-    const float nz = noise ? noise_w * __ldg(noise + p) : 0.f;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  auto body = [&](const float (&ov)[8], const float (&gv)[8], float ga, float gb, float gc, float nz, long off) {
+    const float4 r0 = wq[0], r1 = wq[1], q0 = wq[2], q1 = wq[3], b0 = wq[4], b1 = wq[5];
+    const float w0[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const float w1[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const float w2[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float gt = w0[i] * ga + w1[i] * gb + w2[i] * gc;
       rrgb[i] = fmaf(ov[i], gt, rrgb[i]);
       rin[i] = fmaf(ov[i], gv[i], rin[i]);
-      const float gy = fmaf(sv[i], gt, gv[i] * si[i]) * lrelu_slope(ov[i]);
-      racc[i] = fmaf(gy, lrelu_inv(ov[i]) - nz - bv[i], racc[i]);
-      o[i] = gy * dv[i];
+      const float g = fmaf(sv[i], gt, gv[i] * si[i]);
+      o[i] = g * kp[i] * (ov[i] > 0.f ? 1.f : 0.2f);
+      racc[i] = fmaf(o[i], nz + bv[i], racc[i]);
     }
     store8(gz + off, o);
+  };
+  // two pixels per iteration so that both sets of loads are in flight together (see act_bwd_kernel)
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += 2 * stride) {
+    const long pA = idx / vecs, pB = (idx + stride) / vecs;
+    const bool hasB = idx + stride < total;
+    const long offA = base + pA * C + cv * 8, offB = base + pB * C + cv * 8;
+    float ovA[8], gvA[8], ovB[8], gvB[8];
+    load8(out + offA, ovA);
+    if (gin != nullptr) {
+      load8p(gin + offA, gvA);   // gz may alias gin (in-place)
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gvA[i] = 0.f;
+    }
+    const float gaA = __ldg(g0 + pA), gbA = __ldg(g0 + HW + pA), gcA = __ldg(g0 + 2L * HW + pA);
+    const float nzA = noise ? __ldg(noise + pA) : 0.f;
+    float gaB = 0.f, gbB = 0.f, gcB = 0.f, nzB = 0.f;
+    if (hasB) {
+      load8(out + offB, ovB);
+      if (gin != nullptr) {
+        load8p(gin + offB, gvB);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gvB[i] = 0.f;
+      }
+      gaB = __ldg(g0 + pB); gbB = __ldg(g0 + HW + pB); gcB = __ldg(g0 + 2L * HW + pB);
+      nzB = noise ? __ldg(noise + pB) : 0.f;
+    }
+    body(ovA, gvA, gaA, gbA, gcA, noise_w * nzA, offA);
+    if (hasB) body(ovB, gvB, gaB, gbB, gcB, noise_w * nzB, offB);
   }
+  // gy*y = g*out - gy*(nz+b)  (see act_bwd_kernel);  sum g*out = s_in*rin + s_rgb*rrgb;  racc was accumulated on gz = gy*d
+#pragma unroll
+  for (int i = 0; i < 8; ++i) racc[i] = si[i] * rin[i] + sv[i] * rrgb[i] - racc[i] * SFK_SQRT2 / kp[i];
   flush_channel_acc(sacc, racc, cv, C, gdacc + static_cast<long>(n) * C);
   __syncthreads();
   flush_channel_acc(sacc, rrgb, cv, C, gs + static_cast<long>(n) * gs_stride);
@@ -1623,7 +1681,7 @@ int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);
-      act_torgb_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
+      act_torgb_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, 4 * c * sizeof(float), S_(st)>>>(
           static_cast<const T*>(out), static_cast<const T*>(gin), static_cast<T*>(gz), d, noise, noise_w, bias, gdacc, wrgb, sv, s_stride, grgb, gs,
           gs_stride, s_in, gs_in, h * w, c);
     };
