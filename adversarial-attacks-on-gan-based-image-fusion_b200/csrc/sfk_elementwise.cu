@@ -557,6 +557,94 @@ __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const f
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// All modulated-conv layers of the generator in ONE launch each (the per-layer kernels above stay for single-layer callers):
+// the styles of every layer are known before the first conv runs, and the demodulation gradient is only consumed after the last.
+// Layer table (device, int64 [n_layers][SFK_STYLE_TAB_COLS]): s_off, cin, cout, q_off, d_off, rows, wb_off, wm_off, d_cols, fold
+//   q_off / d_off / wb_off / wm_off index the concatenated Q (cout x cin), d and gdacc ([n][cout] per layer), base weights
+//   ([rows][cin]) and modulated weights ([n][rows][cin] per layer) buffers; rows = taps * (cout or 4*cout); fold != 0 folds d in.
+__global__ void demod_fwd_batched_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ Qc, float* __restrict__ dc,
+                                         const long long* __restrict__ tab, int N) {
+  const long long* t = tab + static_cast<long>(blockIdx.y) * SFK_STYLE_TAB_COLS;
+  const int s_off = static_cast<int>(t[0]), Cin = static_cast<int>(t[1]), Cout = static_cast<int>(t[2]);
+  const float* Q = Qc + t[3];
+  float* d = dc + t[4];
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = N * Cout;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < total; r += warps) {
+    const int j = r % Cout, n = r / Cout;
+    float acc = 0.f;
+    for (int i = lane; i < Cin; i += 32) {
+      const float sv = __ldg(s + static_cast<long>(n) * s_stride + s_off + i);
+      acc = fmaf(sv * sv, __ldg(Q + static_cast<long>(j) * Cin + i), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) d[r] = rsqrtf(acc + 1e-8f);
+  }
+}
+
+template <typename T>
+__global__ void modulate_weights_batched_kernel(const float* __restrict__ wbc, const float* __restrict__ s, int s_stride, T* __restrict__ wmc,
+                                                const float* __restrict__ dc, const long long* __restrict__ tab, int N) {
+  const long long* t = tab + static_cast<long>(blockIdx.y) * SFK_STYLE_TAB_COLS;
+  const int s_off = static_cast<int>(t[0]), Cin = static_cast<int>(t[1]), Cout = static_cast<int>(t[2]);
+  const long rows = t[5];
+  const float* wbase = wbc + t[6];
+  T* wmod = wmc + t[7] * N;
+  const int d_cols = static_cast<int>(t[8]);
+  const float* d = t[9] ? dc + t[4] : nullptr;
+  const int rows_per_tap = static_cast<int>(rows / 9);
+  const int vecs = Cin / 8;
+  const long total = static_cast<long>(N) * rows * vecs;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = idx % vecs;
+    const long r = (idx / vecs) % rows;
+    const int n = idx / (vecs * rows);
+    const float4* wp = reinterpret_cast<const float4*>(wbase + r * Cin + v * 8);
+    const float4* sp = reinterpret_cast<const float4*>(s + static_cast<long>(n) * s_stride + s_off + v * 8);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
+    if (d != nullptr) {
+      const float dv = __ldg(d + static_cast<long>(n) * d_cols + (r % rows_per_tap) % d_cols);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] *= dv;
+    }
+    store8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, o);
+  }
+  (void)Cout;
+}
+
+__global__ void demod_bwd_batched_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ Qc, const float* __restrict__ dc,
+                                         const float* __restrict__ gdc, float* __restrict__ gs, int gs_stride, const long long* __restrict__ tab) {
+  __shared__ float red[8][33];
+  const long long* t = tab + static_cast<long>(blockIdx.z) * SFK_STYLE_TAB_COLS;
+  const int s_off = static_cast<int>(t[0]), Cin = static_cast<int>(t[1]), Cout = static_cast<int>(t[2]);
+  if (static_cast<int>(blockIdx.x) * 32 >= Cin) return;
+  const float* Q = Qc + t[3];
+  const float* d = dc + t[4];
+  const float* gdacc = gdc + t[4];
+  const int n = blockIdx.y;
+  const int li = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + li;
+  float acc = 0.f;
+  if (i < Cin) {
+    for (int j = sl; j < Cout; j += 8) {
+      const float dj = __ldg(d + n * Cout + j);
+      acc = fmaf(__ldg(gdacc + n * Cout + j) * dj * dj, __ldg(Q + static_cast<long>(j) * Cin + i), acc);
+    }
+  }
+  red[sl][li] = acc;
+  __syncthreads();
+  if (sl == 0 && i < Cin) {
+    float tt = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tt += red[q][li];
+    gs[static_cast<long>(n) * gs_stride + s_off + i] -= __ldg(s + static_cast<long>(n) * s_stride + s_off + i) * tt;
+  }
+}
+
 // ============================================================================================
 // blur (upfirdn2d [1,3,3,1], pad (1,1)) over the phase-planar transposed-conv output, fused with
 // demod, noise, bias, leaky-relu
@@ -1562,6 +1650,32 @@ int sfk_demod_bwd(const float* sv, int s_stride, const float* Q, const float* d,
   SFK_REQUIRE(sv && Q && d && gdacc && gs, SFK_E_ARG, "demod_bwd: null");
   demod_bwd_kernel<<<dim3((cin + 31) / 32, n), 256, 0, S_(st)>>>(sv, s_stride, Q, d, gdacc, gs, gs_stride, n, cin, cout);
   return sfk_check_launch("demod_bwd");
+}
+
+int sfk_demod_fwd_batched(const float* sv, int s_stride, const float* q_cat, float* d_cat, const long long* tab, int n_layers, int n,
+                          int max_cout, sfk_stream_t st) {
+  SFK_REQUIRE(sv && q_cat && d_cat && tab && n_layers > 0 && max_cout > 0, SFK_E_ARG, "demod_fwd_batched: bad args");
+  demod_fwd_batched_kernel<<<dim3(grid_for(static_cast<long>(n) * max_cout * 32, 2), n_layers), kBlock, 0, S_(st)>>>(sv, s_stride, q_cat, d_cat, tab, n);
+  return sfk_check_launch("demod_fwd_batched");
+}
+
+int sfk_modulate_weights_batched(const float* wbase_cat, const float* sv, int s_stride, void* wmod_cat, const float* d_cat, const long long* tab,
+                                 int n_layers, int n, sfk_stream_t st) {
+  SFK_REQUIRE(wbase_cat && sv && wmod_cat && d_cat && tab && n_layers > 0 && s_stride % 4 == 0, SFK_E_ARG, "modulate_weights_batched: bad args");
+  SFK_REQUIRE(sfk_aligned16(wbase_cat) && sfk_aligned16(sv) && sfk_aligned16(wmod_cat), SFK_E_ALIGN, "modulate_weights_batched: alignment");
+  const unsigned gx = static_cast<unsigned>((sfk_num_sms() * 8 + n_layers - 1) / n_layers);
+  if (sfk_act_f32())
+    modulate_weights_batched_kernel<float><<<dim3(gx, n_layers), kBlock, 0, S_(st)>>>(wbase_cat, sv, s_stride, static_cast<float*>(wmod_cat), d_cat, tab, n);
+  else
+    modulate_weights_batched_kernel<bf16><<<dim3(gx, n_layers), kBlock, 0, S_(st)>>>(wbase_cat, sv, s_stride, static_cast<bf16*>(wmod_cat), d_cat, tab, n);
+  return sfk_check_launch("modulate_weights_batched");
+}
+
+int sfk_demod_bwd_batched(const float* sv, int s_stride, const float* q_cat, const float* d_cat, const float* gd_cat, float* gs, int gs_stride,
+                          const long long* tab, int n_layers, int n, int max_cin, sfk_stream_t st) {
+  SFK_REQUIRE(sv && q_cat && d_cat && gd_cat && gs && tab && n_layers > 0 && max_cin > 0, SFK_E_ARG, "demod_bwd_batched: bad args");
+  demod_bwd_batched_kernel<<<dim3((max_cin + 31) / 32, n, n_layers), 256, 0, S_(st)>>>(sv, s_stride, q_cat, d_cat, gd_cat, gs, gs_stride, tab);
+  return sfk_check_launch("demod_bwd_batched");
 }
 
 int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void* wmod, int n, int taps, int cout, int cin, const float* d,

@@ -240,13 +240,49 @@ class SynthesisEngine:
                     hp = l.res // 2 + 1
                     max_T = max(max_T, 4 * hp * hp * l.cout)
             self.L.append(e)
-        self.wmod = _empty((B * max_w,), device)
+        self._pack_style_space(B, device)
         self.T = _empty((B * max(max_T, 8),), device)
         self.gx_scratch = _empty((B, 4, 4, c0), device)
         self.s = _empty((B, spec.s_dim), device, torch.float32)
         self.gs = _zeros((B, spec.s_dim), device)
-        self._gd_all = [e["gdacc"] for e in self.L if "gdacc" in e]
         self._build_descs()
+
+    def _pack_style_space(self, B, device):
+        """Concatenate the per-layer demodulation / weight-modulation operands so that ONE launch each serves every layer
+        (sfk_demod_fwd_batched, sfk_modulate_weights_batched, sfk_demod_bwd_batched); the per-layer tensors become views."""
+        convs = [e for e in self.L if e["l"].kind != "rgb"]
+        q_off = d_off = wb_off = wm_off = 0
+        rows_tab = []
+        for e in convs:
+            l = e["l"]
+            rows = e["wbase"].shape[0] * e["wbase"].shape[1]
+            fold = 0 if (l.kind == "up" and not e["fused_up"]) else 1     # the blur kernel of an unfused up-layer applies d itself
+            rows_tab.append([l.s_off, l.cin, l.cout, q_off, d_off, rows, wb_off, wm_off, l.cout, fold])
+            q_off += l.cout * l.cin
+            d_off += B * l.cout
+            wb_off += rows * l.cin
+            wm_off += rows * l.cin
+        self.q_cat = _empty((q_off,), device, torch.float32)
+        self.d_cat = _empty((d_off,), device, torch.float32)
+        self.gd_cat = _zeros((d_off,), device)
+        self.wb_cat = _empty((wb_off,), device, torch.float32)
+        self.wm_cat = _empty((B * wm_off,), device)
+        for e, r in zip(convs, rows_tab):
+            l = e["l"]
+            _, cin, cout, qo, do, rows, wbo, wmo, _, _ = r
+            q = self.q_cat[qo:qo + cout * cin].view(cout, cin)
+            q.copy_(e["Q"])
+            e["Q"] = q
+            wb = self.wb_cat[wbo:wbo + rows * cin].view(e["wbase"].shape)
+            wb.copy_(e["wbase"])
+            e["wbase"] = wb
+            e["d"] = self.d_cat[do:do + B * cout].view(B, cout)
+            e["gdacc"] = self.gd_cat[do:do + B * cout].view(B, cout)
+            e["wmod"] = self.wm_cat[B * wmo:B * (wmo + rows * cin)].view(B, rows, cin)
+        self.style_tab = torch.tensor(rows_tab, dtype=torch.int64, device=device)
+        assert self.style_tab.shape[1] == lib.STYLE_TAB_COLS
+        self.max_cin = max(e["l"].cin for e in convs)
+        self.max_cout = max(e["l"].cout for e in convs)
 
     # ---------------------------------------------------------------------------------------
     def _build_descs(self):
@@ -260,8 +296,7 @@ class SynthesisEngine:
                 continue
             e["x"] = x
             if l.kind == "conv":
-                wmod = self.wmod[: B * 9 * l.cout * l.cin].view(B, 9 * l.cout, l.cin)
-                e["wmod"] = wmod
+                wmod = e["wmod"]
                 e["fwd"] = lib.make_igemm_desc(
                     x, B, l.res, l.res, l.cin, 1, wmod, B, 9 * l.cout, e["out"], l.res, l.res, l.cout, 1, lib.pick_block_n(l.cout),
                     lib.conv3x3_taps(l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,   # demod is folded into wmod
@@ -283,8 +318,7 @@ class SynthesisEngine:
                         colscale=self.s, gs=self.gs, vec_stride=sd, vec_off=l.s_off, err=self.err)
             elif e["fused_up"]:
                 h = l.res // 2
-                wmod = self.wmod[: B * 36 * l.cout * l.cin].view(B, 36 * l.cout, l.cin)
-                e["wmod"] = wmod
+                wmod = e["wmod"]
                 e["fwd"] = lib.make_igemm_desc(
                     x, B, h, h, l.cin, 1, wmod, B, 36 * l.cout, e["out"], h, h, 4 * l.cout, 1, lib.pick_block_n(4 * l.cout),
                     lib.conv3x3_taps(4 * l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,
@@ -295,8 +329,7 @@ class SynthesisEngine:
                 e["deferred"] = True
             else:  # up
                 h = l.res // 2
-                wmod = self.wmod[: B * 9 * l.cout * l.cin].view(B, 9 * l.cout, l.cin)
-                e["wmod"] = wmod
+                wmod = e["wmod"]
                 T = self.T[: B * 4 * (h + 1) * (h + 1) * l.cout].view(B, 4, h + 1, h + 1, l.cout)
                 e["T"] = T
                 e["fwd"] = lib.make_igemm_desc(x, B, h, h, l.cin, 1, wmod, B, 9 * l.cout, T, h + 1, h + 1, l.cout, 4,
@@ -325,16 +358,16 @@ class SynthesisEngine:
             self.s.copy_(s)
         s = self.s
         skip = None
+        # every layer's demodulation and per-sample weights in two launches; demodulation rides on the weights wherever the
+        # conv epilogue would apply it (the blur kernel of the unfused up-layers applies it itself, after the FIR)
+        lib.demod_fwd_batched(s, self.q_cat, self.d_cat, self.style_tab, self.max_cout)
+        lib.modulate_weights_batched(self.wb_cat, s, self.wm_cat, self.d_cat, self.style_tab)
         for e in self.L:
             l = e["l"]
             if l.kind == "rgb":
                 lib.torgb_fwd(e["x"], e["wrgb"], s, l.s_off, e["bias"], skip, e["rgb"])
                 skip = e["rgb"]
                 continue
-            lib.demod_fwd(s, l.s_off, e["Q"], e["d"])
-            # demodulation rides on the weights wherever the conv epilogue would apply it (the blur kernel of the unfused
-            # up-layers applies it itself, after the FIR)
-            lib.modulate_weights(e["wbase"], s, l.s_off, e["wmod"], None if (l.kind == "up" and not e["fused_up"]) else e["d"])
             lib.igemm(e["fwd"])
             if l.kind == "up" and not e["fused_up"]:
                 lib.blur_act_fwd(e["T"], e["out"], e["d"], e["noise"], e["noise_w"], e["bias"])
@@ -352,14 +385,12 @@ class SynthesisEngine:
         kernel adds ToRGB's backward and applies the conv's activation backward in place (sfk_act_torgb_bwd)."""
         s = self.s
         self.gs.zero_()
-        for g in self._gd_all:
-            g.zero_()
+        self.gd_cat.zero_()
         L = self.L
         nb = (len(L) - 2) // 3
 
         def conv_tail(e):
-            lib.igemm(e["bwd"])                       # -> gradient of the producer of x, + fused style gradient
-            lib.demod_bwd(s, e["l"].s_off, e["Q"], e["d"], e["gdacc"], self.gs)
+            lib.igemm(e["bwd"])                       # -> gradient of the producer of x (+ style gradient unless deferred)
 
         def conv_act_rgb(conv, rgb, grgb, producer):
             # ToRGB backward and the conv's activation backward in one pass over conv["out"] / conv["gout"]; `producer` is the
@@ -385,6 +416,8 @@ class SynthesisEngine:
             conv_tail(up)                              # first writer of below_conv["gout"]
             conv_act_rgb(below_conv, below_rgb, grgb, up)
         conv_tail(L[0])
+        # demodulation gradient of every layer (needs each layer's finished gdacc; nothing upstream reads gs before this)
+        lib.demod_bwd_batched(s, self.q_cat, self.d_cat, self.gd_cat, self.gs, self.style_tab, self.max_cin)
         return self.gs
 
 

@@ -51,7 +51,7 @@ EXPORTS = [
     "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
-    "sfk_modulate_weights", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
+    "sfk_modulate_weights", "sfk_demod_fwd_batched", "sfk_modulate_weights_batched", "sfk_demod_bwd_batched", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
     "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_update_patch",
     "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample",
@@ -295,6 +295,26 @@ def modulate_weights(wbase, s, s_off, wmod, d=None):
     taps, cout, cin = wbase.shape
     _chk(load().sfk_modulate_weights(_p(wbase), _sub(s, s_off), sd, _p(wmod), n, taps, cout, cin, _p(d),
                                      d.shape[1] if d is not None else 0, _stream()), "modulate_weights")
+
+
+STYLE_TAB_COLS = 10   # s_off, cin, cout, q_off, d_off, rows, wb_off, wm_off, d_cols, fold  (int64, see sfk.h)
+
+
+def demod_fwd_batched(s, q_cat, d_cat, tab, max_cout):
+    n, sd = s.shape
+    _chk(load().sfk_demod_fwd_batched(_p(s), sd, _p(q_cat), _p(d_cat), _p(tab), tab.shape[0], n, max_cout, _stream()), "demod_fwd_batched")
+
+
+def modulate_weights_batched(wbase_cat, s, wmod_cat, d_cat, tab):
+    n, sd = s.shape
+    _chk(load().sfk_modulate_weights_batched(_p(wbase_cat), _p(s), sd, _p(wmod_cat), _p(d_cat), _p(tab), tab.shape[0], n, _stream()),
+         "modulate_weights_batched")
+
+
+def demod_bwd_batched(s, q_cat, d_cat, gd_cat, gs, tab, max_cin):
+    n, sd = s.shape
+    _chk(load().sfk_demod_bwd_batched(_p(s), sd, _p(q_cat), _p(d_cat), _p(gd_cat), _p(gs), gs.shape[1], _p(tab), tab.shape[0], n, max_cin,
+                                      _stream()), "demod_bwd_batched")
 
 
 def blur_act_fwd(T, out, d, noise, noise_w, bias):

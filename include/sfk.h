@@ -157,6 +157,18 @@ int sfk_demod_bwd(const float* s, int s_stride, const float* Q, const float* d, 
  * per-column scale; d_cols divides cout (the fused upsample conv stacks 4 phases of d_cols output channels in one tap). */
 int sfk_modulate_weights(const float* wbase, const float* s, int s_stride, void* wmod, int n, int taps, int cout,
                          int cin, const float* d, int d_cols, sfk_stream_t st);
+/* The three style-space kernels above for ALL modulated-conv layers of the generator in one launch each.  `tab` is a device table of
+ * int64 [n_layers][SFK_STYLE_TAB_COLS]: { s_off, cin, cout, q_off, d_off, rows, wb_off, wm_off, d_cols, fold }.
+ *   q_cat  : concatenated Q (cout x cin per layer, at q_off)          d_cat / gd_cat : [n][cout] per layer at d_off
+ *   wbase_cat : [rows][cin] per layer at wb_off (rows = 9*cout, or 9*4*cout for a fused upsample conv, d_cols = cout)
+ *   wmod_cat  : [n][rows][cin] per layer at n*wm_off;  fold != 0 multiplies the demodulation d into the weights */
+#define SFK_STYLE_TAB_COLS 10
+int sfk_demod_fwd_batched(const float* s, int s_stride, const float* q_cat, float* d_cat, const long long* tab, int n_layers,
+                          int n, int max_cout, sfk_stream_t st);
+int sfk_modulate_weights_batched(const float* wbase_cat, const float* s, int s_stride, void* wmod_cat, const float* d_cat,
+                                 const long long* tab, int n_layers, int n, sfk_stream_t st);
+int sfk_demod_bwd_batched(const float* s, int s_stride, const float* q_cat, const float* d_cat, const float* gd_cat, float* gs,
+                          int gs_stride, const long long* tab, int n_layers, int n, int max_cin, sfk_stream_t st);
 /* upfirdn2d([1,3,3,1] blur, pad (1,1)) of the phase-planar transposed-conv output, fused with
  * demod * . + noise + bias, leaky_relu*sqrt2.  T: [n][4][h+1][w+1][c] -> out [n][2h][2w][c]. */
 int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias,

@@ -52,6 +52,8 @@ def main():
         d = lib.make_igemm_desc(x, n, h, w, cin, 1, wt, n, 9 * cout, out, h + 1, w + 1, cout, 4, lib.pick_block_n(cout, 4), lib.tconv_taps(cout), err=err)
         bytes_alg = 2 * n * h * w * (cin + 4 * cout)
     d.stages = stages
+    if os.environ.get('SFK_BN'):
+        d.block_n = int(os.environ['SFK_BN'])
     if os.environ.get('SFK_FLAGS') is not None:
         d.flags = int(os.environ['SFK_FLAGS'])
     if os.environ.get('SFK_ROLES'):

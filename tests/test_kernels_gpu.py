@@ -373,6 +373,44 @@ def test_style_space_kernels():
     _close(gb, gb_ref, rtol=1e-4, what="fuse bwd b")
 
 
+def test_style_space_batched_matches_per_layer():
+    """the one-launch-for-all-layers variants against the per-layer kernels (two layers, one of them 4-phase with folded d)"""
+    from sfattack import lib
+    g = _gen(21)
+    n = 3
+    layers = [dict(cin=32, cout=16, rows=9 * 16, fold=0, s_off=0), dict(cin=16, cout=8, rows=9 * 4 * 8, fold=1, s_off=32)]
+    SD = 48
+    s = torch.randn(n, SD, generator=g, device=_dev()) + 1
+    tab, qo, do, wo = [], 0, 0, 0
+    for L in layers:
+        L["Q"] = torch.rand(L["cout"], L["cin"], generator=g, device=_dev())
+        L["wb"] = torch.randn(9, L["rows"] // 9, L["cin"], generator=g, device=_dev())
+        L["gd"] = torch.randn(n, L["cout"], generator=g, device=_dev())
+        tab.append([L["s_off"], L["cin"], L["cout"], qo, do, L["rows"], wo, wo, L["cout"], L["fold"]])
+        L["qo"], L["do"], L["wo"] = qo, do, wo
+        qo += L["cout"] * L["cin"]; do += n * L["cout"]; wo += L["rows"] * L["cin"]
+    q_cat = torch.cat([L["Q"].reshape(-1) for L in layers])
+    wb_cat = torch.cat([L["wb"].reshape(-1) for L in layers])
+    gd_cat = torch.cat([L["gd"].reshape(-1) for L in layers])
+    d_cat = torch.empty(do, device=_dev())
+    wm_cat = torch.empty(n * wo, device=_dev(), dtype=torch.bfloat16)
+    tabt = torch.tensor(tab, dtype=torch.int64, device=_dev())
+    lib.demod_fwd_batched(s, q_cat, d_cat, tabt, 16)
+    lib.modulate_weights_batched(wb_cat, s, wm_cat, d_cat, tabt)
+    gs = torch.zeros(n, SD, device=_dev())
+    lib.demod_bwd_batched(s, q_cat, d_cat, gd_cat, gs, tabt, 32)
+    gs_ref = torch.zeros(n, SD, device=_dev())
+    for L in layers:
+        d = torch.empty(n, L["cout"], device=_dev())
+        lib.demod_fwd(s, L["s_off"], L["Q"], d)
+        assert torch.equal(d, d_cat[L["do"]:L["do"] + n * L["cout"]].view(n, L["cout"]))
+        wm = torch.empty(n, L["rows"], L["cin"], device=_dev(), dtype=torch.bfloat16)
+        lib.modulate_weights(L["wb"], s, L["s_off"], wm, d if L["fold"] else None)
+        assert torch.equal(wm, wm_cat[n * L["wo"]:n * (L["wo"] + L["rows"] * L["cin"])].view(n, L["rows"], L["cin"]))
+        lib.demod_bwd(s, L["s_off"], L["Q"], d, L["gd"], gs_ref)
+    assert torch.equal(gs, gs_ref)
+
+
 def test_act_bwd_and_torgb():
     from oracle import stylegan2 as sg
     from sfattack import lib
