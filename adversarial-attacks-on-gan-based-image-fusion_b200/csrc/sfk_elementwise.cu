@@ -596,22 +596,26 @@ __global__ void modulate_weights_batched_kernel(const float* __restrict__ wbc, c
   const float* d = t[9] ? dc + t[4] : nullptr;
   const int rows_per_tap = static_cast<int>(rows / 9);
   const int vecs = Cin / 8;
-  const long total = static_cast<long>(N) * rows * vecs;
+  const long total = rows * vecs;
+  // one thread = one 8-wide weight vector for EVERY sample: the fp32 base weights are read once, not once per sample
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
     const int v = idx % vecs;
-    const long r = (idx / vecs) % rows;
-    const int n = idx / (vecs * rows);
+    const long r = idx / vecs;
     const float4* wp = reinterpret_cast<const float4*>(wbase + r * Cin + v * 8);
-    const float4* sp = reinterpret_cast<const float4*>(s + static_cast<long>(n) * s_stride + s_off + v * 8);
-    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
-    float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
-    if (d != nullptr) {
-      const float dv = __ldg(d + static_cast<long>(n) * d_cols + (r % rows_per_tap) % d_cols);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+    const int dcol = (r % rows_per_tap) % d_cols;
+    for (int n = 0; n < N; ++n) {
+      const float4* sp = reinterpret_cast<const float4*>(s + static_cast<long>(n) * s_stride + s_off + v * 8);
+      const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+      float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
+      if (d != nullptr) {
+        const float dv = __ldg(d + static_cast<long>(n) * d_cols + dcol);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] *= dv;
+        for (int e = 0; e < 8; ++e) o[e] *= dv;
+      }
+      store8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, o);
     }
-    store8(wmod + (static_cast<long>(n) * rows + r) * Cin + v * 8, o);
   }
   (void)Cout;
 }
@@ -1013,9 +1017,7 @@ __global__ void torgb_fwd_kernel(const T* __restrict__ x, const float* __restric
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (active) {
       const T* xp = x + (static_cast<long>(n) * HW + p) * C;
-      for (int v = sub; v < vecs; v += LP) {
-        float xv[8];
-        load8(xp + v * 8, xv);
+      auto dot = [&](const float (&xv)[8], int v) {
         const float4* wp = reinterpret_cast<const float4*>(swm + v * 24);
         const float4 r0 = wp[0], r1 = wp[1], g0 = wp[2], g1 = wp[3], b0 = wp[4], b1 = wp[5];
         a0 = fmaf(xv[0], r0.x, a0); a0 = fmaf(xv[1], r0.y, a0); a0 = fmaf(xv[2], r0.z, a0); a0 = fmaf(xv[3], r0.w, a0);
@@ -1024,6 +1026,23 @@ __global__ void torgb_fwd_kernel(const T* __restrict__ x, const float* __restric
         a1 = fmaf(xv[4], g1.x, a1); a1 = fmaf(xv[5], g1.y, a1); a1 = fmaf(xv[6], g1.z, a1); a1 = fmaf(xv[7], g1.w, a1);
         a2 = fmaf(xv[0], b0.x, a2); a2 = fmaf(xv[1], b0.y, a2); a2 = fmaf(xv[2], b0.z, a2); a2 = fmaf(xv[3], b0.w, a2);
         a2 = fmaf(xv[4], b1.x, a2); a2 = fmaf(xv[5], b1.y, a2); a2 = fmaf(xv[6], b1.z, a2); a2 = fmaf(xv[7], b1.w, a2);
+      };
+      int v = sub;
+      for (; v + 3 * LP < vecs; v += 4 * LP) {   // four 16-byte loads in flight per thread
+        float x0[8], x1[8], x2[8], x3[8];
+        load8(xp + v * 8, x0);
+        load8(xp + (v + LP) * 8, x1);
+        load8(xp + (v + 2 * LP) * 8, x2);
+        load8(xp + (v + 3 * LP) * 8, x3);
+        dot(x0, v);
+        dot(x1, v + LP);
+        dot(x2, v + 2 * LP);
+        dot(x3, v + 3 * LP);
+      }
+      for (; v < vecs; v += LP) {
+        float xv[8];
+        load8(xp + v * 8, xv);
+        dot(xv, v);
       }
     }
     for (int o = LP >> 1; o > 0; o >>= 1) {

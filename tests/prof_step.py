@@ -38,6 +38,10 @@ def main():
             agg[k][0] += 1; agg[k][1] += e0.elapsed_time(e1) * 1e3
         tot = sum(v for _, v in agg.values())
         print(f"{len(rec)} calls, {tot:.0f} us")
+        only = os.environ.get("SFK_PROF_NAME")
+        if only:
+            for k, e0, e1 in rec:
+                if k in only.split(","): print(f"    {k}: {e0.elapsed_time(e1) * 1e3:.1f} us")
         for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
             print(f"  {k:24s} {c:3d} {v:8.1f} us {100 * v / tot:5.1f}%")
         return
