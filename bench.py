@@ -239,10 +239,16 @@ def run_ours(args):
     barrier()
     sampler.mark_begin()
     lib.LAUNCHES = 0
+    profiled = os.environ.get("SFK_NCU_RANGE") == "1"     # ncu --profile-from-start off: capture only the timed steps
+    if profiled:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
+    if profiled:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     sampler.mark_end()
     launches = lib.LAUNCHES

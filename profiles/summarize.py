@@ -58,6 +58,8 @@ def full(src, dst, cmd=""):
     H, data = _rows(src)
 
     def col(suffix):
+        if suffix in H:
+            return H.index(suffix)
         for i, h in enumerate(H):
             if h.endswith(suffix):
                 return i
@@ -76,7 +78,10 @@ def full(src, dst, cmd=""):
         i = ci.get(k)
         if i is None or r[i] in ("", "n/a"):
             return float("nan")
-        v = float(r[i].replace(",", ""))
+        try:
+            v = float(r[i].replace(",", ""))
+        except ValueError:
+            return float("nan")
         if unit_scale and units:
             v *= unit_scale.get(units[i], 1.0)
         return v
