@@ -97,6 +97,18 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// shared -> global tensor store of one box (bulk async group; completion tracked with cp.async.bulk.wait_group[.read])
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -416,6 +428,8 @@ struct KGroup {
 struct __align__(64) Igemm2Args {
   CUtensorMap mapA[4];  // box height TH + 0..3 rows
   CUtensorMap mapB;
+  CUtensorMap mapO;     // output, for the staged TMA-store epilogue (ts != 0): box {ts_slabw ch, TW, 1, 32/TWB rows, 1}
+  int ts, ts_slabw, ts_nbuf, ts_off;   // staging: per epilogue warp ts_nbuf buffers of 32 rows x ts_slabw bf16 at smem_base + ts_off
   int n_img, out_h, out_w, out_c;
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
@@ -716,6 +730,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     for (int i = 0; i < kRegGs; ++i) gsr[i] = 0.f;
     int tile = blockIdx.x;
     int t_h = tile / a.tiles_w, t_w = tile % a.tiles_w;
+    const uint32_t ts_base = smem_base + static_cast<uint32_t>(a.ts_off + q * a.ts_nbuf * 32 * a.ts_slabw * 2);
+    int ts_buf = 0;
     const bool use_noise = (flags & SFK_EP_NOISE) != 0;
     auto noise_at = [&](int hh, int ww) -> float {
       return (use_noise && !a.out_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
@@ -755,6 +771,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       valid = valid && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float nz = a.noise_w * nz_raw;
+      // staged store: this warp's 32 rows are (32/TWB) tile rows of TW useful pixels, a dense box starting at (h_w0, w_0)
+      const int h_w0 = h - lane / a.TWB, w_0 = w - tw;
+      const uint32_t ts_row = static_cast<uint32_t>((lane / a.TWB) * a.TW + tw) * static_cast<uint32_t>(a.ts_slabw * 2);
+      const uint32_t ts_swz = a.ts_slabw == 64 ? ((ts_row >> 7) & 7u) : ((ts_row >> 7) & 3u);
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;
@@ -841,7 +861,39 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             v[4 * i + 3] *= ss.w;
           }
         }
-        if (valid) {
+        if (a.ts) {
+          // stage the bf16 rows in shared memory (swizzled like the tensor map) and let TMA write full lines: a direct
+          // 16-byte store per thread touches 16-32 different 128-byte lines per warp instruction, and those LSU wavefronts
+          // share the L1/shared-memory data pipe with the tensor core's operand reads
+          const int co = c0 % a.ts_slabw;
+          if (co == 0) {   // about to refill a buffer: its previous store must have finished reading it
+            if (lane == 0) {
+              if (a.ts_nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+          }
+          const uint32_t buf = ts_base + static_cast<uint32_t>(ts_buf * 32 * a.ts_slabw * 2);
+          if (tw < a.TW) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 8) {
+              const uint32_t j = static_cast<uint32_t>((co + i) >> 3);
+              sts128(buf + ts_row + ((j ^ ts_swz) << 4), pack8(v + i));
+            }
+          }
+          if (co + NC == a.ts_slabw) {   // slab complete
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int cs = n0 + c0 + NC - a.ts_slabw;
+              if (a.out_d2s)
+                tma_store_5d(&a.mapO, buf, cs & ((2 << a.cq_log2) - 1), w_0, cs >> (a.cq_log2 + 1), h_w0, n);
+              else
+                tma_store_5d(&a.mapO, buf, cs, w_0, 0, h_w0, n * a.num_acc + acc);
+            }
+            ts_buf = (ts_buf + 1) % a.ts_nbuf;
+          }
+        } else if (valid) {
           if (flags & SFK_EP_ACCUM) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
@@ -867,6 +919,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (one arrival per warp)
     }
+    if (a.ts && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
     if (reg_gs) {
 #pragma unroll
       for (int i = 0; i < kRegGs; ++i) {
@@ -1284,13 +1337,42 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   int per_sm = (total_ctas > sms && cols <= 256) ? 2 : 1;
   const int stage_bytes = k.a_stage_bytes + k.b_stage_bytes;
   const int resident = k.b_resident ? b_total : 0;
-  if (per_sm == 2 && (100 * 1024 - resident - 1024) / stage_bytes < 2) per_sm = 1;
-  const int budget = (per_sm == 2 ? 100 : 200) * 1024 - resident - 1024;
+  // staged TMA-store epilogue: whenever the tile's columns split into 64- (or 32-) column slabs and nothing is accumulated
+  static int ts_env = -2;
+  if (ts_env == -2) { const char* e = getenv("SFK_TMA_STORE"); ts_env = e ? atoi(e) : -1; }   // 0 never, 1 wherever possible, default: policy below
+  k.ts = 0;
+  k.ts_slabw = 64;
+  k.ts_nbuf = 2;
+  if (ts_env && !(d->flags & SFK_EP_ACCUM) && d->block_n % 32 == 0) {
+    if (d->out_d2s) {
+      if (((d->out_c / 2) % 64) == 0) k.ts = 1;                 // a slab never straddles the two row phases
+    } else {
+      k.ts = 1;
+      k.ts_slabw = d->block_n % 64 == 0 ? 64 : 32;
+    }
+  }
+  int staging = k.ts ? 4 * k.ts_nbuf * 32 * k.ts_slabw * 2 : 0;
+  const int cap1 = 216 * 1024;   // one CTA per SM: 227 KB opt-in limit minus the kernel's static shared memory
+  if (per_sm == 2 && (100 * 1024 - resident - 1024 - staging) / stage_bytes < 2) per_sm = 1;
+  if (k.ts && per_sm == 1 && (cap1 - resident - 1024 - staging) / stage_bytes < 2) {   // keep two pipeline stages: single-buffer
+    k.ts_nbuf = 1;
+    staging /= 2;
+  }
+  // Measured (8 pairs): the staged store pays where a tile has 128 columns and the staging can be double-buffered (256^2
+  // 128->128 conv 184 -> 179 us, 256^2 fused upsample 359 -> 333 us); narrow tiles lose to the extra fence/wait latency on the
+  // epilogue's critical path (1024^2 32->32 385 -> 412 us, 512^2 64->64 207 -> 248 us), so they keep direct stores.
+  if (k.ts && ts_env < 0 && !(d->block_n == 128 && k.ts_nbuf == 2)) {
+    k.ts = 0;
+    staging = 0;
+    if (total_ctas > sms && cols <= 256 && (100 * 1024 - resident - 1024) / stage_bytes >= 2) per_sm = 2;
+  }
+  const int budget = (per_sm == 2 ? 100 * 1024 : cap1) - resident - 1024 - staging;
   int stages = d->stages > 0 ? d->stages : budget / stage_bytes;
   const int ksteps_per_cta = k.num_cblk * ng * ((tiles_per_group + ctas_per_group - 1) / ctas_per_group);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > ksteps_per_cta) stages = ksteps_per_cta;
-  SFK_REQUIRE(stages >= 1 && stages * stage_bytes + resident + 1024 <= 220 * 1024, SFK_E_SHAPE, "igemm: tile does not fit shared memory");
+  SFK_REQUIRE(stages >= 1 && stages * stage_bytes + resident + staging + 1024 <= 220 * 1024, SFK_E_SHAPE, "igemm: tile does not fit shared memory");
+  k.ts_off = stages * stage_bytes + resident;
   k.stages = stages;
   k.acc_stages = (2 * cols <= (per_sm == 2 ? 256 : 512)) ? 2 : 1;
   k.dual_issue = (k.acc_stages == 2 && stages >= 2 * k.num_cblk * ng) ? 1 : 0;
@@ -1309,7 +1391,25 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
                      swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(B) failed");
   }
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + resident + 1024;
+  if (k.ts) {
+    const cuuint64_t oc = static_cast<cuuint64_t>(d->out_c), ow = static_cast<cuuint64_t>(d->out_w), oh = static_cast<cuuint64_t>(d->out_h);
+    cuuint64_t dims[5], strides[4];
+    if (d->out_d2s) {   // [n][2*oh][2*ow][Cq] viewed as {pixel pair (2Cq), W, row phase, H, N}
+      const cuuint64_t cq = oc / 4, frow = 2 * ow * cq * 2;
+      dims[0] = 2 * cq; dims[1] = ow; dims[2] = 2; dims[3] = oh; dims[4] = static_cast<cuuint64_t>(d->n_img);
+      strides[0] = 2 * cq * 2; strides[1] = frow; strides[2] = 2 * frow; strides[3] = 2 * oh * frow;
+    } else {            // [n*num_acc][oh][ow][oc] with a unit dummy dimension in the row-phase slot
+      dims[0] = oc; dims[1] = ow; dims[2] = 1; dims[3] = oh; dims[4] = static_cast<cuuint64_t>(d->n_img) * d->num_acc;
+      strides[0] = oc * 2; strides[1] = ow * oc * 2; strides[2] = ow * oc * 2; strides[3] = oh * ow * oc * 2;
+    }
+    cuuint32_t box[5] = {static_cast<cuuint32_t>(k.ts_slabw), static_cast<cuuint32_t>(k.TW), 1, static_cast<cuuint32_t>(32 / k.TWB), 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&k.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     k.ts_slabw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(out) failed");
+  }
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + resident + staging + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaSuccess;

@@ -80,6 +80,49 @@ def test_synthesis_forward_backward_vs_oracle():
     assert _relerr(gw, gw_ref) < 6e-2
 
 
+@pytest.mark.parametrize("mode,B", [("bf16", 3), ("fp32", 1), ("fp32", 3)])
+def test_synthesis_all_up_layers_fused_vs_oracle(monkeypatch, mode, B):
+    """Every up-layer as ONE fused upsample conv (depth-to-space forward, space-to-depth data gradient), down to the 4->8
+    layer (TW = 4 tiles, Cq = 16 column blocks), odd batch sizes; fp32 storage holds the tight tolerance."""
+    from oracle import stylegan2 as sg
+    from sfattack import lib
+    from sfattack.engine import SynthesisEngine
+    monkeypatch.setenv("SFK_FUSED_UP_RES", "8")
+    spec, GP, *_ = _small_setup(size=64)
+    g = torch.Generator().manual_seed(17)
+    w = torch.randn(B, spec.n_latent, spec.style_dim, generator=g)
+    wr = w.clone().requires_grad_(True)
+    styles = sg.styles_from_wplus(GP, spec, wr)
+    img_ref = sg.synthesis_from_styles(GP, spec, styles)
+    gimg = torch.randn(img_ref.shape, generator=g)
+    gs_ref = torch.cat(torch.autograd.grad((img_ref * gimg).sum(), styles), 1)
+    if mode == "fp32":
+        lib.set_activation_dtype(torch.float32)
+    try:
+        err = torch.zeros(1, dtype=torch.int32, device=DEV)
+        syn = SynthesisEngine(spec, GP, B, torch.device(DEV), err)
+        assert sum(1 for e in syn.L if e.get("fused_up")) == 4
+        syn.styles_from_wplus(w.to(DEV))
+        img = syn.forward()
+        gs = syn.backward(gimg.to(DEV))
+        torch.cuda.synchronize()
+        assert err.item() == 0
+        scale = img_ref.abs().max().item()
+        max_abs = (img.cpu() - img_ref.detach()).abs().max().item()
+        if mode == "fp32":
+            assert max_abs < 1e-4 * max(1.0, scale), (max_abs, scale)
+            # the leaky ReLU has a kink at 0: an activation of magnitude ~1e-7 can land on the other side of it than in the
+            # oracle (different summation order); ONE such element was traced for sample 1 of this seed (tests/diag_fused.py)
+            # and moves that sample's style gradient by 2-4e-3, every other sample agrees to 1e-6
+            per_sample = [_relerr(gs[i], gs_ref[i]) for i in range(B)]
+            assert max(per_sample) < 1e-2 and sorted(per_sample)[0] < 1e-4, per_sample
+        else:
+            assert max_abs < 4e-2 * scale, (max_abs, scale)
+            assert _cos(gs, gs_ref) > 0.998 and _relerr(gs, gs_ref) < 6e-2, (_cos(gs, gs_ref), _relerr(gs, gs_ref))
+    finally:
+        lib.set_activation_dtype(torch.bfloat16)
+
+
 def test_vgg_stack_vs_oracle():
     from oracle.vgg_ref import vgg_forward
     from sfattack.engine import ConvStack, vgg_layers
