@@ -1339,7 +1339,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   const int resident = k.b_resident ? b_total : 0;
   // staged TMA-store epilogue: whenever the tile's columns split into 64- (or 32-) column slabs and nothing is accumulated
   static int ts_env = -2;
-  if (ts_env == -2) { const char* e = getenv("SFK_TMA_STORE"); ts_env = e ? atoi(e) : -1; }   // 0 never, 1 wherever possible, default: policy below
+  if (ts_env == -2) { const char* e = getenv("SFK_TMA_STORE"); ts_env = e ? atoi(e) : 0; }   // 0 never (default), 1 wherever possible, 2 only 128-column tiles
   k.ts = 0;
   k.ts_slabw = 64;
   k.ts_nbuf = 2;
@@ -1358,10 +1358,11 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
     k.ts_nbuf = 1;
     staging /= 2;
   }
-  // Measured (8 pairs): the staged store pays where a tile has 128 columns and the staging can be double-buffered (256^2
-  // 128->128 conv 184 -> 179 us, 256^2 fused upsample 359 -> 333 us); narrow tiles lose to the extra fence/wait latency on the
-  // epilogue's critical path (1024^2 32->32 385 -> 412 us, 512^2 64->64 207 -> 248 us), so they keep direct stores.
-  if (k.ts && ts_env < 0 && !(d->block_n == 128 && k.ts_nbuf == 2)) {
+  // Measured (8 pairs): the staged store gains a little where a tile has 128 columns and the staging can be double-buffered
+  // (256^2 128->128 conv 184 -> 179 us, 256^2 fused upsample 359 -> 333 us); narrow tiles lose to the extra fence/wait latency
+  // on the epilogue's critical path (1024^2 32->32 385 -> 412 us, 512^2 64->64 207 -> 248 us).  Whole step: off 10.74 ms,
+  // 128-column policy 10.76-10.83 ms, everywhere 11.09 ms -> off by default.
+  if (k.ts && ts_env == 2 && !(d->block_n == 128 && k.ts_nbuf == 2)) {
     k.ts = 0;
     staging = 0;
     if (total_ctas > sms && cols <= 256 && (100 * 1024 - resident - 1024) / stage_bytes >= 2) per_sm = 2;
