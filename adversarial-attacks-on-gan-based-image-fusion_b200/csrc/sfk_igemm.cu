@@ -105,6 +105,10 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
+  return make_uint4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m), __shfl_xor_sync(0xffffffffu, v.z, m),
+                    __shfl_xor_sync(0xffffffffu, v.w, m));
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -429,6 +433,7 @@ struct __align__(64) Igemm2Args {
   CUtensorMap mapA[4];  // box height TH + 0..3 rows
   CUtensorMap mapB;
   CUtensorMap mapO;     // output, for the staged TMA-store epilogue (ts != 0): box {ts_slabw ch, TW, 1, 32/TWB rows, 1}
+  int xs;   // quad-transposed direct stores (see the epilogue)
   int ts, ts_slabw, ts_nbuf, ts_off;   // staging: per epilogue warp ts_nbuf buffers of 32 rows x ts_slabw bf16 at smem_base + ts_off
   int n_img, out_h, out_w, out_c;
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
@@ -893,6 +898,23 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             }
             ts_buf = (ts_buf + 1) % a.ts_nbuf;
           }
+        } else if (NC == 32 && a.xs && !(flags & SFK_EP_ACCUM)) {
+          // 4x4 transpose of the 16-byte pieces across the four lanes of a pixel quad (two butterfly exchanges): afterwards lane
+          // i of a quad owns piece i of all four pixels, so one store instruction writes 64 contiguous bytes per quad and touches
+          // 8 lines per warp instead of 16 (32 for the depth-to-space output)
+          const uint4 I0 = pack8(v), I1 = pack8(v + 8), I2 = pack8(v + 16), I3 = pack8(v + 24);
+          const int qi = lane & 3;
+          const bool hi = (qi & 2) != 0, odd = (qi & 1) != 0;
+          const uint4 r0 = shfl_xor_u4(hi ? I0 : I2, 2), r1 = shfl_xor_u4(hi ? I1 : I3, 2);
+          const uint4 J0 = hi ? r0 : I0, J1 = hi ? r1 : I1, J2 = hi ? I2 : r0, J3 = hi ? I3 : r1;
+          const uint4 ra = shfl_xor_u4(odd ? J0 : J1, 1), rb = shfl_xor_u4(odd ? J2 : J3, 1);
+          const uint4 K[4] = {odd ? ra : J0, odd ? J1 : ra, odd ? rb : J2, odd ? J3 : rb};
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          const long pitch = a.out_d2s ? (a.out_c >> 1) : a.out_c;   // elements between the pixels of neighbouring lanes
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if ((vmask >> (lane - qi + k)) & 1u) stg8(a.out + off + (k - qi) * pitch + qi * 8, K[k]);
+          }
         } else if (valid) {
           if (flags & SFK_EP_ACCUM) {
 #pragma unroll
@@ -1340,6 +1362,13 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   // staged TMA-store epilogue: whenever the tile's columns split into 64- (or 32-) column slabs and nothing is accumulated
   static int ts_env = -2;
   if (ts_env == -2) { const char* e = getenv("SFK_TMA_STORE"); ts_env = e ? atoi(e) : 0; }   // 0 never (default), 1 wherever possible, 2 only 128-column tiles
+  static int xs_env = -2;
+  // Measured: the transpose pays where the epilogue is light (plain data gradients: 1024^2 332 -> 310 us) or the scatter is
+  // widest (depth-to-space with Cq >= 64: 341 -> 317 us); the noise/bias/activation epilogues of narrow tiles are issue-bound
+  // and lose to the 16 extra shuffles (1024^2 forward 395 -> 422 us, 512^2 202 -> 243 us, 1024^2 fused upsample 363 -> 395 us).
+  if (xs_env == -2) { const char* e = getenv("SFK_XSTORE"); xs_env = e ? atoi(e) : 1; }   // 0 never, 1 policy, 2 everywhere
+  const int fl = d->flags & ~SFK_EP_PROFILE;
+  k.xs = (xs_env == 2 || (xs_env == 1 && (fl == 0 || (d->out_d2s && d->out_c >= 256)))) ? 1 : 0;
   k.ts = 0;
   k.ts_slabw = 64;
   k.ts_nbuf = 2;
