@@ -324,7 +324,9 @@ def run_ours(args):
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if world > 1:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only (rank 0 of the 1-GPU run)"}
+        elif not args.no_cpu_baseline:
             rate, times = cpu_oracle_iteration_rate(args.size, args.cpu_iters, 1)
             cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"{args.cpu_iters} PGD iteration(s) on 1 of the {B} pairs at {args.size}x{args.size} (oracle/pipeline.py, fp32, "
