@@ -44,7 +44,9 @@ def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: Attac
     gscale = 2.0 / (k * k)
     losses = torch.zeros(cfg.steps, B, device=dev)
     if cfg.kind == "patch":
-        patch = patch0.to(dev).clone().contiguous()
+        # one patch per attacked image (the reference runs at batch 1 with a (1,3,S,S) patch, adversarial_patch.py:94-106); a
+        # single initial patch is replicated, the copies then evolve independently (a shared, all-reduced patch is SURVEY 8f-4)
+        patch = patch0.to(dev).expand_as(eng.x).clone().contiguous()
         mask = mask.to(dev).expand_as(eng.x).contiguous()
         lo = torch.empty(2 * B, device=dev)
         hi = torch.empty(2 * B, device=dev)

@@ -397,24 +397,40 @@ def nhwc_bf16_to_nchw(x, y):
 
 def attack_update_linf(x, x0, gpool, alpha, eps, direction, lo, hi, stats, k):
     n, _, s, _ = x.shape
+    _check_update_args(x, gpool, k, x0=x0)
     _chk(load().sfk_attack_update_linf(_p(x), _p(x0), _p(gpool), _f(alpha), _f(eps), _f(direction), _f(lo), _f(hi), _p(stats), n, s, k,
                                        _stream()), "attack_update_linf")
 
 
+def _check_update_args(x, gpool, k, **same_shape):
+    """the update kernels index every per-image operand with the image index: a broadcastable-but-smaller tensor would be read
+    out of bounds, so shapes are checked here (the C ABI only sees pointers)"""
+    n, c, s, s2 = x.shape
+    assert c == 3 and s == s2 and s % k == 0, f"sfk: image batch must be (n,3,S,S) with S % k == 0, got {tuple(x.shape)}, k={k}"
+    assert tuple(gpool.shape) == (n, 3, s // k, s // k), f"sfk: pooled gradient {tuple(gpool.shape)} does not match {tuple(x.shape)} / {k}"
+    for name, t in same_shape.items():
+        assert t is None or tuple(t.shape) == tuple(x.shape), f"sfk: `{name}` {tuple(t.shape)} must have the shape of x {tuple(x.shape)}"
+
+
 def attack_update_patch(x, x0, patch, mask, gpool, lr, direction, use_sign, lo, hi, gscale, stats, k):
     n, _, s, _ = x.shape
+    _check_update_args(x, gpool, k, x0=x0, patch=patch, mask=mask)
+    assert lo.numel() >= n and hi.numel() >= n
     _chk(load().sfk_attack_update_patch(_p(x), _p(x0), _p(patch), _p(mask), _p(gpool), _f(lr), _f(direction), int(use_sign), _p(lo),
                                         _p(hi), _f(gscale), _p(stats), n, s, k, _stream()), "attack_update_patch")
 
 
 def attack_update_adam(x, gpool, m, v, lr, t, gscale, k, b1=0.9, b2=0.999, eps=1e-8, gfull=None, gfull_scale=1.0):
     n, _, s, _ = x.shape
+    _check_update_args(x, gpool, k, m=m, v=v, gfull=gfull)
     _chk(load().sfk_attack_update_adam(_p(x), _p(gpool), _p(gfull), _f(gfull_scale), _p(m), _p(v), _f(lr), _f(b1), _f(b2), _f(eps), int(t), _f(gscale), n, s, k,
                                        _stream()), "attack_update_adam")
 
 
 def attack_update_l2(x, x0, gpool, norms, dn, alpha, eps, direction, lo, hi, phase, k):
     n, _, s, _ = x.shape
+    _check_update_args(x, gpool, k, x0=x0)
+    assert norms.numel() >= n and dn.numel() >= n
     _chk(load().sfk_attack_update_l2(_p(x), _p(x0), _p(gpool), _p(norms), _p(dn), _f(alpha), _f(eps), _f(direction), _f(lo), _f(hi),
                                      int(phase), n, s, k, _stream()), "attack_update_l2")
 

@@ -2,7 +2,11 @@
   C1  FGSM, eps = 8/255, one 256x256 pair, StyleGAN2-256 (config-f widths), style (spatial) fusion + VGG loss, batch 1:
       checked against the CPU oracle -- fp32 parity mode to north_star's 1e-3, bf16 product path to its stated tolerance.
   C2/C3  1024x1024: size-independent properties (the oracle needs minutes per iteration there): eps-ball and [0,1] invariants,
-      monotone untargeted loss, idempotent projection, linearity of the style-gradient reduction."""
+      monotone untargeted loss, idempotent projection, linearity of the style-gradient reduction.
+  C4  patch 161x161 on StyleGAN2-512: nothing outside the mask moves, clean-range clamp, raw-gradient and sign steps.
+  C5  L2 ball at 1024 with the perceptual regulariser on the inputs: ball + [0,1] invariants, rising loss."""
+import math
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -105,3 +109,57 @@ def test_c2_c3_full_size_properties_1024():
         eng.check()
         del eng
         torch.cuda.empty_cache()
+
+
+def test_c4_patch_512_properties():
+    """BASELINE configs[3]: square patch, side floor(sqrt(0.1)*512) = 161, centred, on StyleGAN2-512 (16 latents); size-independent
+    properties of the loop: pixels outside the mask never move, the result stays inside the clean range, the loss rises."""
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    S, B = 512, 2
+    spec, GP, es, EP, vsd, FP = _models(S)
+    assert spec.n_latent == 16
+    xa, xb, _, _, g = _pairs(B, S, 41)
+    side = int(math.sqrt(0.1) * S)
+    assert side == 161
+    mask = torch.zeros(1, 3, S, S)
+    o = (S - side) // 2
+    mask[:, :, o:o + side, o:o + side] = 1.0
+    patch0 = torch.rand(1, 3, S, S, generator=g)
+    eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion="arithmetic", batch=B, device=DEV, loss=LossCfg(1.0, 1.0))
+    for sign in (False, True):          # raw-gradient step (adversarial_patch.py:131) and the sign variant of north_star
+        out = run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind="patch", steps=4, alpha=0.05 if sign else 2e3, patch_sign=sign),
+                         mask=mask, patch0=patch0)
+        X0 = torch.cat([xa, xb]).to(DEV)
+        x, m = out["x_adv"], mask.to(DEV).expand_as(X0)
+        assert torch.isfinite(x).all() and torch.isfinite(out["fused_adv"]).all()
+        assert torch.equal(x[m == 0], X0[m == 0])                                    # nothing outside the patch moves
+        lo, hi = X0.flatten(1).min(1).values, X0.flatten(1).max(1).values
+        assert (x.flatten(1).min(1).values >= lo - 1e-6).all() and (x.flatten(1).max(1).values <= hi + 1e-6).all()
+        assert (x[m == 1] != X0[m == 1]).float().mean() > 0.9                        # the patch is actually applied
+        assert (out["losses"][-1] >= out["losses"][0]).all(), out["losses"]
+    eng.check()
+
+
+def test_c5_l2_1024_with_input_regulariser_properties():
+    """BASELINE configs[4]: L2-bounded attack at 1024 with the perceptual regulariser on the adversarial inputs
+    (loss = fused-output term - c_reg * VGG-feature MSE(adv input, clean input), cf. attack_main2.py:632-635,649)."""
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    S, B = 1024, 2
+    spec, GP, es, EP, vsd, FP = _models(S)
+    xa, xb, _, _, g = _pairs(B, S, 51)
+    eps2 = 0.5 * math.sqrt(3 * S * S) * (8 / 255) / 8          # = 0.5 * sqrt(3 S^2) / 255
+    eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion="arithmetic", batch=B, device=DEV, loss=LossCfg(1.0, 1.0, 0.05))
+    # the clean point is a stationary point of the untargeted loss (zero gradient), so the loop starts from a +-1/255 dither
+    start = (torch.rand(2, B, 3, S, S, generator=g) * 2 - 1) * ((1 / 255) / eps2)
+    out = run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind="l2", steps=4, eps=eps2, alpha=eps2 / 10), start_noise=start)
+    X0 = torch.cat([xa, xb]).to(DEV)
+    x = out["x_adv"]
+    assert torch.isfinite(x).all() and torch.isfinite(out["losses"]).all()
+    assert x.min() >= 0 and x.max() <= 1
+    dn = (x - X0).flatten(1).norm(dim=1)
+    assert (dn <= eps2 * (1 + 1e-4)).all(), (dn, eps2)                                # inside the L2 ball
+    assert (dn > 0.1 * eps2).all(), dn                                                # normalised steps of eps2/10 were taken
+    assert (out["losses"][-1] > out["losses"][0]).all()
+    eng.check()
