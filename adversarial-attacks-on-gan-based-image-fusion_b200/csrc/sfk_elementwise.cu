@@ -562,7 +562,8 @@ __global__ void modulate_weights_kernel(const float* __restrict__ wbase, const f
 // the styles of every layer are known before the first conv runs, and the demodulation gradient is only consumed after the last.
 // Layer table (device, int64 [n_layers][SFK_STYLE_TAB_COLS]): s_off, cin, cout, q_off, d_off, rows, wb_off, wm_off, d_cols, fold
 //   q_off / d_off / wb_off / wm_off index the concatenated Q (cout x cin), d and gdacc ([n][cout] per layer), base weights
-//   ([rows][cin]) and modulated weights ([n][rows][cin] per layer) buffers; rows = taps * (cout or 4*cout); fold != 0 folds d in.
+//   ([rows][cin]) and modulated weights ([n][rows][cin] per layer) buffers; rows = taps * (cout or 4*cout); fold != 0 folds d in,
+//   fold == 2 also the activation gain sqrt(2) (for the SFK_EP_LRELU_RAW epilogue).
 __global__ void demod_fwd_batched_kernel(const float* __restrict__ s, int s_stride, const float* __restrict__ Qc, float* __restrict__ dc,
                                          const long long* __restrict__ tab, int N) {
   const long long* t = tab + static_cast<long>(blockIdx.y) * SFK_STYLE_TAB_COLS;
@@ -594,6 +595,7 @@ __global__ void modulate_weights_batched_kernel(const float* __restrict__ wbc, c
   T* wmod = wmc + t[7] * N;
   const int d_cols = static_cast<int>(t[8]);
   const float* d = t[9] ? dc + t[4] : nullptr;
+  const float gain = t[9] == 2 ? SFK_SQRT2 : 1.f;
   const int rows_per_tap = static_cast<int>(rows / 9);
   const int vecs = Cin / 8;
   const long total = rows * vecs;
@@ -610,7 +612,7 @@ __global__ void modulate_weights_batched_kernel(const float* __restrict__ wbc, c
       const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
       float o[8] = {w0.x * s0.x, w0.y * s0.y, w0.z * s0.z, w0.w * s0.w, w1.x * s1.x, w1.y * s1.y, w1.z * s1.z, w1.w * s1.w};
       if (d != nullptr) {
-        const float dv = __ldg(d + static_cast<long>(n) * d_cols + dcol);
+        const float dv = __ldg(d + static_cast<long>(n) * d_cols + dcol) * gain;
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] *= dv;
       }

@@ -235,6 +235,10 @@ __device__ __forceinline__ void epilogue16(const Args& a, int n, int acc, int h,
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = lrelu_fwd(v[i]);
   }
+  if (flags & SFK_EP_LRELU_RAW) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);
+  }
   if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {
     float x[16];
     if (valid) {
@@ -831,6 +835,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         if (flags & SFK_EP_LRELU) {
 #pragma unroll
           for (int i = 0; i < NC; ++i) v[i] = lrelu_fwd(v[i]);
+        }
+        if (flags & SFK_EP_LRELU_RAW) {
+#pragma unroll
+          for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);
         }
         if ((flags & SFK_EP_GSDOT) && reg_gs) {
           // c0 is 0 or 32 here (block_n <= 64, NC == 32 or the 16-wide path with c0 in {0,16,32,48})
@@ -1449,6 +1457,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
     SFK_SET_ATTR(SFK_EP_BIAS | SFK_EP_RELU);
     SFK_SET_ATTR(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
     SFK_SET_ATTR(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
+    SFK_SET_ATTR(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW);
     SFK_SET_ATTR(SFK_EP_XMASK);
     SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE);
     SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);
@@ -1464,6 +1473,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
     SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU);
     SFK_CASE(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
     SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
+    SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW);
     SFK_CASE(SFK_EP_XMASK);
     SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE);
     SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);

@@ -229,6 +229,7 @@ class SynthesisEngine:
                     e["wT"] = Ws.permute(2, 3, 1, 0).reshape(9 * l.cin, l.cout).to(ACT()).contiguous()  # [tap][cin][cout], shared
                 e["Q"] = (Ws * Ws).sum((2, 3)).contiguous()                                       # (cout,cin)
                 e["bias"] = f32(P[f"{l.name}.activate.bias"])
+                e["bias_ep"] = (e["bias"] * math.sqrt(2.0)).contiguous()      # for the gain-folded conv epilogue
                 e["noise"] = f32(P[f"noises.noise_{l.noise_idx}"][0, 0])
                 e["noise_w"] = float(P[f"{l.name}.noise.weight"].reshape(-1)[0])
                 e["d"] = _empty((B, l.cout), device, torch.float32)
@@ -256,7 +257,9 @@ class SynthesisEngine:
         for e in convs:
             l = e["l"]
             rows = e["wbase"].shape[0] * e["wbase"].shape[1]
-            fold = 0 if (l.kind == "up" and not e["fused_up"]) else 1     # the blur kernel of an unfused up-layer applies d itself
+            # the blur kernel of an unfused up-layer applies d itself; everywhere else d and the activation gain sqrt(2) ride on the
+            # weights (lrelu(x)*g == lrelu(g*x)): the conv epilogue is then  max(u, 0.2u),  u = acc + sqrt2*(noise + bias)
+            fold = 0 if (l.kind == "up" and not e["fused_up"]) else 2
             rows_tab.append([l.s_off, l.cin, l.cout, q_off, d_off, rows, wb_off, wm_off, l.cout, fold])
             q_off += l.cout * l.cin
             d_off += B * l.cout
@@ -299,8 +302,8 @@ class SynthesisEngine:
                 wmod = e["wmod"]
                 e["fwd"] = lib.make_igemm_desc(
                     x, B, l.res, l.res, l.cin, 1, wmod, B, 9 * l.cout, e["out"], l.res, l.res, l.cout, 1, lib.pick_block_n(l.cout),
-                    lib.conv3x3_taps(l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,   # demod is folded into wmod
-                    bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err)
+                    lib.conv3x3_taps(l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU_RAW,   # demod and gain ride on wmod
+                    bias=e["bias_ep"], noise=e["noise"], noise_w=e["noise_w"] * math.sqrt(2.0), err=self.err)
                 gx_dst = prev_conv["gout"] if prev_conv is not None else self.gx_scratch
                 # The style modulation (x s) and style gradient (sum x*gx~) of a data gradient are finished by the kernel that
                 # consumes it (act_bwd / act_torgb_bwd stream both tensors anyway) wherever such a consumer exists; the launch
@@ -321,8 +324,8 @@ class SynthesisEngine:
                 wmod = e["wmod"]
                 e["fwd"] = lib.make_igemm_desc(
                     x, B, h, h, l.cin, 1, wmod, B, 36 * l.cout, e["out"], h, h, 4 * l.cout, 1, lib.pick_block_n(4 * l.cout),
-                    lib.conv3x3_taps(4 * l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU,
-                    bias=e["bias"], noise=e["noise"], noise_w=e["noise_w"], err=self.err, out_d2s=1)
+                    lib.conv3x3_taps(4 * l.cout), flags=lib.EP_NOISE | lib.EP_BIAS | lib.EP_LRELU_RAW,
+                    bias=e["bias_ep"], noise=e["noise"], noise_w=e["noise_w"] * math.sqrt(2.0), err=self.err, out_d2s=1)
                 e["bwd"] = lib.make_igemm_desc(
                     e["gout"], B, h, h, 4 * l.cout, 1, e["wT"], 1, 9 * l.cin, prev_conv["gout"], h, h, l.cin, 1,
                     lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), err=self.err, a_s2d=1)   # finished by act_torgb_bwd

@@ -16,8 +16,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libsfattack.so")
 
 SFK_MAX_TAPS = 16
-EP_DSCALE, EP_NOISE, EP_BIAS, EP_RELU, EP_LRELU, EP_XMASK, EP_GSDOT, EP_COLSCALE, EP_ACCUM = (
-    1, 2, 4, 8, 16, 32, 64, 128, 256)
+EP_DSCALE, EP_NOISE, EP_BIAS, EP_RELU, EP_LRELU, EP_XMASK, EP_GSDOT, EP_COLSCALE, EP_ACCUM, EP_LRELU_RAW = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256, 512)
 
 
 class SfkTap(C.Structure):

@@ -60,7 +60,9 @@ enum {
   SFK_EP_XMASK = 32,     /* acc *= (xin > 0)                    (ReLU backward, fused into dgrad) */
   SFK_EP_GSDOT = 64,     /* gs[n][col] += sum_hw xin*acc        (style gradient, fused into dgrad) */
   SFK_EP_COLSCALE = 128, /* acc *= colscale[n][col]             (gx = s * gx~) */
-  SFK_EP_ACCUM = 256     /* out += acc                          (second consumer of an activation) */
+  SFK_EP_ACCUM = 256,    /* out += acc                          (second consumer of an activation) */
+  SFK_EP_LRELU_RAW = 512 /* max(acc, 0.2*acc): FusedLeakyReLU whose gain sqrt(2) the caller has folded into the weights, bias
+                            and noise strength (lrelu(x)*g == lrelu(g*x) for g > 0): one instruction less per element */
 };
 
 typedef struct {

@@ -378,8 +378,9 @@ def test_style_space_batched_matches_per_layer():
     from sfattack import lib
     g = _gen(21)
     n = 3
-    layers = [dict(cin=32, cout=16, rows=9 * 16, fold=0, s_off=0), dict(cin=16, cout=8, rows=9 * 4 * 8, fold=1, s_off=32)]
-    SD = 48
+    layers = [dict(cin=32, cout=16, rows=9 * 16, fold=0, s_off=0), dict(cin=16, cout=8, rows=9 * 4 * 8, fold=1, s_off=32),
+              dict(cin=16, cout=16, rows=9 * 16, fold=2, s_off=48)]
+    SD = 64
     s = torch.randn(n, SD, generator=g, device=_dev()) + 1
     tab, qo, do, wo = [], 0, 0, 0
     for L in layers:
@@ -406,7 +407,13 @@ def test_style_space_batched_matches_per_layer():
         assert torch.equal(d, d_cat[L["do"]:L["do"] + n * L["cout"]].view(n, L["cout"]))
         wm = torch.empty(n, L["rows"], L["cin"], device=_dev(), dtype=torch.bfloat16)
         lib.modulate_weights(L["wb"], s, L["s_off"], wm, d if L["fold"] else None)
-        assert torch.equal(wm, wm_cat[n * L["wo"]:n * (L["wo"] + L["rows"] * L["cin"])].view(n, L["rows"], L["cin"]))
+        got = wm_cat[n * L["wo"]:n * (L["wo"] + L["rows"] * L["cin"])].view(n, L["rows"], L["cin"])
+        if L["fold"] == 2:      # demodulation AND the activation gain sqrt(2) folded in
+            ref = L["wb"].reshape(1, L["rows"], L["cin"]) * s[:, None, L["s_off"]:L["s_off"] + L["cin"]] * \
+                d.repeat(1, L["rows"] // L["cout"])[:, :, None] * math.sqrt(2)
+            _close(got, ref, what="modulate * demod * sqrt2")
+        else:
+            assert torch.equal(wm, got)
         lib.demod_bwd(s, L["s_off"], L["Q"], d, L["gd"], gs_ref)
     assert torch.equal(gs, gs_ref)
 
