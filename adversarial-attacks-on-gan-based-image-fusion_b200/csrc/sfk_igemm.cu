@@ -741,6 +741,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     int t_h = tile / a.tiles_w, t_w = tile % a.tiles_w;
     const uint32_t ts_base = smem_base + static_cast<uint32_t>(a.ts_off + q * a.ts_nbuf * 32 * a.ts_slabw * 2);
     int ts_buf = 0;
+    // staged store: this warp's 32 rows are (32/TWB) tile rows of TW useful pixels, stored as one dense, swizzled box
+    const int lrow = lane / a.TWB;
+    const uint32_t ts_row = static_cast<uint32_t>(lrow * a.TW + tw) * static_cast<uint32_t>(a.ts_slabw * 2);
+    const uint32_t ts_swz = a.ts_slabw == 64 ? ((ts_row >> 7) & 7u) : ((ts_row >> 7) & 3u);
     const bool use_noise = (flags & SFK_EP_NOISE) != 0;
     auto noise_at = [&](int hh, int ww) -> float {
       return (use_noise && !a.out_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
@@ -780,10 +784,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       valid = valid && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float nz = a.noise_w * nz_raw;
-      // staged store: this warp's 32 rows are (32/TWB) tile rows of TW useful pixels, a dense box starting at (h_w0, w_0)
-      const int h_w0 = h - lane / a.TWB, w_0 = w - tw;
-      const uint32_t ts_row = static_cast<uint32_t>((lane / a.TWB) * a.TW + tw) * static_cast<uint32_t>(a.ts_slabw * 2);
-      const uint32_t ts_swz = a.ts_slabw == 64 ? ((ts_row >> 7) & 7u) : ((ts_row >> 7) & 3u);
+      const int h_w0 = h - lrow, w_0 = w - tw;   // first pixel of this warp's box (staged store)
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;

@@ -1,5 +1,5 @@
-"""Tiny end-to-end workload for `compute-sanitizer --tool memcheck python tests/sanitize_small.py`: every attack rule, both fusion
-modes, fused and unfused up-layers, odd batch, on a 64x64 model (a few seconds without the sanitizer)."""
+"""Tiny end-to-end workload (a few seconds): every attack rule, both fusion modes, fused and unfused up-layers, odd batch, on a
+64x64 model.  Meant for memory checkers / debuggers where one is available: python tests/sanitize_small.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
