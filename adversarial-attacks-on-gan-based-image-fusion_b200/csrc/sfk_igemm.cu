@@ -438,6 +438,7 @@ struct __align__(64) Igemm2Args {
   CUtensorMap mapB;
   CUtensorMap mapO;     // output, for the staged TMA-store epilogue (ts != 0): box {ts_slabw ch, TW, 1, 32/TWB rows, 1}
   int xs;   // quad-transposed direct stores (see the epilogue)
+  int m2;   // two M tiles (16 tile rows) per pipeline stage: every weight tile loaded into shared memory feeds 256 output rows
   int ts, ts_slabw, ts_nbuf, ts_off;   // staging: per epilogue warp ts_nbuf buffers of 32 rows x ts_slabw bf16 at smem_base + ts_off
   int n_img, out_h, out_w, out_c;
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
@@ -657,6 +658,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const int par = (warp == 3) ? 1 : 0;
       const int step = a.dual_issue ? 2 : 1;
       const int kpt = a.num_cblk * a.num_groups;   // ring slots per tile
+      const uint64_t m2_a16 = static_cast<uint64_t>((8 * a.TWB * a.row_bytes) >> 4);
+      const uint32_t m2_col = static_cast<uint32_t>(a.num_acc * a.block_n);
       for (int it = par; blockIdx.x + it * static_cast<int>(gridDim.x) < tiles_per_group && ok; it += step) {
         int ks = it * kpt;
         const int as = it % a.acc_stages;
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         if (!mbar_wait(&tmem_empty_bar[as], aph ^ 1, a.err)) break;
         if (prof) t_wa += clock64() - ta0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * a.num_acc * a.block_n);
+        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * (a.m2 + 1) * a.num_acc * a.block_n);
         for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
           int t0 = 0;
           for (int g = 0; g < a.num_groups && ok; ++g, ++ks) {
@@ -699,6 +702,14 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
 #pragma unroll
                   for (int k = 1; k < 4; ++k)
                     if (k < kslices) umma_bf16(TC[j], AD[j] + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                  if (a.m2) {   // second M tile: rows 8..15 of the box (8 * TWB smem rows further down), its own accumulator
+                    const uint64_t ad2 = AD[j] + m2_a16;
+                    const uint32_t tc2 = TC[j] + m2_col;
+                    umma_bf16(tc2, ad2, BD[j], idesc, AF[j]);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+                      if (k < kslices) umma_bf16(tc2, ad2 + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                  }
                 }
               }
             }
@@ -750,6 +761,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       return (use_noise && !a.out_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
     };
     float nz_next = tile < tiles_per_group ? noise_at(t_h * a.TH + th, t_w * a.TW + tw) : 0.f;
+    float nz_next2 = (a.m2 && tile < tiles_per_group) ? noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw) : 0.f;   // second M tile
     // depth-to-space output: one raw noise value per output phase of this thread's coarse pixel
     const bool d2s_noise = use_noise && a.out_d2s;
     float nq0 = 0.f, nq1 = 0.f, nq2 = 0.f, nq3 = 0.f;
@@ -764,9 +776,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     for (int it = 0; tile < tiles_per_group; ++it) {
       const int as = it % a.acc_stages;
       const uint32_t aph = (it / a.acc_stages) & 1;
-      const int h = t_h * a.TH + th, w = t_w * a.TW + tw;
+      int h = t_h * a.TH + th;
+      const int w = t_w * a.TW + tw;
       bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
-      const float nz_raw = nz_next;
+      const float nz_raw = nz_next, nz_raw2 = nz_next2;
       const float nz4[4] = {nq0, nq1, nq2, nq3};
       tile += gridDim.x;
       t_w += gridDim.x;
@@ -776,6 +789,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       }
       if (tile < tiles_per_group) {
         nz_next = noise_at(t_h * a.TH + th, t_w * a.TW + tw);
+        if (a.m2) nz_next2 = noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw);
         noise4_at(t_h * a.TH + th, t_w * a.TW + tw);
       }
       const long long te0 = prof ? clock64() : 0;
@@ -785,6 +799,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float nz = a.noise_w * nz_raw;
       const int h_w0 = h - lrow, w_0 = w - tw;   // first pixel of this warp's box (staged store)
+      uint32_t acc_col = static_cast<uint32_t>(as * (a.m2 + 1) * a.num_acc * a.block_n);   // first TMEM column of the tile (half)
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;
@@ -805,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           }
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>((as * a.num_acc + acc) * a.block_n + c0);
+                               acc_col + static_cast<uint32_t>(acc * a.block_n + c0);
         if (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         if (!(flags & SFK_EP_DSCALE) && (flags & (SFK_EP_NOISE | SFK_EP_BIAS))) {
           const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
@@ -938,12 +953,20 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           for (int i = 0; i < NC; i += 8) stg8(a.out + off + i, pack8(v + i));
         }
       };
-      for (int acc = 0; acc < a.num_acc; ++acc) {
-        const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
-        if ((a.block_n & 31) == 0 && (!a.out_d2s || ((a.out_c >> 2) & 31) == 0)) {
-          for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix);
-        } else {
-          for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix);
+      for (int half = 0; half <= a.m2; ++half) {
+        if (half == 1) {   // second M tile of the stage: output rows 8 further down, the next accumulator block
+          h += 8;
+          valid = ok && (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
+          nz = a.noise_w * nz_raw2;
+          acc_col += static_cast<uint32_t>(a.num_acc * a.block_n);
+        }
+        for (int acc = 0; acc < a.num_acc; ++acc) {
+          const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
+          if ((a.block_n & 31) == 0 && (!a.out_d2s || ((a.out_c >> 2) & 31) == 0)) {
+            for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix);
+          } else {
+            for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1281,6 +1304,17 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   if (rl_env == -2) { const char* e = getenv("SFK_S2D_RESIDENT"); rl_env = e ? atoi(e) : 0; }   // measured at 1024^2: streamed weights at 2 CTAs/SM 455 us, resident at 1 CTA/SM 571 us
   const int resident_limit = (d->out_d2s || (d->a_s2d && rl_env)) ? 150 * 1024 : 72 * 1024;
   const bool halo = k.TW == 16 && !d->a_s2d && !d->out_d2s && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= resident_limit && light_epilogue));
+  // Two M tiles per stage where the weights are streamed (they do not fit shared memory) in 128-column tiles: the stage's
+  // weight tile (3 taps x 16 KB) then feeds 256 output rows instead of 128, which takes ~15 % off the shared-memory port
+  // (TMA writes + tensor-core operand reads).  Needs both halves' accumulators double-buffered: 4 x 128 columns.
+  static int m2_env = -2;
+  if (m2_env == -2) { const char* e = getenv("SFK_M2"); m2_env = e ? atoi(e) : 1; }
+  k.m2 = (m2_env && k.TW == 16 && !halo && b_total_est > resident_limit && d->block_n == 128 && d->num_acc == 1 && !d->out_d2s &&
+          d->out_h >= 16 && KC == 64) ? 1 : 0;
+  if (k.m2) {
+    k.TH = 16;
+    k.tiles_h = (d->out_h + k.TH - 1) / k.TH;
+  }
   const bool share = k.TW >= 8;
   int ng = 0;
   int dymin[kMaxGroups], dymax[kMaxGroups], dxmin[kMaxGroups], dxmax[kMaxGroups], tdy[kMaxGroups][kMaxGroupTaps], tdx[kMaxGroups][kMaxGroupTaps];
@@ -1364,8 +1398,8 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   if (ctas_per_group < 1) ctas_per_group = 1;
   if (ctas_per_group > tiles_per_group) ctas_per_group = tiles_per_group;
   const int total_ctas = ctas_per_group * groups_total;
-  const int cols = d->num_acc * d->block_n;
-  int per_sm = (total_ctas > sms && cols <= 256) ? 2 : 1;
+  const int cols = d->num_acc * d->block_n * (k.m2 + 1);
+  int per_sm = (total_ctas > sms && cols <= 256 && !k.m2) ? 2 : 1;
   const int stage_bytes = k.a_stage_bytes + k.b_stage_bytes;
   const int resident = k.b_resident ? b_total : 0;
   // staged TMA-store epilogue: whenever the tile's columns split into 64- (or 32-) column slabs and nothing is accumulated
@@ -1381,7 +1415,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   k.ts = 0;
   k.ts_slabw = 64;
   k.ts_nbuf = 2;
-  if (ts_env && !(d->flags & SFK_EP_ACCUM) && d->block_n % 32 == 0) {
+  if (ts_env && !k.m2 && !(d->flags & SFK_EP_ACCUM) && d->block_n % 32 == 0) {
     if (d->out_d2s) {
       if (((d->out_c / 2) % 64) == 0) k.ts = 1;                 // a slab never straddles the two row phases
     } else {
