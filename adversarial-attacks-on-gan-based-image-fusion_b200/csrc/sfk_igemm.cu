@@ -764,12 +764,17 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     float nz_next2 = (a.m2 && tile < tiles_per_group) ? noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw) : 0.f;   // second M tile
     // depth-to-space output: one raw noise value per output phase of this thread's coarse pixel
     const bool d2s_noise = use_noise && a.out_d2s;
-    float nq0 = 0.f, nq1 = 0.f, nq2 = 0.f, nq3 = 0.f;
+    float nq0 = 0.f, nq1 = 0.f, nq2 = 0.f, nq3 = 0.f, nr0 = 0.f, nr1 = 0.f, nr2 = 0.f, nr3 = 0.f;   // nr*: second M tile
     auto noise4_at = [&](int hh, int ww) {
       if (d2s_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) {
         const float2* r0 = reinterpret_cast<const float2*>(a.noise + (2L * hh) * (2 * a.out_w) + 2 * ww);
         const float2 u = __ldg(r0), l = __ldg(r0 + a.out_w);
         nq0 = u.x; nq1 = u.y; nq2 = l.x; nq3 = l.y;
+      }
+      if (d2s_noise && a.m2 && tw < a.TW && hh + 8 < a.out_h && ww < a.out_w) {
+        const float2* r0 = reinterpret_cast<const float2*>(a.noise + (2L * (hh + 8)) * (2 * a.out_w) + 2 * ww);
+        const float2 u = __ldg(r0), l = __ldg(r0 + a.out_w);
+        nr0 = u.x; nr1 = u.y; nr2 = l.x; nr3 = l.y;
       }
     };
     if (tile < tiles_per_group) noise4_at(t_h * a.TH + th, t_w * a.TW + tw);
@@ -780,7 +785,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const int w = t_w * a.TW + tw;
       bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
       const float nz_raw = nz_next, nz_raw2 = nz_next2;
-      const float nz4[4] = {nq0, nq1, nq2, nq3};
+      float nz4[4] = {nq0, nq1, nq2, nq3};
+      const float nz4b[4] = {nr0, nr1, nr2, nr3};
       tile += gridDim.x;
       t_w += gridDim.x;
       while (t_w >= a.tiles_w) {
@@ -958,6 +964,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           h += 8;
           valid = ok && (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
           nz = a.noise_w * nz_raw2;
+#pragma unroll
+          for (int p4 = 0; p4 < 4; ++p4) nz4[p4] = nz4b[p4];
           acc_col += static_cast<uint32_t>(a.num_acc * a.block_n);
         }
         for (int acc = 0; acc < a.num_acc; ++acc) {
@@ -1309,7 +1317,7 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   // (TMA writes + tensor-core operand reads).  Needs both halves' accumulators double-buffered: 4 x 128 columns.
   static int m2_env = -2;
   if (m2_env == -2) { const char* e = getenv("SFK_M2"); m2_env = e ? atoi(e) : 1; }
-  k.m2 = (m2_env && k.TW == 16 && !halo && b_total_est > resident_limit && d->block_n == 128 && d->num_acc == 1 && !d->out_d2s &&
+  k.m2 = (m2_env && k.TW == 16 && !halo && b_total_est > resident_limit && d->block_n == 128 && d->num_acc == 1 &&
           d->out_h >= 16 && KC == 64) ? 1 : 0;
   if (k.m2) {
     k.TH = 16;

@@ -167,7 +167,8 @@ def test_tconv_blur_act_fwd_bwd(n, h, cin, cout):
     _close(gdacc, (gy * y).sum((2, 3)), rtol=2e-3, what="gdacc")
 
 
-@pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 64, 32), (1, 24, 64, 16), (2, 32, 32, 32), (1, 8, 128, 64)])
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 64, 32), (1, 24, 64, 16), (2, 32, 32, 32), (1, 8, 128, 64),
+                                          (1, 24, 128, 64)])   # last: streamed weights, two M tiles per stage, ragged rows
 def test_fused_upsample_conv_fwd_bwd(n, h, cin, cout):
     """blur(tconv(x)) as ONE launch: four 3x3 phase convs with a depth-to-space epilogue (forward) and the 3x3 data gradient
     reading the fine-grid gradient through a space-to-depth view (backward), against autograd through conv_transpose2d + upfirdn2d."""
