@@ -199,7 +199,9 @@ def tconv_dgrad_taps(cin: int):
 
 
 def pick_block_n(cout: int, num_acc: int = 1) -> int:
-    bn = min(cout, 128 if num_acc > 1 else 128)
+    """columns per accumulator: 128 for single-accumulator launches; 64 for the 4-phase transposed conv so that the four
+    accumulators (256 columns) can be double-buffered in TMEM (65^2 512->256: 200 -> 160 us)"""
+    bn = min(cout, 128 if num_acc == 1 else 64)
     while num_acc * bn > 512:
         bn //= 2
     return bn

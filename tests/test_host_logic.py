@@ -69,7 +69,7 @@ def test_model_tables_and_flop_accounting():
 def test_block_n_and_patch_utils():
     from sfattack import lib
     from sfattack.attack.patch.adversarial_patch_util import init_patch_square, square_transform, submatrix
-    assert lib.pick_block_n(512) == 128 and lib.pick_block_n(32) == 32 and lib.pick_block_n(256, 4) == 128 and 4 * lib.pick_block_n(512, 4) <= 512
+    assert lib.pick_block_n(512) == 128 and lib.pick_block_n(32) == 32 and lib.pick_block_n(256, 4) == 64 and 2 * 4 * lib.pick_block_n(512, 4) <= 512
     patch, shape = init_patch_square(512, 0.1)
     assert shape == (1, 3, 161, 161)                            # floor(sqrt(0.1)*512) = 161
     canvas, mask = square_transform(patch, (2, 3, 512, 512), shape, 512)
