@@ -335,3 +335,34 @@ def test_fp32_mode_other_attacks_and_reference_loop(fp32_mode):
         eng.adam_step(it + 1, 5e-3)
     eng.check()
     assert _relerr(eng.x.cpu() - img, want - img) < 3e-2
+
+
+@pytest.mark.parametrize("kind", ["linf", "l2", "patch"])
+def test_cuda_graph_replay_matches_eager(kind):
+    """AttackCfg(graph=True): iterations 2..K replayed from one captured CUDA graph give the eager result (up to the order of the
+    floating-point atomics in the style-gradient reductions, which can flip a sign() on an exact tie)."""
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    spec, GP, es, EP, vsd, FP, xa, xb = _small_setup(size=64, B=2)
+    eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion="arithmetic", batch=2, device=DEV, loss=LossCfg(1.0, 1.0), vgg_res=64,
+                       vgg_width_div=4)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.rand(2, 2, 3, 64, 64, generator=g) * 2 - 1
+    mask = torch.zeros(1, 3, 64, 64)
+    mask[:, :, 16:48, 16:48] = 1
+    kw = dict(linf=dict(start_noise=noise), l2=dict(start_noise=noise * 0.01),
+              patch=dict(mask=mask, patch0=torch.rand(1, 3, 64, 64, generator=g)))[kind]
+    cfgs = dict(linf=dict(steps=6), l2=dict(steps=22, eps=1.0, alpha=0.05), patch=dict(steps=22, alpha=0.3))[kind]
+    outs = []
+    for graph in (False, True, True):      # the third run replays the cached graph from its first iteration (Linf)
+        outs.append(run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind=kind, graph=graph, **cfgs), **kw))
+    a, b, c = outs
+    ltol = 2e-2 if kind == "linf" else 8e-2     # 22 continuous steps amplify the atomics' rounding noise (bf16 activations)
+    assert torch.allclose(b["losses"], c["losses"], rtol=ltol, atol=1e-6)
+    # continuous update rules (l2, raw-gradient patch) carry the atomics' rounding noise forward; sign steps agree exactly off ties
+    tol = 1e-6 if kind == "linf" else 1e-3
+    assert ((b["x_adv"] - c["x_adv"]).abs() < tol).float().mean().item() > 0.99
+    assert torch.allclose(a["losses"], b["losses"], rtol=ltol, atol=1e-6), (a["losses"], b["losses"])
+    same = ((a["x_adv"] - b["x_adv"]).abs() < tol).float().mean().item()
+    assert same > 0.99, same
+    assert torch.isfinite(b["fused_adv"]).all()
