@@ -130,6 +130,18 @@ __global__ void __launch_bounds__(kBlock) conv_c3_bwd_kernel(const T* __restrict
         if (oh < 0 || oh >= H) continue;
         const T* grow = g + (static_cast<long>(n) * H + oh) * W * Cout;
         for (int v = sub; v < vecs; v += LP) {
+          // the six gradient vectors this row contributes to the four pixels (columns w0-1 .. w0+4), all loads in flight at once
+          float gc[6][8];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const int ow = w0 + c - 1;
+            if (ow >= 0 && ow < W) {
+              load8(grow + static_cast<long>(ow) * Cout + v * 8, gc[c]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) gc[c][i] = 0.f;
+            }
+          }
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * vecs + v) * 36);
@@ -138,10 +150,7 @@ __global__ void __launch_bounds__(kBlock) conv_c3_bwd_kernel(const T* __restrict
             for (int i = 0; i < 8; ++i) wv[i] = wp[i];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int ow = w0 + j - kx + 1;
-              if (ow < 0 || ow >= W) continue;
-              float gv[8];
-              load8(grow + static_cast<long>(ow) * Cout + v * 8, gv);
+              const float* gv = gc[j - kx + 2];      // output column ow = w0 + j - kx + 1
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 a[j][0] = fmaf(gv[i], wv[i].x, a[j][0]);
