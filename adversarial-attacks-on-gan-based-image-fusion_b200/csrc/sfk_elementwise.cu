@@ -257,10 +257,11 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
     p /= Wo;
     const int i = p % Ho;
     const int n = p / Ho;
-    float xin[4][8];
+    float xin[4][8], rin[4][8];
     bool inb[4];
-    float m[8];
+    float m[8], g[8];
     int am[8];
+    load8(gy + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8, g);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       m[q] = -INFINITY;
@@ -272,6 +273,7 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
       inb[s] = (h < H) && (w < W);
       if (inb[s]) {
         load8(x + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8, xin[s]);
+        if (tap_ref) load8(tap_ref + ((static_cast<long>(n) * H + h) * W + w) * C + v * 8, rin[s]);   // all loads up front
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (xin[s][q] > m[q]) {
@@ -281,8 +283,6 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
         }
       }
     }
-    float g[8];
-    load8(gy + ((static_cast<long>(n) * Ho + i) * Wo + j) * C + v * 8, g);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       if (!inb[s]) continue;
@@ -292,10 +292,8 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict
 #pragma unroll
       for (int q = 0; q < 8; ++q) o[q] = (am[q] == s) ? g[q] : 0.f;
       if (tap_ref) {
-        float r[8];
-        load8(tap_ref + off, r);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] += tap_coef * (xin[s][q] - r[q]);
+        for (int q = 0; q < 8; ++q) o[q] += tap_coef * (xin[s][q] - rin[s][q]);
       }
       if (relu_mask) {
 #pragma unroll
