@@ -2,6 +2,7 @@
 
   python profiles/summarize.py launches gpurun_out/launches.csv  profiles/launches_rN      -> .md + .csv (one PGD step)
   python profiles/summarize.py full     gpurun_out/igemm_full.csv profiles/igemm_full_rN   -> .md, and igemm_traffic_rN.json
+  python profiles/summarize.py elem     gpurun_out/elem_full.csv  profiles/elementwise_full_rN -> .md (bandwidth-bound kernels)
 
 `launches`: output of  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...  over a bench.py run; the
 step is the launch window between two consecutive update_linf_kernel launches (one PGD iteration of all pairs).
@@ -116,7 +117,44 @@ def full(src, dst, cmd=""):
     print(f"{n} launches, {tot_t / 1e3:.2f} ms, {tot_b / 1e9:.2f} GB DRAM -> {tr}")
 
 
+def elem(src, dst, cmd=""):
+    """bandwidth-bound kernels of one step: per launch time, DRAM bytes and achieved GB/s (ncu --set full, raw page)"""
+    H, data = _rows(src)
+    units = None
+    if data and not data[0][0].strip().isdigit():
+        units, data = data[0], data[1:]
+
+    def col(name):
+        return H.index(name) if name in H else next((i for i, h in enumerate(H) if h.endswith(name)), None)
+
+    ci = {k: col(k) for k in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                              "dram__throughput.avg.pct_of_peak_sustained_elapsed")}
+    tsc = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3, "ms": 1e3}
+    bsc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(r, k, sc=None):
+        i = ci[k]
+        try:
+            v = float(r[i].replace(",", ""))
+        except (ValueError, TypeError):
+            return float("nan")
+        return v * sc.get(units[i], 1.0) if (sc and units) else v
+
+    with open(dst + ".md", "w") as f:
+        f.write("# ncu --set full: bandwidth-bound kernels of one PGD iteration (8 pairs, 1024x1024)\n\n")
+        if cmd:
+            f.write(f"Command (after the same command exited 0 without ncu): `{cmd}`\n\n")
+        f.write("Achieved GB/s = (dram__bytes_read + dram__bytes_write) / gpu__time_duration of that launch (cold-cache, serialised).\n\n")
+        f.write("| # | kernel | us | DRAM MB (r+w) | achieved GB/s | DRAM % of peak |\n|---:|---|---:|---:|---:|---:|\n")
+        for i, r in enumerate(data):
+            t = val(r, "gpu__time_duration.sum", tsc)
+            by = val(r, "dram__bytes_read.sum", bsc) + val(r, "dram__bytes_write.sum", bsc)
+            f.write(f"| {i} | `{_short(r[ci['Kernel Name']])}` | {t:.1f} | {by / 1e6:.1f} | {by / t / 1e3:.0f} | "
+                    f"{val(r, 'dram__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} |\n")
+    print(f"{len(data)} launches -> {dst}.md")
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     cmd = sys.argv[4] if len(sys.argv) > 4 else ""
-    (launches if mode == "launches" else full)(src, dst, cmd)
+    {"launches": launches, "full": full, "elem": elem}[mode](src, dst, cmd)
