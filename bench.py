@@ -171,6 +171,16 @@ def cpu_oracle_iteration_rate(size: int, iters: int, warm: int = 1):
     return len(times) / sum(times), times
 
 
+def workload_config(steps, size, pairs, world):
+    """the `config` both arms print: the same workload, whoever executes it"""
+    return {"workload": f"PGD-{steps} Linf eps=8/255 alpha=2/255 random-start, StyleGAN2-{size} config-f random-init, "
+                        f"arithmetic (mean W+) fusion of pairs, pixel+VGG(conv1_1,conv1_2,pool2,conv4_2) loss at 256x256, "
+                        f"encoder stand-in on the gradient path; BASELINE.json configs[1]",
+            "pairs_per_gpu": pairs, "global_pairs": pairs * world, "image_size": size, "attack": "linf-pgd",
+            "parallelism": f"dp{world} (independent pairs, no in-loop collective)",
+            "l2_policy": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -182,7 +192,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"PGD-10 Linf eps=8/255, StyleGAN2-{SIZE} arithmetic fusion + VGG loss, CPU sample of 1 pair per step"},
+            "config": workload_config(args.steps, SIZE, PAIRS_PER_GPU, max(1, args.gpus)),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -348,14 +358,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": f"PGD-{args.steps} Linf eps=8/255 alpha=2/255 random-start, StyleGAN2-{args.size} config-f random-init, "
-                                       f"arithmetic (mean W+) fusion of pairs, pixel+VGG(conv1_1,conv1_2,pool2,conv4_2) loss at 256x256, "
-                                       f"encoder stand-in on the gradient path; BASELINE.json configs[1]",
-                           "pairs_per_gpu": B, "global_pairs": B * world, "image_size": args.size, "attack": "linf-pgd",
-                           "parallelism": f"dp{world} (independent pairs, no in-loop collective)",
-                           "cuda_graph": bool(args.graph),
-                           "l2_policy": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"},
-                "clocks": clocks, "gpu_launches": launches,
+                "config": workload_config(args.steps, args.size, B, world),
+                "clocks": clocks, "gpu_launches": launches, "cuda_graph": bool(args.graph),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "what": f"{e2e_calls} call(s) of attack_loop.run_attack from pinned host buffers: H2D pairs+start noise, reference "
                                 f"fusion, PGD-{args.steps}, D2H adversarial examples + per-iteration losses"},
