@@ -163,7 +163,8 @@ int sfk_modulate_weights(const float* wbase, const float* s, int s_stride, void*
  * int64 [n_layers][SFK_STYLE_TAB_COLS]: { s_off, cin, cout, q_off, d_off, rows, wb_off, wm_off, d_cols, fold }.
  *   q_cat  : concatenated Q (cout x cin per layer, at q_off)          d_cat / gd_cat : [n][cout] per layer at d_off
  *   wbase_cat : [rows][cin] per layer at wb_off (rows = 9*cout, or 9*4*cout for a fused upsample conv, d_cols = cout)
- *   wmod_cat  : [n][rows][cin] per layer at n*wm_off;  fold != 0 multiplies the demodulation d into the weights */
+ *   wmod_cat  : [n][rows][cin] per layer at n*wm_off;  fold != 0 multiplies the demodulation d into the weights, fold == 2
+ *               also the activation gain sqrt(2) (for the SFK_EP_LRELU_RAW epilogue) */
 #define SFK_STYLE_TAB_COLS 10
 int sfk_demod_fwd_batched(const float* s, int s_stride, const float* q_cat, float* d_cat, const long long* tab, int n_layers,
                           int n, int max_cout, sfk_stream_t st);
