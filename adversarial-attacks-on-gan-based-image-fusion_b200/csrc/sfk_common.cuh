@@ -98,13 +98,16 @@ __device__ __forceinline__ float lrelu_fwd(float v) { return (v > 0.f ? v : 0.2f
 __device__ __forceinline__ float lrelu_inv(float o) { return o > 0.f ? o * SFK_RSQRT2 : o * (SFK_RSQRT2 * 5.0f); }
 __device__ __forceinline__ float lrelu_slope(float o) { return o > 0.f ? SFK_SQRT2 : 0.2f * SFK_SQRT2; }
 
+// SM count of the CURRENT device (cached per device ordinal: a process may drive several GPUs)
 static inline int sfk_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = sms[dev & 63];
+  if (!v) {
+    int q = 0;
+    cudaDeviceGetAttribute(&q, cudaDevAttrMultiProcessorCount, dev);
+    v = q > 0 ? q : 148;
   }
-  return sms;
+  return v;
 }

@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
 // the first term is the same sum the consumer conv's style gradient needs (rin), the second is accumulated on the OUTPUT value
 // gz = gy d and divided by d (> 0) once at the end.  Six ALU ops per element instead of eleven.
 template <typename T>
-__global__ void act_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout, T* __restrict__ gz, const float* __restrict__ d,
+__global__ void act_bwd_kernel(const T* __restrict__ out, const T* gout, T* gz /* may alias gout (in place) */, const float* __restrict__ d,
                                const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
                                const float* __restrict__ s_in, float* __restrict__ gs_in, int vec_stride, int HW, int C) {
   extern __shared__ float sacc[];

@@ -138,6 +138,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint6
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// kind::tf32: fp32 bit patterns in shared memory, read as tf32 (10-bit mantissa); one instruction covers K = 8 elements = 32 bytes,
+// so the operand descriptors advance exactly like the bf16 ones (K = 16 elements = 32 bytes)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void umma_t(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if constexpr (std::is_same<T, float>::value) umma_tf32(tmem_c, adesc, bdesc, idesc, accum);
+  else umma_bf16(tmem_c, adesc, bdesc, idesc, accum);
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -444,15 +459,16 @@ struct __align__(64) Igemm2Args {
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
   int b_per_sample, b_resident, dual_issue;
+  int passes, b_samples;   // passes == 3: split-tf32 (A.hi*B.hi + A.lo*B.hi + A.hi*B.lo); the lo halves sit n_img images / b_samples weight sets further on
   int out_d2s, a_s2d, cpa, cq_log2;   // fused resampling (see sfk.h); cpa = k-blocks per row phase of the space-to-depth input
   int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
   int layout_type, sbo_bytes, tmem_cols, flags, vec_stride;
   float noise_w;
-  __nv_bfloat16* out;
+  void* out;          // bf16 or fp32 (kernel template parameter)
   const float* dscale;
   const float* bias;
   const float* noise;
-  const __nv_bfloat16* xin;
+  const void* xin;
   const float* colscale;
   float* gs;
   int* err;
@@ -480,8 +496,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // FCT >= 0: the epilogue flag set is a compile-time constant (the six combinations the engines use are instantiated, so untaken
 // epilogue paths and their index arithmetic disappear); FCT < 0: flags are read at run time.
-template <int FCT>
+// T: storage type of activations and weights.  __nv_bfloat16 -> kind::f16 MMAs (the product path); float -> kind::tf32 MMAs on fp32
+// storage (the parity mode), optionally as three passes over hi/lo-split operands for fp32-class products.
+// VAR >= 0: the launch variant is a compile-time constant too (bit 0 depth-to-space output, bit 1 two M tiles per stage, bit 2
+// quad-transposed stores; never the staged TMA store), so that the per-tile code of the hot launches carries none of the other
+// variants' branches and address arithmetic (source-level profile, round 1: ~640 instructions per 32-column tile, 160 of them
+// arithmetic); VAR < 0: read from the arguments at run time.
+constexpr int kVarD2S = 1, kVarM2 = 2, kVarXS = 4;
+template <int FCT, typename T, int VAR>
 __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_constant__ Igemm2Args a) {
+  constexpr bool kF32 = std::is_same<T, float>::value;
+  const bool v_d2s = VAR >= 0 ? (VAR & kVarD2S) != 0 : a.out_d2s != 0;
+  const bool v_m2 = VAR >= 0 ? (VAR & kVarM2) != 0 : a.m2 != 0;
+  const bool v_xs = VAR >= 0 ? (VAR & kVarXS) != 0 : a.xs != 0;
+  const bool v_ts = VAR >= 0 ? false : a.ts != 0;
+  const int m2n = v_m2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
@@ -520,8 +549,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     uint64_t da = 0, db = 0;
     if (t < a.num_taps) {
       if (slot < a.stages) da = hi | static_cast<uint64_t>(((base_a + slot * a.a_stage_bytes) >> 4) + static_cast<uint32_t>(a.f_a16[t]));
-      if (a.b_resident) {
-        if (slot < a.num_cblk) db = hi | static_cast<uint64_t>(((base_b + slot * a.num_taps * a.b_tap_bytes) >> 4) + static_cast<uint32_t>(a.f_b16[t]));
+      if (a.b_resident) {   // slot = channel block (+ num_cblk for the lo halves of the split-tf32 passes)
+        if (slot < a.num_cblk * (a.passes == 3 ? 2 : 1)) db = hi | static_cast<uint64_t>(((base_b + slot * a.num_taps * a.b_tap_bytes) >> 4) + static_cast<uint32_t>(a.f_b16[t]));
       } else if (slot < a.stages) {
         db = hi | static_cast<uint64_t>(((base_b + slot * a.b_stage_bytes) >> 4) + static_cast<uint32_t>(a.f_b16[t]));
       }
@@ -532,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   }
   if (threadIdx.x < a.block_n) {
     const int c = n0 + threadIdx.x;
-    const int cw = a.out_d2s ? a.out_c / 4 : a.out_c;   // depth-to-space: the 4 phases share the per-channel vectors
+    const int cw = v_d2s ? a.out_c / 4 : a.out_c;   // depth-to-space: the 4 phases share the per-channel vectors
     col_dscale[threadIdx.x] = (a.flags & SFK_EP_DSCALE) ? a.dscale[static_cast<long>(n) * cw + c % cw] : 1.f;
     col_bias[threadIdx.x] = (a.flags & SFK_EP_BIAS) ? a.bias[c % cw] : 0.f;
     col_scale[threadIdx.x] = (a.flags & SFK_EP_COLSCALE) ? a.colscale[static_cast<long>(n) * a.vec_stride + c] : 1.f;
@@ -570,12 +599,14 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     if (lane == 0) {
       bool ok = true;
       if (a.b_resident) {
-        mbar_expect_tx(&bres_bar, static_cast<uint32_t>(a.num_cblk * a.num_taps * a.block_n * a.row_bytes));
-        for (int cb = 0; cb < a.num_cblk; ++cb)
-          for (int g = 0; g < a.num_groups; ++g)
-            for (int j = 0; j < a.groups[g].ntaps; ++j)
-              tma_load_3d(smem_b + (cb * a.num_taps + a.groups[g].bidx[j]) * a.b_tap_bytes, &a.mapB, &bres_bar, cb * a.KC,
-                          a.groups[g].brow[j] + n0, bs);
+        const int halves = a.passes == 3 ? 2 : 1;
+        mbar_expect_tx(&bres_bar, static_cast<uint32_t>(halves * a.num_cblk * a.num_taps * a.block_n * a.row_bytes));
+        for (int hf = 0; hf < halves; ++hf)
+          for (int cb = 0; cb < a.num_cblk; ++cb)
+            for (int g = 0; g < a.num_groups; ++g)
+              for (int j = 0; j < a.groups[g].ntaps; ++j)
+                tma_load_3d(smem_b + ((hf * a.num_cblk + cb) * a.num_taps + a.groups[g].bidx[j]) * a.b_tap_bytes, &a.mapB, &bres_bar,
+                            cb * a.KC, a.groups[g].brow[j] + n0, bs + hf * a.b_samples);
       }
       int ks = 0;
       const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
@@ -602,7 +633,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           t_w -= a.tiles_w;
           ++t_h;
         }
-        for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
+        for (int cbx = 0; cbx < a.num_cblk * a.passes && ok; ++cbx) {
+          // split-tf32: pass 0 = A.hi x B.hi, pass 1 = A.lo x B.hi, pass 2 = A.hi x B.lo
+          const int pass = cbx / a.num_cblk, cb = cbx - pass * a.num_cblk;
+          const int na = n + (pass == 1 ? a.n_img : 0), nb = bs + (pass == 2 ? a.b_samples : 0);
 #pragma unroll
           for (int g = 0; g < kMaxGroups; ++g) {
             if (g < ngroups && ok) {
@@ -615,14 +649,14 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                 mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(Gby[g]));
                 if (a.a_s2d)   // dims {2Cq, W, row phase, H, N}: k-block cb = (row phase, part of the pixel pair)
                   tma_load_5d(smem_a + stage * a.a_stage_bytes, reinterpret_cast<const CUtensorMap*>(Gmap[g]), &full_bar[stage],
-                              (cb % a.cpa) * a.KC, w0 + Gdx[g], cb / a.cpa, h0 + Gdy[g], n);
+                              (cb % a.cpa) * a.KC, w0 + Gdx[g], cb / a.cpa, h0 + Gdy[g], na);
                 else
                   tma_load_5d(smem_a + stage * a.a_stage_bytes, reinterpret_cast<const CUtensorMap*>(Gmap[g]), &full_bar[stage], cb * a.KC,
-                              w0 + Gdx[g], h0 + Gdy[g], Gpl[g], n);
+                              w0 + Gdx[g], h0 + Gdy[g], Gpl[g], na);
                 if (!a.b_resident) {
                   for (int j = 0; j < Gnt[g]; ++j)
                     tma_load_3d(smem_b + stage * a.b_stage_bytes + j * a.b_tap_bytes, &a.mapB, &full_bar[stage], cb * a.KC,
-                                a.groups[g].brow[j] + n0, bs);
+                                a.groups[g].brow[j] + n0, nb);
                 }
               }
               ++ks;
@@ -646,9 +680,11 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     // one elected lane issues tcgen05.mma / tcgen05.commit.
     {
       const bool leader = elect_one();
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a.block_n >> 3) << 17) |
+      // instruction descriptor: D = f32 (bit 4); A/B format at bits [7,10)/[10,13): 1 = bf16, 2 = tf32; both K-major
+      const uint32_t fmt = kF32 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(a.block_n >> 3) << 17) |
                              (static_cast<uint32_t>(128 >> 4) << 24);
-      const int kslices = a.KC / 16;
+      const int kslices = a.row_bytes / 32;   // one MMA consumes 32 bytes of K per row (16 bf16 / 8 tf32)
       const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
       long long t_wd = 0, t_wa = 0;
       const long long t_start = clock64();
@@ -657,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       if (a.b_resident) ok = mbar_wait(&bres_bar, 0, a.err);
       const int par = (warp == 3) ? 1 : 0;
       const int step = a.dual_issue ? 2 : 1;
-      const int kpt = a.num_cblk * a.num_groups;   // ring slots per tile
+      const int kpt = a.num_cblk * a.passes * a.num_groups;   // ring slots per tile
       const uint64_t m2_a16 = static_cast<uint64_t>((8 * a.TWB * a.row_bytes) >> 4);
       const uint32_t m2_col = static_cast<uint32_t>(a.num_acc * a.block_n);
       for (int it = par; blockIdx.x + it * static_cast<int>(gridDim.x) < tiles_per_group && ok; it += step) {
@@ -668,8 +704,9 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         if (!mbar_wait(&tmem_empty_bar[as], aph ^ 1, a.err)) break;
         if (prof) t_wa += clock64() - ta0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * (a.m2 + 1) * a.num_acc * a.block_n);
-        for (int cb = 0; cb < a.num_cblk && ok; ++cb) {
+        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * m2n * a.num_acc * a.block_n);
+        for (int cbx = 0; cbx < a.num_cblk * a.passes && ok; ++cbx) {
+          const int cb = (a.passes == 3 && cbx >= 2 * a.num_cblk) ? cbx - a.num_cblk : (cbx % a.num_cblk);   // resident B slot: lo halves follow the hi ones
           int t0 = 0;
           for (int g = 0; g < a.num_groups && ok; ++g, ++ks) {
             const int nt = a.groups[g].ntaps;
@@ -687,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                 AD[j] = s_adesc[a_row + j];
                 BD[j] = s_bdesc[b_row + j];
                 TC[j] = tmem_tile + static_cast<uint32_t>(s_colf[t0 + j] >> 1);
-                AF[j] = (cb == 0 && (s_colf[t0 + j] & 1)) ? 0u : 1u;
+                AF[j] = (cbx == 0 && (s_colf[t0 + j] & 1)) ? 0u : 1u;
               }
             }
             const long long td0 = prof ? clock64() : 0;
@@ -698,17 +735,17 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < kMaxGroupTaps; ++j) {
                 if (j < nt) {
-                  umma_bf16(TC[j], AD[j], BD[j], idesc, AF[j]);
+                  umma_t<T>(TC[j], AD[j], BD[j], idesc, AF[j]);
 #pragma unroll
                   for (int k = 1; k < 4; ++k)
-                    if (k < kslices) umma_bf16(TC[j], AD[j] + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
-                  if (a.m2) {   // second M tile: rows 8..15 of the box (8 * TWB smem rows further down), its own accumulator
+                    if (k < kslices) umma_t<T>(TC[j], AD[j] + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                  if (v_m2) {   // second M tile: rows 8..15 of the box (8 * TWB smem rows further down), its own accumulator
                     const uint64_t ad2 = AD[j] + m2_a16;
                     const uint32_t tc2 = TC[j] + m2_col;
-                    umma_bf16(tc2, ad2, BD[j], idesc, AF[j]);
+                    umma_t<T>(tc2, ad2, BD[j], idesc, AF[j]);
 #pragma unroll
                     for (int k = 1; k < 4; ++k)
-                      if (k < kslices) umma_bf16(tc2, ad2 + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                      if (k < kslices) umma_t<T>(tc2, ad2 + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
                   }
                 }
               }
@@ -732,9 +769,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int th = row / a.TWB, tw = row % a.TWB;
-    const int chunks = a.block_n / 16;
     const int mycol = colsum16_column(lane);
     const int flags = FCT >= 0 ? FCT : a.flags;
+    T* const outp = static_cast<T*>(a.out);
+    const T* const xinp = static_cast<const T*>(a.xin);
     const bool prof = (a.flags & SFK_EP_PROFILE) != 0 && threadIdx.x == 128;
     long long t_we = 0;
     const long long t_start = clock64();
@@ -758,12 +796,12 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     const uint32_t ts_swz = a.ts_slabw == 64 ? ((ts_row >> 7) & 7u) : ((ts_row >> 7) & 3u);
     const bool use_noise = (flags & SFK_EP_NOISE) != 0;
     auto noise_at = [&](int hh, int ww) -> float {
-      return (use_noise && !a.out_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
+      return (use_noise && !v_d2s && tw < a.TW && hh < a.out_h && ww < a.out_w) ? __ldg(a.noise + static_cast<long>(hh) * a.out_w + ww) : 0.f;   // raw: scaled at use, so nothing waits on this load here
     };
     float nz_next = tile < tiles_per_group ? noise_at(t_h * a.TH + th, t_w * a.TW + tw) : 0.f;
-    float nz_next2 = (a.m2 && tile < tiles_per_group) ? noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw) : 0.f;   // second M tile
+    float nz_next2 = (v_m2 && tile < tiles_per_group) ? noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw) : 0.f;   // second M tile
     // depth-to-space output: one raw noise value per output phase of this thread's coarse pixel
-    const bool d2s_noise = use_noise && a.out_d2s;
+    const bool d2s_noise = use_noise && v_d2s;
     float nq0 = 0.f, nq1 = 0.f, nq2 = 0.f, nq3 = 0.f, nr0 = 0.f, nr1 = 0.f, nr2 = 0.f, nr3 = 0.f;   // nr*: second M tile
     auto noise4_at = [&](int hh, int ww) {
       if (d2s_noise && tw < a.TW && hh < a.out_h && ww < a.out_w) {
@@ -771,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         const float2 u = __ldg(r0), l = __ldg(r0 + a.out_w);
         nq0 = u.x; nq1 = u.y; nq2 = l.x; nq3 = l.y;
       }
-      if (d2s_noise && a.m2 && tw < a.TW && hh + 8 < a.out_h && ww < a.out_w) {
+      if (d2s_noise && v_m2 && tw < a.TW && hh + 8 < a.out_h && ww < a.out_w) {
         const float2* r0 = reinterpret_cast<const float2*>(a.noise + (2L * (hh + 8)) * (2 * a.out_w) + 2 * ww);
         const float2 u = __ldg(r0), l = __ldg(r0 + a.out_w);
         nr0 = u.x; nr1 = u.y; nr2 = l.x; nr3 = l.y;
@@ -795,7 +833,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       }
       if (tile < tiles_per_group) {
         nz_next = noise_at(t_h * a.TH + th, t_w * a.TW + tw);
-        if (a.m2) nz_next2 = noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw);
+        if (v_m2) nz_next2 = noise_at(t_h * a.TH + th + 8, t_w * a.TW + tw);
         noise4_at(t_h * a.TH + th, t_w * a.TW + tw);
       }
       const long long te0 = prof ? clock64() : 0;
@@ -805,13 +843,13 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float nz = a.noise_w * nz_raw;
       const int h_w0 = h - lrow, w_0 = w - tw;   // first pixel of this warp's box (staged store)
-      uint32_t acc_col = static_cast<uint32_t>(as * (a.m2 + 1) * a.num_acc * a.block_n);   // first TMEM column of the tile (half)
+      uint32_t acc_col = static_cast<uint32_t>(as * m2n * a.num_acc * a.block_n);   // first TMEM column of the tile (half)
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;
         float v[NC], x[NC];
         long off = pix * a.out_c + n0 + c0;
-        if (a.out_d2s) {   // this column block is one output phase: pixel (2h + ph/2, 2w + ph%2) of the fine grid
+        if (v_d2s) {   // this column block is one output phase: pixel (2h + ph/2, 2w + ph%2) of the fine grid
           const int ph = (n0 + c0) >> a.cq_log2, ch = (n0 + c0) & ((1 << a.cq_log2) - 1);   // Cq is a power of two (validate)
           off = (((static_cast<long>(n) * 2 * a.out_h + 2 * h + (ph >> 1)) * (2 * a.out_w) + 2 * w + (ph & 1)) << a.cq_log2) + ch;
           nz = a.noise_w * (ph == 0 ? nz4[0] : ph == 1 ? nz4[1] : ph == 2 ? nz4[2] : nz4[3]);
@@ -819,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         if (flags & (SFK_EP_XMASK | SFK_EP_GSDOT)) {   // start the activation load before the TMEM read completes
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < NC; i += 8) unpack8(ldg8(a.xin + off + i), x + i);
+            for (int i = 0; i < NC; i += 8) load8(xinp + off + i, x + i);
           } else {
 #pragma unroll
             for (int i = 0; i < NC; ++i) x[i] = 0.f;
@@ -896,7 +934,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             v[4 * i + 3] *= ss.w;
           }
         }
-        if (a.ts) {
+        if (!kF32 && v_ts) {
           // stage the bf16 rows in shared memory (swizzled like the tensor map) and let TMA write full lines: a direct
           // 16-byte store per thread touches 16-32 different 128-byte lines per warp instruction, and those LSU wavefronts
           // share the L1/shared-memory data pipe with the tensor core's operand reads
@@ -921,14 +959,14 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) {
               const int cs = n0 + c0 + NC - a.ts_slabw;
-              if (a.out_d2s)
+              if (v_d2s)
                 tma_store_5d(&a.mapO, buf, cs & ((2 << a.cq_log2) - 1), w_0, cs >> (a.cq_log2 + 1), h_w0, n);
               else
                 tma_store_5d(&a.mapO, buf, cs, w_0, 0, h_w0, n * a.num_acc + acc);
             }
             ts_buf = (ts_buf + 1) % a.ts_nbuf;
           }
-        } else if (NC == 32 && a.xs && !(flags & SFK_EP_ACCUM)) {
+        } else if (NC == 32 && !kF32 && v_xs && !(flags & SFK_EP_ACCUM)) {
           // 4x4 transpose of the 16-byte pieces across the four lanes of a pixel quad (two butterfly exchanges): afterwards lane
           // i of a quad owns piece i of all four pixels, so one store instruction writes 64 contiguous bytes per quad and touches
           // 8 lines per warp instead of 16 (32 for the depth-to-space output)
@@ -940,26 +978,26 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           const uint4 ra = shfl_xor_u4(odd ? J0 : J1, 1), rb = shfl_xor_u4(odd ? J2 : J3, 1);
           const uint4 K[4] = {odd ? ra : J0, odd ? J1 : ra, odd ? rb : J2, odd ? J3 : rb};
           const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-          const long pitch = a.out_d2s ? (a.out_c >> 1) : a.out_c;   // elements between the pixels of neighbouring lanes
+          const long pitch = v_d2s ? (a.out_c >> 1) : a.out_c;   // elements between the pixels of neighbouring lanes
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if ((vmask >> (lane - qi + k)) & 1u) stg8(a.out + off + (k - qi) * pitch + qi * 8, K[k]);
+            if ((vmask >> (lane - qi + k)) & 1u) stg8(outp + off + (k - qi) * pitch + qi * 8, K[k]);
           }
         } else if (valid) {
           if (flags & SFK_EP_ACCUM) {
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
               float o[8];
-              unpack8(ld8(a.out + off + i), o);
+              load8p(outp + off + i, o);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[i + e] += o[e];
             }
           }
 #pragma unroll
-          for (int i = 0; i < NC; i += 8) stg8(a.out + off + i, pack8(v + i));
+          for (int i = 0; i < NC; i += 8) store8(outp + off + i, v + i);
         }
       };
-      for (int half = 0; half <= a.m2; ++half) {
+      for (int half = 0; half < m2n; ++half) {
         if (half == 1) {   // second M tile of the stage: output rows 8 further down, the next accumulator block
           h += 8;
           valid = ok && (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
@@ -970,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         }
         for (int acc = 0; acc < a.num_acc; ++acc) {
           const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
-          if ((a.block_n & 31) == 0 && (!a.out_d2s || ((a.out_c >> 2) & 31) == 0)) {
+          if ((a.block_n & 31) == 0 && (!v_d2s || ((a.out_c >> 2) & 31) == 0)) {
             for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix);
           } else {
             for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix);
@@ -981,7 +1019,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (one arrival per warp)
     }
-    if (a.ts && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+    if (v_ts && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
     if (reg_gs) {
 #pragma unroll
       for (int i = 0; i < kRegGs; ++i) {
@@ -1232,50 +1270,152 @@ extern "C" int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream) {
 }
 
 namespace {
-int encode_a_map(EncodeTiledFn enc, CUtensorMap* map, const sfk_igemm_desc* d, int KC, int TW, int rows, CUtensorMapSwizzle swz) {
+// Every size below is in BYTES of the storage element (es = 2 bf16 / 4 fp32), so one code path plans both the kind::f16 and the
+// kind::tf32 launches.  `base`/`n_mult`: the split-tf32 mode reads hi/lo copies from the workspace, lo n_img images further on.
+int encode_a_map(EncodeTiledFn enc, CUtensorMap* map, const sfk_igemm_desc* d, const void* base, int n_mult, int es, int KC, int TW,
+                 int rows, CUtensorMapSwizzle swz) {
+  const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const cuuint64_t e = (cuuint64_t)es;
   if (d->a_s2d) {   // [n][2*a_h][2*a_w][Cq] viewed as {pixel pair (2Cq), W, row phase, H, N}
-    const cuuint64_t cq = (cuuint64_t)d->a_c / 4, frow = 2 * (cuuint64_t)d->a_w * cq * 2;   // bytes of one fine row
-    cuuint64_t dims[5] = {2 * cq, (cuuint64_t)d->a_w, 2, (cuuint64_t)d->a_h, (cuuint64_t)d->n_img};
-    cuuint64_t strides[4] = {2 * cq * 2, frow, 2 * frow, 2 * (cuuint64_t)d->a_h * frow};
+    const cuuint64_t cq = (cuuint64_t)d->a_c / 4, frow = 2 * (cuuint64_t)d->a_w * cq * e;   // bytes of one fine row
+    cuuint64_t dims[5] = {2 * cq, (cuuint64_t)d->a_w, 2, (cuuint64_t)d->a_h, (cuuint64_t)d->n_img * n_mult};
+    cuuint64_t strides[4] = {2 * cq * e, frow, 2 * frow, 2 * (cuuint64_t)d->a_h * frow};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)TW, 1, (cuuint32_t)rows, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint32_t es1[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 1;
   }
-  cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_w, (cuuint64_t)d->a_h, (cuuint64_t)d->a_planes, (cuuint64_t)d->n_img};
-  cuuint64_t strides[4] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->a_w * d->a_c * 2, (cuuint64_t)d->a_h * d->a_w * d->a_c * 2,
-                           (cuuint64_t)d->a_planes * d->a_h * d->a_w * d->a_c * 2};
+  cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->a_w, (cuuint64_t)d->a_h, (cuuint64_t)d->a_planes, (cuuint64_t)d->n_img * n_mult};
+  cuuint64_t strides[4] = {(cuuint64_t)d->a_c * e, (cuuint64_t)d->a_w * d->a_c * e, (cuuint64_t)d->a_h * d->a_w * d->a_c * e,
+                           (cuuint64_t)d->a_planes * d->a_h * d->a_w * d->a_c * e};
   cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)rows, 1, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  cuuint32_t es1[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1;
 }
-}  // namespace
 
-extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream);
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
-extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
+// hi = x rounded to tf32 (10-bit mantissa, round to nearest), lo = tf32(x - hi): x*y ~= hi_x*hi_y + lo_x*hi_y + hi_x*lo_y with a
+// relative error of ~2^-21 per product instead of tf32's 2^-11 (the tensor core truncates fp32 bit patterns to tf32; hi and lo are
+// exactly representable, so that truncation is the identity).
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t u = __float_as_uint(v);
+  u = (u + 0x1000u) & 0xffffe000u;
+  return __uint_as_float(u);
+}
+__global__ void tf32_split_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long n4) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    float4 h, l;
+    h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+    l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+struct IgemmPlan {
+  Igemm2Args k;
+  sfk_igemm_desc desc;     // copy (CUDA-core mode and diagnostics)
+  dim3 grid;
+  size_t smem;
+  int fct;                 // epilogue flag set the launch is specialised for
+  int var;                 // launch variant bits (kVar*), -1 if the staged TMA store is on (run-time variant only)
+  int f32;                 // storage: 0 bf16, 1 fp32
+  int use_ref;             // fp32 storage with conv math 3: CUDA-core kernel
+  // split-tf32 operand copies (workspace): [A.hi][A.lo][B.hi][B.lo]
+  const float* a_src; const float* b_src;
+  float* a_hi; float* b_hi;
+  long a_n4, b_n4;
+};
+
+size_t split_ws_bytes(const sfk_igemm_desc* d) {
+  const size_t na = static_cast<size_t>(d->n_img) * d->a_planes * d->a_h * d->a_w * d->a_c * (d->a_s2d ? 1 : 1);
+  const size_t nb = static_cast<size_t>(d->b_samples) * d->b_rows * d->a_c;
+  return 2 * (na + nb) * sizeof(float);
+}
+
+int g_conv_math = 0;   // fp32 storage: 0/2 = split tf32 (three passes), 1 = plain tf32, 3 = CUDA cores
+
+// Instantiated (epilogue, variant) pairs: every launch of the bf16 product path hits a fully specialised kernel; anything else
+// (and the whole fp32 parity mode) runs the same source with run-time flags.
+template <typename T>
+const void* kernel_for(int fct, int var) {
+  if (!std::is_same<T, float>::value && var >= 0) {
+    switch ((fct << 4) | var) {
+#define SFK_CASE(F, V) case (((F) << 4) | (V)): return reinterpret_cast<const void*>(&igemm_tc2_kernel<F, __nv_bfloat16, V>)
+      SFK_CASE(0, 0); SFK_CASE(0, kVarM2); SFK_CASE(0, kVarXS); SFK_CASE(0, kVarXS | kVarM2);
+      SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU, 0); SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU, kVarM2);
+      SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, 0); SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, kVarM2);
+      SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, kVarD2S); SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, kVarD2S | kVarXS);
+      SFK_CASE(SFK_EP_XMASK, 0); SFK_CASE(SFK_EP_XMASK, kVarM2);
+      SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE, 0); SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE, kVarM2);
+#undef SFK_CASE
+      default: break;
+    }
+  }
+  switch (fct) {
+#define SFK_CASE(F) case (F): return reinterpret_cast<const void*>(&igemm_tc2_kernel<F, T, -1>)
+    SFK_CASE(0);
+    SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU);
+    SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW);
+    SFK_CASE(SFK_EP_XMASK);
+    SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE);
+#undef SFK_CASE
+    default: return reinterpret_cast<const void*>(&igemm_tc2_kernel<-1, T, -1>);
+  }
+}
+
+int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
   int rc = validate(d);
   if (rc) return rc;
-  if (sfk_act_f32()) return sfk_igemm_ref(d, stream);   // fp32 parity mode: exact CUDA-core kernel (tcgen05 path is bf16)
+  memset(P, 0, sizeof(*P));
+  P->desc = *d;
+  P->f32 = sfk_act_f32();
+  if (P->f32 && g_conv_math == 3) {
+    P->use_ref = 1;
+    return 0;
+  }
   EncodeTiledFn enc = get_encode_fn();
   SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-
-  static Igemm2Args k;   // large POD; sfk_igemm is not re-entrant across host threads (documented in sfk.h)
-  memset(&k, 0, sizeof(k));
+  Igemm2Args& k = P->k;
+  const int es = P->f32 ? 4 : 2;
+  k.passes = (P->f32 && g_conv_math != 1) ? 3 : 1;
+  k.b_samples = d->b_samples;
+  const void* a_base = d->a;
+  const void* b_base = d->b;
+  if (k.passes == 3) {
+    SFK_REQUIRE(d->ws != nullptr && d->ws_bytes >= split_ws_bytes(d) && sfk_aligned16(d->ws), SFK_E_ARG,
+                "igemm: split-tf32 mode needs desc.ws >= sfk_igemm_workspace_bytes()");
+    const size_t na = static_cast<size_t>(d->n_img) * d->a_planes * d->a_h * d->a_w * d->a_c;
+    const size_t nb = static_cast<size_t>(d->b_samples) * d->b_rows * d->a_c;
+    P->a_src = static_cast<const float*>(d->a);
+    P->b_src = static_cast<const float*>(d->b);
+    P->a_hi = static_cast<float*>(d->ws);
+    P->b_hi = P->a_hi + 2 * na;
+    P->a_n4 = static_cast<long>(na / 4);
+    P->b_n4 = static_cast<long>(nb / 4);
+    a_base = P->a_hi;
+    b_base = P->b_hi;
+  }
   const int kdim = d->a_s2d ? d->a_c / 2 : d->a_c;   // contiguous K extent in memory (space-to-depth: one pixel pair = 2*Cq)
-  const int KC = (kdim % 64 == 0) ? 64 : (kdim % 32 == 0 ? 32 : 16);
-  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const int row_bytes = (kdim * es) % 128 == 0 ? 128 : ((kdim * es) % 64 == 0 ? 64 : 32);
+  const int KC = row_bytes / es;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   k.KC = KC;
   k.num_cblk = d->a_c / KC;
   k.out_d2s = d->out_d2s;
   k.a_s2d = d->a_s2d;
   k.cpa = d->a_s2d ? kdim / KC : 1;
   for (k.cq_log2 = 0; (4 << k.cq_log2) < d->out_c; ++k.cq_log2) {}
-  k.row_bytes = KC * 2;
-  k.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
+  k.row_bytes = row_bytes;
+  k.layout_type = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
   k.sbo_bytes = 8 * k.row_bytes;
   k.TW = d->out_w > 8 ? 16 : (d->out_w > 4 ? 8 : 4);
   k.TH = 128 / k.TW;
@@ -1288,9 +1428,9 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   k.flags = d->flags;
   k.vec_stride = d->vec_stride > 0 ? d->vec_stride : d->out_c;
   k.noise_w = d->noise_w;
-  k.out = static_cast<__nv_bfloat16*>(d->out);
+  k.out = d->out;
   k.dscale = d->dscale; k.bias = d->bias; k.noise = d->noise;
-  k.xin = static_cast<const __nv_bfloat16*>(d->xin);
+  k.xin = d->xin;
   k.colscale = d->colscale; k.gs = d->gs; k.err = d->err;
 
   // ---- group taps that can share ONE activation load
@@ -1301,24 +1441,23 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   //   dy mode (otherwise):      taps that differ only in dy share a box TH+span rows tall (row offsets are multiples of 8)
   // Halo mode pays off where the layer is bound by activation loads (small channel counts: the whole weight set is resident in
   // smem); for wide layers the 16->14 useful columns cost more tensor time than the saved loads.  SFK_HALO=0/1 forces it.
-  static int halo_env = -2;
-  if (halo_env == -2) { const char* e = getenv("SFK_HALO"); halo_env = e ? atoi(e) : -1; }
-  const int b_total_est = (d->a_c / KC) * d->num_taps * (((d->block_n * KC * 2 + 1023) / 1024) * 1024);
+  static const int halo_env = env_int("SFK_HALO", -1);
+  const int halves = k.passes == 3 ? 2 : 1;
+  const int b_total_est = halves * (d->a_c / KC) * d->num_taps * (((d->block_n * row_bytes + 1023) / 1024) * 1024);
   // (measured: forward convs at 1024^2 / 512^2 gain 15-20 %; the data-gradient launches are bound by their heavier epilogue and
   //  lose ~8 % to the narrower tile, so they keep the dy-shared mode)
   const bool light_epilogue = (d->flags & (SFK_EP_GSDOT | SFK_EP_XMASK)) == 0;
   // the fused-resampling launches (4 phases of weights) keep their whole weight set resident at one CTA per SM
-  static int rl_env = -2;
-  if (rl_env == -2) { const char* e = getenv("SFK_S2D_RESIDENT"); rl_env = e ? atoi(e) : 0; }   // measured at 1024^2: streamed weights at 2 CTAs/SM 455 us, resident at 1 CTA/SM 571 us
+  static const int rl_env = env_int("SFK_S2D_RESIDENT", 0);   // measured at 1024^2: streamed weights at 2 CTAs/SM 455 us, resident at 1 CTA/SM 571 us
   const int resident_limit = (d->out_d2s || (d->a_s2d && rl_env)) ? 150 * 1024 : 72 * 1024;
-  const bool halo = k.TW == 16 && !d->a_s2d && !d->out_d2s && (halo_env >= 0 ? halo_env != 0 : (b_total_est <= resident_limit && light_epilogue));
+  const bool can_reside = b_total_est <= resident_limit && halves * (d->a_c / KC) <= kMaxStages;   // one descriptor slot per resident channel block
+  const bool halo = k.TW == 16 && !d->a_s2d && !d->out_d2s && (halo_env >= 0 ? (halo_env != 0 && can_reside) : (can_reside && light_epilogue));
   // Two M tiles per stage where the weights are streamed (they do not fit shared memory) in 128-column tiles: the stage's
   // weight tile (3 taps x 16 KB) then feeds 256 output rows instead of 128, which takes ~15 % off the shared-memory port
   // (TMA writes + tensor-core operand reads).  Needs both halves' accumulators double-buffered: 4 x 128 columns.
-  static int m2_env = -2;
-  if (m2_env == -2) { const char* e = getenv("SFK_M2"); m2_env = e ? atoi(e) : 1; }
-  k.m2 = (m2_env && k.TW == 16 && !halo && b_total_est > resident_limit && d->block_n == 128 && d->num_acc == 1 &&
-          d->out_h >= 16 && KC == 64) ? 1 : 0;
+  static const int m2_env = env_int("SFK_M2", 1);
+  k.m2 = (m2_env && k.TW == 16 && !halo && !can_reside && d->block_n == 128 && d->num_acc == 1 &&
+          d->out_h >= 16 && row_bytes == 128) ? 1 : 0;
   if (k.m2) {
     k.TH = 16;
     k.tiles_h = (d->out_h + k.TH - 1) / k.TH;
@@ -1379,8 +1518,8 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   const int max_span = max_rows_extra;
   // ---- shared memory plan
   k.b_tap_bytes = ((d->block_n * k.row_bytes + 1023) / 1024) * 1024;
-  const int b_total = k.num_cblk * k.num_taps * k.b_tap_bytes;
-  k.b_resident = b_total <= resident_limit ? 1 : 0;
+  const int b_total = halves * k.num_cblk * k.num_taps * k.b_tap_bytes;
+  k.b_resident = (b_total <= resident_limit && halves * k.num_cblk <= kMaxStages) ? 1 : 0;
   for (int g = 0; g < ng; ++g)
     for (int j = 0; j < k.groups[g].ntaps; ++j) {
       k.groups[g].a16[j] = (k.groups[g].roff[j] * k.row_bytes) >> 4;
@@ -1411,19 +1550,17 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   const int stage_bytes = k.a_stage_bytes + k.b_stage_bytes;
   const int resident = k.b_resident ? b_total : 0;
   // staged TMA-store epilogue: whenever the tile's columns split into 64- (or 32-) column slabs and nothing is accumulated
-  static int ts_env = -2;
-  if (ts_env == -2) { const char* e = getenv("SFK_TMA_STORE"); ts_env = e ? atoi(e) : 0; }   // 0 never (default), 1 wherever possible, 2 only 128-column tiles
-  static int xs_env = -2;
+  static const int ts_env = env_int("SFK_TMA_STORE", 0);   // 0 never (default), 1 wherever possible, 2 only 128-column tiles
   // Measured: the transpose pays where the epilogue is light (plain data gradients: 1024^2 332 -> 310 us) or the scatter is
   // widest (depth-to-space with Cq >= 64: 341 -> 317 us); the noise/bias/activation epilogues of narrow tiles are issue-bound
   // and lose to the 16 extra shuffles (1024^2 forward 395 -> 422 us, 512^2 202 -> 243 us, 1024^2 fused upsample 363 -> 395 us).
-  if (xs_env == -2) { const char* e = getenv("SFK_XSTORE"); xs_env = e ? atoi(e) : 1; }   // 0 never, 1 policy, 2 everywhere
+  static const int xs_env = env_int("SFK_XSTORE", 1);   // 0 never, 1 policy, 2 everywhere
   const int fl = d->flags & ~SFK_EP_PROFILE;
-  k.xs = (xs_env == 2 || (xs_env == 1 && (fl == 0 || (d->out_d2s && d->out_c >= 256)))) ? 1 : 0;
+  k.xs = (!P->f32 && (xs_env == 2 || (xs_env == 1 && (fl == 0 || (d->out_d2s && d->out_c >= 256))))) ? 1 : 0;
   k.ts = 0;
   k.ts_slabw = 64;
   k.ts_nbuf = 2;
-  if (ts_env && !k.m2 && !(d->flags & SFK_EP_ACCUM) && d->block_n % 32 == 0) {
+  if (!P->f32 && ts_env && !k.m2 && !(d->flags & SFK_EP_ACCUM) && d->block_n % 32 == 0) {
     if (d->out_d2s) {
       if (((d->out_c / 2) % 64) == 0) k.ts = 1;                 // a slab never straddles the two row phases
     } else {
@@ -1449,26 +1586,28 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
   }
   const int budget = (per_sm == 2 ? 100 * 1024 : cap1) - resident - 1024 - staging;
   int stages = d->stages > 0 ? d->stages : budget / stage_bytes;
-  const int ksteps_per_cta = k.num_cblk * ng * ((tiles_per_group + ctas_per_group - 1) / ctas_per_group);
+  const int ksteps_per_cta = k.num_cblk * k.passes * ng * ((tiles_per_group + ctas_per_group - 1) / ctas_per_group);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > ksteps_per_cta) stages = ksteps_per_cta;
   SFK_REQUIRE(stages >= 1 && stages * stage_bytes + resident + staging + 1024 <= 220 * 1024, SFK_E_SHAPE, "igemm: tile does not fit shared memory");
   k.ts_off = stages * stage_bytes + resident;
   k.stages = stages;
   k.acc_stages = (2 * cols <= (per_sm == 2 ? 256 : 512)) ? 2 : 1;
-  k.dual_issue = (k.acc_stages == 2 && stages >= 2 * k.num_cblk * ng) ? 1 : 0;
+  k.dual_issue = (k.acc_stages == 2 && stages >= 2 * k.num_cblk * k.passes * ng) ? 1 : 0;
   const int want = k.acc_stages * cols;
   k.tmem_cols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
 
   for (int sp = 0; sp <= max_span; ++sp)
-    SFK_REQUIRE(encode_a_map(enc, &k.mapA[sp], d, KC, k.TWB, k.TH + sp, swz) == 0, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(A) failed");
+    SFK_REQUIRE(encode_a_map(enc, &k.mapA[sp], d, a_base, halves, es, KC, k.TWB, k.TH + sp, swz) == 0, SFK_E_DRIVER,
+                "igemm: cuTensorMapEncodeTiled(A) failed");
   for (int sp = max_span + 1; sp < 4; ++sp) k.mapA[sp] = k.mapA[0];
+  const CUtensorMapDataType dt = es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)d->a_c, (cuuint64_t)d->b_rows, (cuuint64_t)d->b_samples};
-    cuuint64_t strides[2] = {(cuuint64_t)d->a_c * 2, (cuuint64_t)d->b_rows * d->a_c * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)d->a_c, (cuuint64_t)d->b_rows, (cuuint64_t)d->b_samples * halves};
+    cuuint64_t strides[2] = {(cuuint64_t)d->a_c * es, (cuuint64_t)d->b_rows * d->a_c * es};
     cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)d->block_n, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&k.mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->b), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint32_t es1[3] = {1, 1, 1};
+    CUresult r = enc(&k.mapB, dt, 3, const_cast<void*>(b_base), dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(B) failed");
   }
@@ -1484,59 +1623,26 @@ extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
       strides[0] = oc * 2; strides[1] = ow * oc * 2; strides[2] = ow * oc * 2; strides[3] = oh * ow * oc * 2;
     }
     cuuint32_t box[5] = {static_cast<cuuint32_t>(k.ts_slabw), static_cast<cuuint32_t>(k.TW), 1, static_cast<cuuint32_t>(32 / k.TWB), 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&k.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint32_t es1[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&k.mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->out, dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      k.ts_slabw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(out) failed");
   }
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + resident + staging + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaSuccess;
-#define SFK_SET_ATTR(F) e = (e == cudaSuccess) ? cudaFuncSetAttribute(igemm_tc2_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) : e
-    SFK_SET_ATTR(-1);
-    SFK_SET_ATTR(0);
-    SFK_SET_ATTR(SFK_EP_BIAS | SFK_EP_RELU);
-    SFK_SET_ATTR(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
-    SFK_SET_ATTR(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
-    SFK_SET_ATTR(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW);
-    SFK_SET_ATTR(SFK_EP_XMASK);
-    SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE);
-    SFK_SET_ATTR(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);
-#undef SFK_SET_ATTR
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
-  dim3 grid(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
-  cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  switch (d->flags & ~SFK_EP_PROFILE) {
-#define SFK_CASE(F) case (F): igemm_tc2_kernel<F><<<grid, kThreads, smem, cs>>>(k); break
-    SFK_CASE(0);
-    SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU);
-    SFK_CASE(SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
-    SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU);
-    SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW);
-    SFK_CASE(SFK_EP_XMASK);
-    SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE);
-    SFK_CASE(SFK_EP_GSDOT | SFK_EP_COLSCALE | SFK_EP_ACCUM);
-#undef SFK_CASE
-    default: igemm_tc2_kernel<-1><<<grid, kThreads, smem, cs>>>(k); break;
-  }
-  return sfk_check_launch("igemm_tc2_kernel");
-}
-
-extern "C" int sfk_role_cycles(unsigned long long* out8, int reset) {
-  if (out8 && cudaMemcpyFromSymbol(out8, g_role_cycles, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
-  if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cudaMemcpyToSymbol(g_role_cycles, z, sizeof(z)) != cudaSuccess) return 1;
-  }
+  P->smem = static_cast<size_t>(stages) * stage_bytes + resident + staging + 1024;
+  P->grid = dim3(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
+  P->fct = d->flags & ~SFK_EP_PROFILE;
+  static const int spec_env = env_int("SFK_SPECIALIZE", 1);   // 0: always the run-time-variant kernels (A/B timing)
+  P->var = (k.ts || !spec_env || (d->flags & SFK_EP_PROFILE)) ? -1 : ((k.out_d2s ? kVarD2S : 0) | (k.m2 ? kVarM2 : 0) | (k.xs ? kVarXS : 0));
+  // opt in to > 48 KB of dynamic shared memory: per (kernel instance, device), idempotent
+  const void* fn = P->f32 ? kernel_for<float>(P->fct, P->var) : kernel_for<__nv_bfloat16>(P->fct, P->var);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return 0;
 }
 
 template <typename T>
-static int launch_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
+int launch_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
   RefArgs<T> r;
   memset(&r, 0, sizeof(r));
   r.A = static_cast<const T*>(d->a);
@@ -1557,6 +1663,87 @@ static int launch_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {
   if (blocks > 65535L * 16) blocks = 65535L * 16;
   igemm_ref_kernel<T><<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(r);
   return sfk_check_launch("igemm_ref_kernel");
+}
+
+
+int launch_plan(const IgemmPlan* P, sfk_stream_t stream) {
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (P->use_ref) return launch_ref<float>(&P->desc, stream);
+  if (P->k.passes == 3) {
+    // operand copies for the split-tf32 passes (same stream: ordered before the GEMM)
+    const int tpb = 256;
+    long ba = (P->a_n4 + tpb - 1) / tpb, bb = (P->b_n4 + tpb - 1) / tpb;
+    if (ba > 148 * 16) ba = 148 * 16;
+    if (bb > 148 * 16) bb = 148 * 16;
+    tf32_split_kernel<<<static_cast<unsigned>(ba), tpb, 0, cs>>>(reinterpret_cast<const float4*>(P->a_src), reinterpret_cast<float4*>(P->a_hi),
+                                                                reinterpret_cast<float4*>(P->a_hi) + P->a_n4, P->a_n4);
+    tf32_split_kernel<<<static_cast<unsigned>(bb), tpb, 0, cs>>>(reinterpret_cast<const float4*>(P->b_src), reinterpret_cast<float4*>(P->b_hi),
+                                                                reinterpret_cast<float4*>(P->b_hi) + P->b_n4, P->b_n4);
+  }
+  const void* fn = P->f32 ? kernel_for<float>(P->fct, P->var) : kernel_for<__nv_bfloat16>(P->fct, P->var);
+  void* args[1] = {const_cast<Igemm2Args*>(&P->k)};
+  cudaError_t e = cudaLaunchKernel(fn, P->grid, dim3(kThreads), args, P->smem, cs);
+  if (e != cudaSuccess) {
+    sfk_set_error(cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return sfk_check_launch("igemm_tc2_kernel");
+}
+}  // namespace
+
+extern "C" int sfk_set_conv_math(int mode) {
+  if (mode < 0 || mode > 3) return SFK_E_ARG;
+  g_conv_math = mode;
+  return 0;
+}
+extern "C" int sfk_get_conv_math(void) { return g_conv_math; }
+
+extern "C" size_t sfk_igemm_workspace_bytes(const sfk_igemm_desc* d) {
+  if (!d || !sfk_act_f32() || g_conv_math == 1 || g_conv_math == 3) return 0;
+  return split_ws_bytes(d);
+}
+
+// One-shot form: plans on the caller's stack frame (heap for the 5 KB argument block), launches, forgets.  Re-entrant.
+extern "C" int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream) {
+  IgemmPlan* P = static_cast<IgemmPlan*>(malloc(sizeof(IgemmPlan)));
+  if (!P) return SFK_E_ARG;
+  int rc = build_plan(d, P);
+  if (rc == 0) rc = launch_plan(P, stream);
+  free(P);
+  return rc;
+}
+
+// Prepared form: everything host-side (tap grouping, shared-memory plan, tensor-map encoding) happens once; sfk_igemm_run is a
+// single cudaLaunchKernel.  A plan is immutable, so any number of host threads / streams may run it concurrently.
+extern "C" int sfk_igemm_prepare(const sfk_igemm_desc* d, sfk_igemm_plan** out) {
+  SFK_REQUIRE(out != nullptr, SFK_E_ARG, "igemm_prepare: null output");
+  IgemmPlan* P = static_cast<IgemmPlan*>(malloc(sizeof(IgemmPlan)));
+  SFK_REQUIRE(P != nullptr, SFK_E_ARG, "igemm_prepare: out of host memory");
+  const int rc = build_plan(d, P);
+  if (rc) {
+    free(P);
+    return rc;
+  }
+  *out = reinterpret_cast<sfk_igemm_plan*>(P);
+  return 0;
+}
+extern "C" int sfk_igemm_run(const sfk_igemm_plan* plan, sfk_stream_t stream) {
+  SFK_REQUIRE(plan != nullptr, SFK_E_ARG, "igemm_run: null plan");
+  return launch_plan(reinterpret_cast<const IgemmPlan*>(plan), stream);
+}
+extern "C" int sfk_igemm_destroy(sfk_igemm_plan* plan) {
+  free(plan);
+  return 0;
+}
+
+
+extern "C" int sfk_role_cycles(unsigned long long* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, g_role_cycles, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_role_cycles, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
 }
 
 extern "C" int sfk_igemm_ref(const sfk_igemm_desc* d, sfk_stream_t stream) {

@@ -43,12 +43,14 @@ class SfkIgemmDesc(C.Structure):
         ("err", C.c_void_p),
         ("stages", C.c_int32),
         ("out_d2s", C.c_int32), ("a_s2d", C.c_int32),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
     ]
 
 
 # every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
+    "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_prepare", "sfk_igemm_run", "sfk_igemm_destroy", "sfk_set_conv_math", "sfk_get_conv_math",
+    "sfk_igemm_workspace_bytes", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_demod_fwd_batched", "sfk_modulate_weights_batched", "sfk_demod_bwd_batched", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
@@ -73,6 +75,9 @@ def load() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.sfk_last_error_string.restype = C.c_char_p
         _lib.sfk_version.restype = C.c_int
+        _lib.sfk_igemm_workspace_bytes.restype = C.c_size_t
+        _lib.sfk_igemm_run.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.sfk_igemm_destroy.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -84,6 +89,38 @@ def set_activation_dtype(dtype: torch.dtype):
 
 def activation_dtype() -> torch.dtype:
     return torch.float32 if load().sfk_get_activation_dtype() else torch.bfloat16
+
+
+CONV_MATH = {"auto": 0, "tf32": 1, "tf32x3": 2, "cuda_cores": 3}
+
+
+def set_conv_math(mode: str):
+    """arithmetic of the tensor-core conv under fp32 storage (sfk.h): "tf32x3" (default: split tf32, fp32-class products),
+    "tf32" (plain kind::tf32), "cuda_cores" (sfk_igemm_ref).  Plans are bound to the mode they were prepared under."""
+    _chk0(load().sfk_set_conv_math(CONV_MATH[mode]), "set_conv_math")
+
+
+def conv_math() -> str:
+    m = load().sfk_get_conv_math()
+    return {0: "tf32x3", 1: "tf32", 2: "tf32x3", 3: "cuda_cores"}[m]
+
+
+def mode_key() -> tuple:
+    """(storage dtype, conv math): everything process-global that a prepared plan or an engine's buffers depend on"""
+    return (load().sfk_get_activation_dtype(), load().sfk_get_conv_math())
+
+
+# scratch of the split-tf32 conv (one per device, shared by all launches: they are ordered on one stream).  Grown when a
+# descriptor is created, never while plans that captured the old pointer are alive (the pointer is part of the plan key).
+_WS = {}
+
+
+def _workspace(dev: torch.device, need: int) -> torch.Tensor:
+    t = _WS.get(dev)
+    if t is None or t.numel() < need:
+        t = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        _WS[dev] = t
+    return t
 
 
 def _stream() -> C.c_void_p:
@@ -108,6 +145,11 @@ def _chk(rc: int, what: str):
         raise SfkError(f"{what} failed rc={rc}: {load().sfk_last_error_string().decode()}")
 
 
+def _chk0(rc: int, what: str):
+    if rc != 0:
+        raise SfkError(f"{what} failed rc={rc}: {load().sfk_last_error_string().decode()}")
+
+
 def _f(v) -> C.c_float:
     return C.c_float(float(v))
 
@@ -117,6 +159,7 @@ def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out
                     taps: Sequence[tuple], flags=0, dscale=None, bias=None, noise=None, noise_w=0.0, xin=None,
                     colscale=None, gs=None, err=None, stages=0, vec_stride=0, vec_off=0, out_d2s=0, a_s2d=0) -> SfkIgemmDesc:
     d = SfkIgemmDesc()
+    block_n = fit_block_n(block_n, n_img, out_h, out_w, out_c)
     d.a, d.n_img, d.a_h, d.a_w, d.a_c, d.a_planes = _p(a), n_img, a_h, a_w, a_c, a_planes
     d.b, d.b_samples, d.b_rows = _p(b), b_samples, b_rows
     d.out, d.out_h, d.out_w, d.out_c = _p(out), out_h, out_w, out_c
@@ -130,9 +173,33 @@ def make_igemm_desc(a, n_img, a_h, a_w, a_c, a_planes, b, b_samples, b_rows, out
     d.out_d2s, d.a_s2d = out_d2s, a_s2d
     d.colscale = _sub(colscale, vec_off) if colscale is not None else C.c_void_p(0)
     d.gs = _sub(gs, vec_off) if gs is not None else C.c_void_p(0)
+    need = int(load().sfk_igemm_workspace_bytes(C.byref(d)))
+    if need:
+        _workspace(a.device, need)
+    d._dev = a.device
+    d._need = need
+    d._plan = None
     # keep the tensors alive as long as the descriptor
     d._keep = (a, b, out, dscale, bias, noise, xin, colscale, gs, err)
     return d
+
+
+class _Plan:
+    """owner of one sfk_igemm_plan (freed with the descriptor that cached it)"""
+
+    def __init__(self, desc: "SfkIgemmDesc"):
+        ws = _workspace(desc._dev, desc._need) if desc._need else None
+        desc.ws, desc.ws_bytes = (ws.data_ptr(), ws.numel()) if ws is not None else (0, 0)
+        h = C.c_void_p()
+        _chk0(load().sfk_igemm_prepare(C.byref(desc), C.byref(h)), "sfk_igemm_prepare")
+        self.h, self.key, self.ws = h, (mode_key(), desc.ws), ws
+
+    def __del__(self):
+        try:
+            if self.h and _lib is not None:
+                _lib.sfk_igemm_destroy(self.h)
+        except Exception:
+            pass
 
 
 def igemm_flops(d: SfkIgemmDesc) -> float:
@@ -142,16 +209,33 @@ def igemm_flops(d: SfkIgemmDesc) -> float:
     return f / 4 if (d.out_d2s or d.a_s2d) else f
 
 
-def igemm(desc: SfkIgemmDesc, ref: bool = False, v1: bool = False):
-    fn = load().sfk_igemm_ref if ref else (load().sfk_igemm_v1 if v1 else load().sfk_igemm)
+def _igemm_launch(desc: SfkIgemmDesc, ref: bool, v1: bool, oneshot: bool):
+    L = load()
+    if ref or v1:
+        _chk((L.sfk_igemm_ref if ref else L.sfk_igemm_v1)(C.byref(desc), _stream()), "sfk_igemm_ref" if ref else "sfk_igemm_v1")
+        return
+    if oneshot:      # the plan-and-forget entry point (kept for callers that build descriptors on the fly)
+        if desc._need:
+            ws = _workspace(desc._dev, desc._need)
+            desc.ws, desc.ws_bytes = ws.data_ptr(), ws.numel()
+        _chk(L.sfk_igemm(C.byref(desc), _stream()), "sfk_igemm")
+        return
+    # prepared plan, cached on the descriptor; re-planned if the process-global modes or the workspace changed underneath it
+    p = desc._plan
+    if p is None or p.key[0] != mode_key() or (desc._need and _WS.get(desc._dev) is not p.ws):
+        p = desc._plan = _Plan(desc)
+    _chk(L.sfk_igemm_run(p.h, _stream()), "sfk_igemm_run")
+
+
+def igemm(desc: SfkIgemmDesc, ref: bool = False, v1: bool = False, oneshot: bool = False):
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _chk(fn(C.byref(desc), _stream()), "sfk_igemm")
+        _igemm_launch(desc, ref, v1, oneshot)
         e1.record()
         _PROFILE.append((e0, e1, igemm_flops(desc), (desc.n_img, desc.out_h, desc.out_w, desc.a_c, desc.out_c, desc.num_taps, desc.num_acc)))
         return
-    _chk(fn(C.byref(desc), _stream()), "sfk_igemm_ref" if ref else "sfk_igemm")
+    _igemm_launch(desc, ref, v1, oneshot)
 
 
 EP_PROFILE = 1 << 16
@@ -196,6 +280,21 @@ def tconv_taps(cout: int):
 def tconv_dgrad_taps(cin: int):
     """transpose of the above: gx~[i] = sum_k gT[2i+k] W[k]^T, gT read from phase plane (ky%2, kx%2) at shift k//2."""
     return [(ky // 2, kx // 2, (ky % 2) * 2 + (kx % 2), 0, (ky * 3 + kx) * cin) for ky in range(3) for kx in range(3)]
+
+
+def fit_block_n(block_n: int, n_img: int, out_h: int, out_w: int, out_c: int) -> int:
+    """Narrower accumulators for launches that would leave most SMs idle.  A CTA owns one (image, N-block) and walks K serially,
+    so the 4x4 .. 16x16 layers of the generator (K = 4608, one or two 128-row tiles per image) are bound by the length of that
+    serial loop, not by bandwidth: 8 images x 4 N-blocks of 128 columns = 32 CTAs on 148 SMs, 72 k-steps of ~770 cycles each
+    (round 1: 25-50 us per launch).  Halving block_n doubles the CTAs and shortens every k-step (the MMA's shared-memory reads
+    are (128 + N) x 32 bytes).  SFK_LOWRES_BN=0 keeps the requested width."""
+    if os.environ.get("SFK_LOWRES_BN", "1") == "0":
+        return block_n
+    tw = 16 if out_w > 8 else (8 if out_w > 4 else 4)
+    tiles = -(-out_h // (128 // tw)) * -(-out_w // tw)
+    while block_n > 32 and n_img * (out_c // block_n) * tiles < 100:
+        block_n //= 2
+    return block_n
 
 
 def pick_block_n(cout: int, num_acc: int = 1) -> int:

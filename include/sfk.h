@@ -29,7 +29,8 @@ typedef void* sfk_stream_t; /* cudaStream_t */
 
 int sfk_version(void);
 /* Activation storage of every entry point: 0 = bf16 (default, product path), 1 = fp32 (parity mode: the same schedules at fp32
- * storage; the conv runs the CUDA-core kernel because the tcgen05 path is bf16).  Process-global; set before allocating. */
+ * storage; the conv runs the same tcgen05 pipeline with kind::tf32 MMAs, see sfk_set_conv_math).  Process-global; set before
+ * allocating. */
 int sfk_set_activation_dtype(int f32);
 int sfk_get_activation_dtype(void);
 const char* sfk_last_error_string(void);
@@ -97,9 +98,30 @@ typedef struct {
    * a_s2d:   A is physically [n][2*a_h][2*a_w][a_c/4]; its K index is p*Cq+c for fine pixel (2h+p/2, 2w+p%2) (space-to-depth
    *          view, used by the data gradient of the fused op). */
   int32_t out_d2s, a_s2d;
+  /* scratch for the split-tf32 parity mode (fp32 storage, conv math 0/2): >= sfk_igemm_workspace_bytes(desc) bytes, 16-byte
+   * aligned, private to this launch while it runs (launches on one stream may share it).  Unused (may be NULL) otherwise. */
+  void* ws;
+  size_t ws_bytes;
 } sfk_igemm_desc;
 
-int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);   /* persistent kernel; call from one host thread at a time */
+/* One-shot launch: plans (tap grouping, shared-memory plan, tensor-map encoding) and launches.  Re-entrant: no static state. */
+int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);
+/* Prepared launches: sfk_igemm_prepare does all the host-side work once and returns an immutable plan bound to the descriptor's
+ * buffers, storage mode and conv math; sfk_igemm_run is then a single kernel launch and may be called concurrently from any
+ * number of host threads / streams.  (The reference has no counterpart: torch caches cuDNN plans the same way.) */
+typedef struct sfk_igemm_plan sfk_igemm_plan;
+int sfk_igemm_prepare(const sfk_igemm_desc* d, sfk_igemm_plan** plan);
+int sfk_igemm_run(const sfk_igemm_plan* plan, sfk_stream_t stream);
+int sfk_igemm_destroy(sfk_igemm_plan* plan);
+/* Arithmetic of the tensor-core conv when the activation storage is fp32 (sfk_set_activation_dtype(1)):
+ *   0 / 2  split tf32: three kind::tf32 passes over hi/lo-split operands (A.hi*B.hi + A.lo*B.hi + A.hi*B.lo), products accurate to
+ *          ~2^-21 relative -- the mode held to north_star's 1e-3 tolerance;   needs desc.ws
+ *   1      plain kind::tf32 (10-bit mantissa operands, fp32 accumulate)
+ *   3      CUDA-core kernel (sfk_igemm_ref), the third opinion
+ * bf16 storage always uses kind::f16 bf16 MMAs.  Process-global; set before preparing plans. */
+int sfk_set_conv_math(int mode);
+int sfk_get_conv_math(void);
+size_t sfk_igemm_workspace_bytes(const sfk_igemm_desc* d);
 /* One-tile-per-CTA variant of the same contract (first implementation; kept for A/B timing and as a second cross-check). */
 int sfk_igemm_v1(const sfk_igemm_desc* d, sfk_stream_t stream);
 /* Profiling aid: with flag bit 16 set, sfk_igemm accumulates per-role wait/total cycles (producer, MMA issuer, epilogue);
