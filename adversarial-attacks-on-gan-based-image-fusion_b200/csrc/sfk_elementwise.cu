@@ -1532,6 +1532,94 @@ __global__ void minmax_kernel(const float* __restrict__ x, float* __restrict__ l
   }
 }
 
+// ---- universal (shared) patch: one patch for every image of the batch -------------------------------------
+// gsum[c][h][w] = mask * gscale * sum_n gpool[n][c][h/k][w/k]: the batch's gradient w.r.t. the shared patch (each image sees the
+// patch through its own mask apply, adversarial_patch.py:137).  Overwrites gsum; one thread per patch pixel, images in registers.
+__global__ void patch_grad_reduce_kernel(const float* __restrict__ gpool, const float* __restrict__ mask, float* __restrict__ gsum,
+                                         float gscale, int N, int S, int k) {
+  const long per = 3L * S * S;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float m = __ldg(mask + i);
+    float acc = 0.f;
+    if (m != 0.f) {
+      for (int n = 0; n < N; ++n) acc += pooled_grad(gpool, n, i, S, k);
+    }
+    gsum[i] = m * gscale * acc;
+  }
+}
+
+// x[n] = clamp((1 - mask) * x0[n] + mask * patch, lo[n], hi[n]) with ONE patch / mask for all images (attack_main2.py:416-418)
+__global__ void patch_apply_shared_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ patch,
+                                          const float* __restrict__ mask, const float* __restrict__ lo, const float* __restrict__ hi, int S) {
+  const int n = blockIdx.y;
+  const long per = 3L * S * S;
+  const float l = lo[n], h = hi[n];
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < per; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long off = static_cast<long>(n) * per + i;
+    const float m = __ldg(mask + i);
+    const float v = (1.f - m) * x0[off] + m * __ldg(patch + i);
+    x[off] = fminf(fmaxf(v, l), h);
+  }
+}
+
+// ---- SSIM (cal_SSMI, interpolation.py:903-919: skimage.metrics.structural_similarity of the rgb2gray images, library defaults:
+// 7x7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03, mean over the pixels whose window lies inside the image).
+// One thread per window centre; the two gray tiles (16+6)^2 are built in shared memory from the NCHW fp32 images.
+constexpr int kSsimT = 16, kSsimW = 7, kSsimR = 3;
+__global__ void __launch_bounds__(kSsimT * kSsimT) ssim_gray7_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                                                    int H, int W, float c1, float c2, float inv_count) {
+  __shared__ float ta[kSsimT + 2 * kSsimR][kSsimT + 2 * kSsimR + 1];
+  __shared__ float tb[kSsimT + 2 * kSsimR][kSsimT + 2 * kSsimR + 1];
+  const int n = blockIdx.z;
+  const int h0 = blockIdx.y * kSsimT, w0 = blockIdx.x * kSsimT;     // window centres (h0 + ty + R, w0 + tx + R)
+  const long plane = static_cast<long>(H) * W;
+  const float* pa = a + static_cast<long>(n) * 3 * plane;
+  const float* pb = b + static_cast<long>(n) * 3 * plane;
+  constexpr int TT = kSsimT + 2 * kSsimR;
+  for (int i = threadIdx.x; i < TT * TT; i += blockDim.x) {
+    const int r = i / TT, c = i % TT;
+    const int h = h0 + r, w = w0 + c;
+    float ga = 0.f, gb = 0.f;
+    if (h < H && w < W) {
+      const long o = static_cast<long>(h) * W + w;
+      ga = 0.2125f * __ldg(pa + o) + 0.7154f * __ldg(pa + plane + o) + 0.0721f * __ldg(pa + 2 * plane + o);   // skimage.color.rgb2gray
+      gb = 0.2125f * __ldg(pb + o) + 0.7154f * __ldg(pb + plane + o) + 0.0721f * __ldg(pb + 2 * plane + o);
+    }
+    ta[r][c] = ga;
+    tb[r][c] = gb;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / kSsimT, tx = threadIdx.x % kSsimT;
+  float val = 0.f;
+  if (h0 + ty + 2 * kSsimR < H && w0 + tx + 2 * kSsimR < W) {     // whole window inside the image
+    // second moments about the window's centre pixel: (co)variances are shift invariant, and E[x^2] - E[x]^2 of the raw values would
+    // cancel catastrophically in fp32 on the smooth regions where SSIM is most sensitive
+    const float u0 = ta[ty + kSsimR][tx + kSsimR], v0 = tb[ty + kSsimR][tx + kSsimR];
+    float sa = 0.f, sb = 0.f, saa = 0.f, sbb = 0.f, sab = 0.f;
+#pragma unroll
+    for (int r = 0; r < kSsimW; ++r)
+#pragma unroll
+      for (int c = 0; c < kSsimW; ++c) {
+        const float u = ta[ty + r][tx + c] - u0, v = tb[ty + r][tx + c] - v0;
+        sa += u; sb += v; saa = fmaf(u, u, saa); sbb = fmaf(v, v, sbb); sab = fmaf(u, v, sab);
+      }
+    constexpr float NP = kSsimW * kSsimW, cov_norm = NP / (NP - 1.f);
+    const float du = sa / NP, dv = sb / NP;
+    const float ux = u0 + du, uy = v0 + dv;
+    const float vx = cov_norm * (saa / NP - du * du), vy = cov_norm * (sbb / NP - dv * dv), vxy = cov_norm * (sab / NP - du * dv);
+    val = ((2.f * ux * uy + c1) * (2.f * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2));
+  }
+  val = warp_sum(val);
+  __shared__ float red[kSsimT * kSsimT / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = val;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int q = 0; q < kSsimT * kSsimT / 32; ++q) s += red[q];
+    atomicAdd(out + n, s * inv_count);
+  }
+}
+
 inline cudaStream_t S_(sfk_stream_t s) { return static_cast<cudaStream_t>(s); }
 inline unsigned per_sample_blocks(long items, int n) {
   long b = (items + kBlock - 1) / kBlock;
@@ -1962,6 +2050,33 @@ int sfk_minmax_per_sample(const float* x, float* lo, float* hi, int n, long per_
   SFK_REQUIRE(x && lo && hi, SFK_E_ARG, "minmax: null");
   minmax_kernel<<<n, 1024, 0, S_(st)>>>(x, lo, hi, per_sample);
   return sfk_check_launch("minmax");
+}
+
+int sfk_patch_grad_reduce(const float* gpool, const float* mask, float* gsum, float gscale, int n, int size, int k, sfk_stream_t st) {
+  SFK_REQUIRE(gpool && mask && gsum, SFK_E_ARG, "patch_grad_reduce: null");
+  SFK_REQUIRE(n >= 1 && size >= 1 && k >= 1 && size % k == 0, SFK_E_SHAPE, "patch_grad_reduce: bad shape");
+  patch_grad_reduce_kernel<<<grid_for(3L * size * size), kBlock, 0, S_(st)>>>(gpool, mask, gsum, gscale, n, size, k);
+  return sfk_check_launch("patch_grad_reduce");
+}
+
+int sfk_patch_apply_shared(float* x, const float* x0, const float* patch, const float* mask, const float* lo, const float* hi, int n,
+                           int size, sfk_stream_t st) {
+  SFK_REQUIRE(x && x0 && patch && mask && lo && hi, SFK_E_ARG, "patch_apply_shared: null");
+  dim3 grid(per_sample_blocks(3L * size * size, n), n);
+  patch_apply_shared_kernel<<<grid, kBlock, 0, S_(st)>>>(x, x0, patch, mask, lo, hi, size);
+  return sfk_check_launch("patch_apply_shared");
+}
+
+int sfk_ssim_gray7(const float* a, const float* b, float* out, int n, int h, int w, float data_range, sfk_stream_t st) {
+  SFK_REQUIRE(a && b && out, SFK_E_ARG, "ssim: null");
+  SFK_REQUIRE(n >= 1 && h >= kSsimW && w >= kSsimW, SFK_E_SHAPE, "ssim: images must be at least 7x7");
+  const int vh = h - 2 * kSsimR, vw = w - 2 * kSsimR;     // window centres
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n, S_(st));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid((vw + kSsimT - 1) / kSsimT, (vh + kSsimT - 1) / kSsimT, n);
+  const float c1 = (0.01f * data_range) * (0.01f * data_range), c2 = (0.03f * data_range) * (0.03f * data_range);
+  ssim_gray7_kernel<<<grid, kSsimT * kSsimT, 0, S_(st)>>>(a, b, out, h, w, c1, c2, 1.f / (static_cast<float>(vh) * vw));
+  return sfk_check_launch("ssim_gray7");
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@ Layouts: activations NHWC bf16, images NCHW fp32, style ve
 """
 from __future__ import annotations
 
+import functools
 import math
 import os
 from dataclasses import dataclass, field
@@ -28,6 +29,19 @@ from .params import EncSpec, GenSpec, VGG_CONVS, fused_up_base_weights
 def ACT() -> torch.dtype:
     """activation storage type of the library right now: bf16 (product) or fp32 (parity mode)"""
     return lib.activation_dtype()
+
+
+def _on_device(fn):
+    """Launches go to torch's current stream of the CURRENT device; an engine built for another device switches to it first
+    (the C ABI only sees pointers and a stream)."""
+    @functools.wraps(fn)
+    def wrap(self, *a, **k):
+        dev = self.dev
+        if dev.type == "cuda" and dev.index is not None and torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return fn(self, *a, **k)
+        return fn(self, *a, **k)
+    return wrap
 
 
 def _empty(shape, dev, dtype=None):
@@ -73,7 +87,8 @@ def encoder_layers(spec: EncSpec) -> List[StackLayer]:
 class ConvStack:
     def __init__(self, layers: List[StackLayer], weights: Sequence[Tuple[torch.Tensor, torch.Tensor]], n: int, res: int,
                  device, err: torch.Tensor):
-        self.layers, self.n, self.res, self.dev, self.err = layers, n, res, device, err
+        self.layers, self.n, self.res, self.dev, self.err = layers, n, res, torch.device(device), err
+        self.mode = lib.mode_key()      # storage dtype / conv math the buffers and plans were built for
         self.w_f32, self.bias, self.w_fwd, self.w_bwd = {}, {}, {}, {}
         h = w = res
         c = 3
@@ -119,6 +134,7 @@ class ConvStack:
                 lib.pick_block_n(l.cin), lib.conv3x3_dgrad_taps(l.cin), flags=flags,
                 xin=self.out[i - 1] if flags else None, err=self.err)
 
+    @_on_device
     def forward(self, x: torch.Tensor):
         """x: (n,3,res,res) fp32 NCHW."""
         for i, l in enumerate(self.layers):
@@ -137,6 +153,7 @@ class ConvStack:
         per = self.out[i].numel() // self.n
         return coef / per, 2.0 * coef / per
 
+    @_on_device
     def backward(self, tap_refs: Optional[Sequence[torch.Tensor]] = None, tap_coef: float = 0.0,
                  loss: Optional[torch.Tensor] = None, top_grad_ready: bool = False) -> torch.Tensor:
         """Back-propagate sum_taps coef*MSE(tap, ref) (and/or a gradient already stored, masked, in g[-1])
@@ -190,7 +207,8 @@ class SynthesisEngine:
     """StyleGAN2 synthesis from a concatenated StyleSpace vector s (B, s_dim)."""
 
     def __init__(self, spec: GenSpec, P: Dict[str, torch.Tensor], batch: int, device, err: torch.Tensor):
-        self.spec, self.B, self.dev, self.err = spec, batch, device, err
+        self.spec, self.B, self.dev, self.err = spec, batch, torch.device(device), err
+        self.mode = lib.mode_key()
         B = batch
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         self.layers = spec.layers
@@ -346,17 +364,21 @@ class SynthesisEngine:
             prev_conv = e
 
     # ---------------------------------------------------------------------------------------
+    @_on_device
     def styles_from_wplus(self, wplus: torch.Tensor, s_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         s_out = self.s if s_out is None else s_out
         lib.style_affine_fwd(wplus, self.A_all, self.b_all, self.row_widx, s_out, self.aff_scale)
         return s_out
 
+    @_on_device
     def wplus_grad_from_styles(self, gs: torch.Tensor, gw: torch.Tensor) -> torch.Tensor:
         lib.style_affine_bwd(gs, self.A_all, self.layer_row_start, self.layer_widx, gw, self.aff_scale)
         return gw
 
+    @_on_device
     def forward(self, s: Optional[torch.Tensor] = None) -> torch.Tensor:
         """s (B, s_dim) fp32 (default: self.s).  Returns the image buffer (B,3,size,size) fp32."""
+        assert self.mode == lib.mode_key(), "engine was built under another activation dtype / conv math (rebuild it)"
         if s is not None and s.data_ptr() != self.s.data_ptr():
             self.s.copy_(s)
         s = self.s
@@ -380,6 +402,7 @@ class SynthesisEngine:
     def image(self) -> torch.Tensor:
         return self.L[-1]["rgb"]
 
+    @_on_device
     def backward(self, g_img: torch.Tensor) -> torch.Tensor:
         """g_img (B,3,size,size) fp32 -> gs (B, s_dim) fp32 (owned).  Must follow forward() with the same s.
 
@@ -488,6 +511,7 @@ class AttackEngine:
         self.stats = _zeros((2 * B,), dev)
 
     # ---------------------------------------------------------------------------------------
+    @_on_device
     def set_inputs(self, xa: torch.Tensor, xb: torch.Tensor):
         B = self.B
         self.x0[:B].copy_(xa)
@@ -509,6 +533,7 @@ class AttackEngine:
             self.syn.styles_from_wplus(self.codes, self.s_all)
             lib.fuse_spatial_fwd(self.s_all[:B], self.s_all[B:], self.FP["alpha"], self.FP["beta"], self.FP["c"], self.syn.s)
 
+    @_on_device
     def fused_forward(self) -> torch.Tensor:
         """current x -> fused image (B,3,S,S) fp32 (buffer owned by the synthesis engine)."""
         self._encode()
@@ -519,6 +544,7 @@ class AttackEngine:
         lib.avgpool_affine_fwd(img, self.vgg_in, self.k_vgg, 1.0, 0.0)
         self.vgg.forward(self.vgg_in)
 
+    @_on_device
     def compute_reference(self, target: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """Reference = fusion of the clean pair (untargeted) or of `target` (targeted)."""
         B = self.B
@@ -541,6 +567,7 @@ class AttackEngine:
                 r.copy_(t)
         self.x.copy_(keep)
 
+    @_on_device
     def forward_backward(self):
         """loss (B,) and the gradient w.r.t. the pooled, [-1,1]-mapped inputs g_xin (2B,3,R,R);
         d loss / d x(full res, [0,1]) = (2/k^2) * g_xin[h/k][w/k]."""
@@ -643,6 +670,8 @@ class ReconAttackEngine:
         self.x, self.x_org, self.x_tgt, self.g_full, self.g_rec = (_empty((B, 3, S, S), dev, torch.float32) for _ in range(5))
         self.xin, self.g_xin, self.rec_in = (_empty((B, 3, R, R), dev, torch.float32) for _ in range(3))
         self.loss = _zeros((B,), dev)
+        # the three terms the reference logs every 5 iterations (attack_main2.py:660-666), unweighted, per sample
+        self.terms = _zeros((3, B), dev)      # l_latent_target, l_latent_org, l_img_org
         self.m, self.v = torch.zeros_like(self.x), torch.zeros_like(self.x)
 
     def _encode(self, x):
@@ -650,6 +679,7 @@ class ReconAttackEngine:
         lib.gap_fwd(self.enc.forward(self.xin), self.feat)
         lib.linear_fwd(self.feat, self.head_w, self.head_b, self.codes.view(self.B, -1))
 
+    @_on_device
     def set_inputs(self, img: torch.Tensor, img_target: torch.Tensor):
         """no_grad setup of optimize_vgg (attack_main2.py:588-603): latents and VGG features of the clean and target image."""
         self.x_org.copy_(img)
@@ -664,19 +694,25 @@ class ReconAttackEngine:
         self.m.zero_()
         self.v.zero_()
 
+    @_on_device
     def reconstruct(self, x: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._encode(self.x if x is None else x)
         self.syn.styles_from_wplus(self.codes)
         return self.syn.forward()
 
+    @_on_device
     def forward_backward(self):
-        """-> loss (B,), g_xin (pooled-resolution gradient; full-res = g_xin[h/k][w/k]/k^2), g_full (direct full-res term)."""
+        """-> loss (B,), g_xin (pooled-resolution gradient; full-res = g_xin[h/k][w/k]/k^2), g_full (direct full-res term).
+        self.terms holds the unweighted l_latent_target / l_latent_org / l_img_org of this iteration (the reference's log line)."""
         c, B, S = self.cfg, self.B, self.S
         per = 3 * S * S
         self.loss.zero_()
+        self.terms.zero_()
         img_rec = self.reconstruct()
-        lib.mse_f32(self.codes, self.lat_t, self.gcodes, self.loss, c.w_latent_target / self.LD, 2 * c.w_latent_target / self.LD, False)
-        lib.mse_f32(self.codes, self.lat_o, self.gcodes, self.loss, c.w_latent_org / self.LD, 2 * c.w_latent_org / self.LD, True)
+        lib.mse_f32(self.codes, self.lat_t, self.gcodes, self.terms[0], 1.0 / self.LD, 2 * c.w_latent_target / self.LD, False)
+        lib.mse_f32(self.codes, self.lat_o, self.gcodes, self.terms[1], 1.0 / self.LD, 2 * c.w_latent_org / self.LD, True)
+        lib.axpby(self.loss, self.terms[0], self.loss, 1.0, c.w_latent_target)
+        lib.axpby(self.loss, self.terms[1], self.loss, 1.0, c.w_latent_org)
         g_vin = None
         if self.vgg_rec is not None:
             lib.avgpool_affine_fwd(img_rec, self.rec_in, self.k_vgg, 1.0, 0.0)
@@ -697,9 +733,11 @@ class ReconAttackEngine:
             lib.axpby(g_enc, g_v, self.g_xin, 1.0, 1.0)
         else:
             self.g_xin.copy_(g_enc)
-        lib.image_loss_grad(self.x, self.x_org, None, self.g_full, self.loss, c.w_img_org / per, 2 * c.w_img_org / per, 1)
+        lib.image_loss_grad(self.x, self.x_org, None, self.g_full, self.terms[2], 1.0 / per, 2 * c.w_img_org / per, 1)
+        lib.axpby(self.loss, self.terms[2], self.loss, 1.0, c.w_img_org)
         return self.loss, self.g_xin, self.g_full
 
+    @_on_device
     def adam_step(self, t: int, lr: float):
         k = self.k_in
         lib.attack_update_adam(self.x, self.g_xin, self.m, self.v, lr, t, 1.0 / (k * k), k, gfull=self.g_full, gfull_scale=1.0)

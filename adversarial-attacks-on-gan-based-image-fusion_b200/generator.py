@@ -23,15 +23,19 @@ class Generator:
         self.size, self.style_dim, self.n_latent = size, style_dim, self.spec.n_latent
         self.device = torch.device(device)
         self.params = params if params is not None else make_generator_params(self.spec, seed)
-        self._engines: Dict[int, SynthesisEngine] = {}
+        self._engines: Dict[tuple, SynthesisEngine] = {}
         self._err = None
         self._map = None
+        self.version = 0          # bumped whenever the weights or the device change (engine caches key on it)
 
     # --- torch.nn.Module-ish conveniences used by the reference scripts
     def to(self, device):
-        self.device = torch.device(device)
-        self._engines.clear()
-        self._map = None
+        if torch.device(device) != self.device:
+            self.device = torch.device(device)
+            self._engines.clear()
+            self._err = None
+            self._map = None
+            self.version += 1
         return self
 
     def eval(self):
@@ -47,13 +51,15 @@ class Generator:
         self.params = {k: sd[k].detach().clone() for k in self.params}
         self._engines.clear()
         self._map = None
+        self.version += 1
 
     def engine(self, batch: int) -> SynthesisEngine:
-        if batch not in self._engines:
+        key = (batch, lib.mode_key())
+        if key not in self._engines:
             if self._err is None:
                 self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._engines[batch] = SynthesisEngine(self.spec, self.params, batch, self.device, self._err)
-        return self._engines[batch]
+            self._engines[key] = SynthesisEngine(self.spec, self.params, batch, self.device, self._err)
+        return self._engines[key]
 
     # --- mapping network z -> w  (8 x EqualLinear(lr_mul=0.01) + fused lrelu; off the hot path)
     def get_latent(self, z: torch.Tensor) -> torch.Tensor:

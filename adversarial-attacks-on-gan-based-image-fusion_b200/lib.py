@@ -56,7 +56,8 @@ EXPORTS = [
     "sfk_modulate_weights", "sfk_demod_fwd_batched", "sfk_modulate_weights_batched", "sfk_demod_bwd_batched", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
     "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_update_patch",
-    "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample",
+    "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample", "sfk_patch_grad_reduce", "sfk_patch_apply_shared",
+    "sfk_ssim_gray7",
 ]
 
 _lib = None
@@ -539,3 +540,23 @@ def attack_update_l2(x, x0, gpool, norms, dn, alpha, eps, direction, lo, hi, pha
 def minmax_per_sample(x, lo, hi):
     n = x.shape[0]
     _chk(load().sfk_minmax_per_sample(_p(x), _p(lo), _p(hi), n, C.c_long(x.numel() // n), _stream()), "minmax")
+
+
+def patch_grad_reduce(gpool, mask, gsum, gscale, k):
+    """gsum (1,3,S,S) = mask * gscale * sum_n gpool[n][c][h/k][w/k]: gradient of the batch w.r.t. ONE shared patch"""
+    n, _, sp, _ = gpool.shape
+    s = sp * k
+    assert tuple(mask.shape[-3:]) == (3, s, s) and tuple(gsum.shape[-3:]) == (3, s, s) and mask.numel() == gsum.numel() == 3 * s * s
+    _chk(load().sfk_patch_grad_reduce(_p(gpool), _p(mask), _p(gsum), _f(gscale), n, s, k, _stream()), "patch_grad_reduce")
+
+
+def patch_apply_shared(x, x0, patch, mask, lo, hi):
+    n, _, s, _ = x.shape
+    assert tuple(x0.shape) == tuple(x.shape) and patch.numel() == mask.numel() == 3 * s * s and lo.numel() >= n and hi.numel() >= n
+    _chk(load().sfk_patch_apply_shared(_p(x), _p(x0), _p(patch), _p(mask), _p(lo), _p(hi), n, s, _stream()), "patch_apply_shared")
+
+
+def ssim_gray7(a, b, out, data_range=2.0):
+    n, c, h, w = a.shape
+    assert c == 3 and tuple(b.shape) == tuple(a.shape) and out.numel() >= n
+    _chk(load().sfk_ssim_gray7(_p(a), _p(b), _p(out), n, h, w, _f(data_range), _stream()), "ssim_gray7")

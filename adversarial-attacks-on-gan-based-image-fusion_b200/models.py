@@ -20,12 +20,16 @@ class Encoder:
         self.spec = spec
         self.params = params if params is not None else make_encoder_params(spec, seed)
         self.device = torch.device(device)
-        self._stacks: Dict[int, ConvStack] = {}
+        self._stacks: Dict[tuple, ConvStack] = {}
         self._err = None
+        self.version = 0
 
     def to(self, device):
-        self.device = torch.device(device)
-        self._stacks.clear()
+        if torch.device(device) != self.device:
+            self.device = torch.device(device)
+            self._stacks.clear()
+            self._err = None
+            self.version += 1
         return self
 
     def eval(self):
@@ -33,14 +37,15 @@ class Encoder:
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         n = x.shape[0]
-        if n not in self._stacks:
+        key = (n, lib.mode_key())
+        if key not in self._stacks:
             if self._err is None:
                 self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
             w = [(self.params[f"convs.{i}.weight"], self.params[f"convs.{i}.bias"]) for i in range(len(self.spec.widths))]
-            self._stacks[n] = ConvStack(encoder_layers(self.spec), w, n, self.spec.in_res, self.device, self._err)
+            self._stacks[key] = ConvStack(encoder_layers(self.spec), w, n, self.spec.in_res, self.device, self._err)
             self._hw = self.params["head.weight"].to(self.device).contiguous()
             self._hb = self.params["head.bias"].to(self.device).contiguous()
-        st = self._stacks[n]
+        st = self._stacks[key]
         top = st.forward(x.to(self.device, torch.float32).contiguous())
         feat = torch.empty(n, self.spec.widths[-1], device=self.device)
         lib.gap_fwd(top, feat)

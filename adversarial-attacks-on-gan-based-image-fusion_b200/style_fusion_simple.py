@@ -5,6 +5,7 @@ SURVEY A.4: parts are blended pairwise in StyleSpace with a learned (here random
 from __future__ import annotations
 
 import json
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -21,45 +22,73 @@ _PARTS = {   # get_all_active_parts() of the three hierarchies (code/style_fusio
 }
 
 
-class _Blender:
-    """stand-in for sf_hierarchy.nodes["all"]"""
+class _Node:
+    """One node of the hierarchy (stand-in for a `stylefusion.sf_hierarchy` node): its FusionNet is the per-dimension
+    gate q = sigmoid(alpha*s_a + beta*s_b + c), s = q*s_a + (1-q)*s_b that blends this part's StyleSpace vector into the running
+    result.  `load_fusion_net(path, device)` (code/style_fusion_simple.py:77) loads the gate {"alpha","beta","c"} from a torch file."""
 
-    def __init__(self, parts: List[str], s_dim: int, device, seed: int = 2):
-        self.parts, self.device = parts, device
-        self.gates = {p: {k: v.to(device) for k, v in make_fusion_params(s_dim, seed + i).items()} for i, p in enumerate(parts)}
-        self.fusion_net = self
+    def __init__(self, name: str, s_dim: int, device, seed: int):
+        self.name, self.device, self.s_dim = name, device, s_dim
+        self.fusion_net = _Gate({k: v.to(device) for k, v in make_fusion_params(s_dim, seed).items()})
 
-    def get_all_active_parts(self):
-        return list(self.parts)
+    def load_fusion_net(self, path, device):
+        sd = torch.load(path, map_location="cpu")
+        missing = [k for k in ("alpha", "beta", "c") if k not in sd]
+        if missing:
+            raise KeyError(f"{path}: fusion-net file lacks {missing} (expected the gate tensors alpha/beta/c of length {self.s_dim})")
+        for k in ("alpha", "beta", "c"):
+            if tuple(sd[k].shape) != (self.s_dim,):
+                raise ValueError(f"{path}: {k} has shape {tuple(sd[k].shape)}, expected ({self.s_dim},)")
+        self.fusion_net = _Gate({k: sd[k].float().to(device).contiguous() for k in ("alpha", "beta", "c")})
+        return self.fusion_net
 
-    def load_fusion_net(self, path, device):      # real FusionNet checkpoints are not loadable by the stand-in
-        return None
+
+class _Gate:
+    def __init__(self, p):
+        self.p = p
 
     def to(self, device):
+        self.p = {k: v.to(device) for k, v in self.p.items()}
         return self
 
     def eval(self):
         return self
 
+    def __call__(self, s_a: torch.Tensor, s_b: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(s_a)
+        lib.fuse_spatial_fwd(s_a.contiguous(), s_b.contiguous(), self.p["alpha"], self.p["beta"], self.p["c"], out)
+        return out
+
+
+class _Root(_Node):
+    """nodes["all"]: walks the parts in hierarchy order and gates every part whose style differs from the running result"""
+
+    def __init__(self, hierarchy, parts: List[str], s_dim: int, device, seed: int):
+        super().__init__("all", s_dim, device, seed)
+        self.hierarchy, self.parts = hierarchy, parts
+
+    def get_all_active_parts(self):
+        return list(self.parts)
+
     def forward(self, s_dict: Dict[str, list]):
-        cat = lambda s: torch.cat(s, 1).contiguous() if isinstance(s, (list, tuple)) else s
+        cat = lambda s: torch.cat(list(s), 1).contiguous() if isinstance(s, (list, tuple)) else s
         out = cat(s_dict[self.parts[0]])
         for p in self.parts[1:]:
             if p not in s_dict:
                 continue
             b = cat(s_dict[p])
-            if b.data_ptr() == out.data_ptr() or torch.equal(b, out):
+            if torch.equal(b, out):
                 continue
-            g = self.gates[p]
-            res = torch.empty_like(out)
-            lib.fuse_spatial_fwd(out, b, g["alpha"], g["beta"], g["c"], res)
-            out = res
+            out = self.hierarchy.nodes[p].fusion_net(out, b)
         return out
 
 
 class _Hierarchy:
-    def __init__(self, blender):
-        self.nodes = {"all": blender}
+    """stand-in for SFHierarchyFFHQ / SFHierarchyCar / SFHierarchyChurch: `.nodes[name]`, root `nodes["all"]`"""
+
+    def __init__(self, parts: List[str], s_dim: int, device, seed: int = 2):
+        self.nodes = {p: _Node(p, s_dim, device, seed + i) for i, p in enumerate(parts) if p != "all"}
+        self.nodes["all"] = _Root(self, parts, s_dim, device, seed + parts.index("all"))
 
 
 class StyleFusionSimple:
@@ -76,12 +105,17 @@ class StyleFusionSimple:
                 self.original_net.load_state_dict(torch.load(stylegan_weights, map_location="cpu")["g_ema"], strict=True)
         self.original_net.to(self.device)
         self.mean_latent = self.original_net.mean_latent(4096)                                             # :60
-        blender = _Blender(_PARTS[stylegan_type], self.original_net.spec.s_dim, self.device)
-        self.sf_hierarchy = _Hierarchy(blender)                                                            # :62-71
+        self.sf_hierarchy = _Hierarchy(_PARTS[stylegan_type], self.original_net.spec.s_dim, self.device)   # :62-71
         self.base_blender = self.sf_hierarchy.nodes["all"]
         if fusion_nets_weights:
             with open(fusion_nets_weights, "r") as f:                                                      # :73-80
-                self.fusion_nets_paths = json.load(f)
+                fusion_nets_paths = json.load(f)
+            base = os.path.dirname(os.path.abspath(fusion_nets_weights))
+            for key in fusion_nets_paths.keys():
+                path = fusion_nets_paths[key]
+                self.sf_hierarchy.nodes[key].load_fusion_net(path if os.path.isabs(path) else os.path.join(base, path), self.device)
+                self.sf_hierarchy.nodes[key].fusion_net.to(self.device)
+                self.sf_hierarchy.nodes[key].fusion_net.eval()
 
     def generate_img(self, base_latent, latents_type="z", hair=None, face=None, background=None, all=None, mouth=None, eyes=None,
                      wheels=None, car=None, bg_top=None, bg_bottom=None):                                  # :82-108

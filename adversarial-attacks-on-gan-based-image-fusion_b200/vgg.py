@@ -24,17 +24,21 @@ class VGGBase:
         self.device = torch.device(device)
         self._stacks: Dict[tuple, ConvStack] = {}
         self._err = None
+        self.version = 0
 
     def to(self, device):
-        self.device = torch.device(device)
-        self._stacks.clear()
+        if torch.device(device) != self.device:
+            self.device = torch.device(device)
+            self._stacks.clear()
+            self._err = None
+            self.version += 1
         return self
 
     def eval(self):
         return self
 
     def stack(self, n: int, res: int) -> ConvStack:
-        key = (n, res)
+        key = (n, res, lib.mode_key())
         if key not in self._stacks:
             if self._err is None:
                 self._err = torch.zeros(1, dtype=torch.int32, device=self.device)

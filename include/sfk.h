@@ -262,6 +262,19 @@ int sfk_attack_update_adam(float* x, const float* gpool, const float* gfull, flo
 int sfk_attack_update_l2(float* x, const float* x0, const float* gpool, float* norms, float* dn, float alpha,
                          float eps, float dir, float lo, float hi, int phase, int n, int size, int k, sfk_stream_t st);
 int sfk_minmax_per_sample(const float* x, float* lo, float* hi, int n, long per_sample, sfk_stream_t st);
+/* Universal (shared) patch, the data-parallel form of patch.train (adversarial_patch.py:26-74): one patch / mask
+ * (3 x size x size) for all n images.
+ *   grad_reduce: gsum = mask * gscale * sum_n gpool[n][c][h/k][w/k]   (overwrites gsum; all-reduce it over ranks, then patch -= lr*gsum)
+ *   apply:       x[n] = clamp((1-mask)*x0[n] + mask*patch, lo[n], hi[n])                    (adversarial_patch.py:137-138) */
+int sfk_patch_grad_reduce(const float* gpool, const float* mask, float* gsum, float gscale, int n, int size, int k, sfk_stream_t st);
+int sfk_patch_apply_shared(float* x, const float* x0, const float* patch, const float* mask, const float* lo, const float* hi, int n,
+                           int size, sfk_stream_t st);
+
+/* ---------------------------------------------------------------------------------------------
+ * Outcome metric: SSIM of two RGB image batches (NCHW fp32), as cal_SSMI computes it (code/attack/interpolation.py:903-919:
+ * skimage rgb2gray + structural_similarity with library defaults: 7x7 uniform window, sample covariance, K1 0.01, K2 0.03,
+ * mean over the windows that lie inside the image).  out[n] = mean SSIM of image pair n.  data_range: 2 for [-1,1] floats. */
+int sfk_ssim_gray7(const float* a, const float* b, float* out, int n, int h, int w, float data_range, sfk_stream_t st);
 
 #ifdef __cplusplus
 }

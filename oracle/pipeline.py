@@ -306,3 +306,63 @@ def optimize_vgg_oracle(gspec, GP, espec, EP, vgg_sd, img, img_target, cfg: Reco
             record.append(dict(loss=L.detach().clone(), grad=x.grad.detach().clone(), img_rec=img_rec.detach().clone()))
         opt.step()
     return x.detach()
+
+
+# ---------------------------------------------------------------------------------------------
+def patch_attack_oracle(gspec, GP, espec, EP, vgg_sd, img, patch, mask, target_img, max_count: int, cfg: ReconLossCfg = None,
+                        record=None):
+    """Restatement of patch.attack (code/attack/patch/adversarial_patch.py:94-160): raw-gradient descent on the patch through
+    encoder -> generator -> VGG, `Loss = -l_latent_org` by default (:126), re-mask and clamp to the clean range every step
+    (:131-138).  img/patch/mask (b,3,S,S) in [-1,1]; per-sample means (the reference runs batch 1).  -> (adv_x, mask, patch, rec)."""
+    cfg = cfg or ReconLossCfg(0.0, -1.0, 0.0, 0.0, 0.0, 0.0)
+    k = gspec.size // espec.in_res
+    pool = (lambda t: F.avg_pool2d(t, k, k)) if k > 1 else (lambda t: t)
+    with torch.no_grad():                                                                   # :98-104
+        latent_org = encoder_forward(EP, espec, pool(img))
+        latent_target = encoder_forward(EP, espec, pool(target_img))
+        f_target = vgg_forward(vgg_sd, pool(target_img))
+    lo = img.flatten(1).min(1)[0].view(-1, 1, 1, 1)
+    hi = img.flatten(1).max(1)[0].view(-1, 1, 1, 1)
+    patch = patch.clone()
+    adv_x = (1 - mask) * img + mask * patch                                                 # :106 (no clamp before the first step)
+    adv_x = torch.maximum(torch.minimum(adv_x, hi), lo)      # the CUDA path clamps here too; a no-op for patches inside the range
+    rec = None
+    for count in range(max_count):                                                          # :111-158
+        x = adv_x.detach().clone().requires_grad_(True)
+        lat = encoder_forward(EP, espec, pool(x))
+        rec = sg.synthesis_from_styles(GP, gspec, sg.styles_from_wplus(GP, gspec, lat))
+        L = cfg.w_latent_target * per_sample_mse(lat, latent_target) + cfg.w_latent_org * per_sample_mse(lat, latent_org)
+        L = L + cfg.w_img_rec_target * per_sample_mse(rec, target_img)
+        if cfg.w_lpips_rec != 0.0:
+            L = L + cfg.w_lpips_rec * sum(per_sample_mse(a, b) for a, b in zip(vgg_forward(vgg_sd, pool(rec)), f_target))
+        (g,) = torch.autograd.grad(L.sum(), x)
+        if record is not None:
+            record.append(dict(loss=L.detach().clone(), grad=g.clone()))
+        patch = patch - g                                                                   # :133
+        adv_x = (1 - mask) * img + mask * patch                                             # :137
+        adv_x = torch.maximum(torch.minimum(adv_x, hi), lo)                                 # :138
+    return adv_x.detach(), mask, patch, rec.detach()
+
+
+def universal_patch_oracle(gspec, GP, espec, EP, vgg_sd, imgs, patch, mask, target_img, max_count: int, lr: float = 1.0):
+    """batch form of the above with ONE shared patch: patch -= lr * sum_n mask * dL_n/dx_n."""
+    cfg = ReconLossCfg(0.0, -1.0, 0.0, 0.0, 0.0, 0.0)
+    k = gspec.size // espec.in_res
+    pool = (lambda t: F.avg_pool2d(t, k, k)) if k > 1 else (lambda t: t)
+    with torch.no_grad():
+        latent_org = encoder_forward(EP, espec, pool(imgs))
+    lo = imgs.flatten(1).min(1)[0].view(-1, 1, 1, 1)
+    hi = imgs.flatten(1).max(1)[0].view(-1, 1, 1, 1)
+    patch = patch.clone()
+    apply = lambda p: torch.maximum(torch.minimum((1 - mask) * imgs + mask * p, hi), lo)
+    adv_x = apply(patch)
+    losses = []
+    for _ in range(max_count):
+        x = adv_x.detach().clone().requires_grad_(True)
+        lat = encoder_forward(EP, espec, pool(x))
+        L = cfg.w_latent_org * per_sample_mse(lat, latent_org)
+        (g,) = torch.autograd.grad(L.sum(), x)
+        losses.append(L.detach())
+        patch = patch - lr * (mask * g).sum(0, keepdim=True)
+        adv_x = apply(patch)
+    return patch, adv_x.detach(), torch.stack(losses)

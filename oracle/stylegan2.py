@@ -123,7 +123,7 @@ def synthesis_from_styles(P, spec: GenSpec, styles: Sequence[torch.Tensor], retu
 
 def mean_latent(P, spec: GenSpec, n: int, seed: int = 0) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
-    z = torch.randn(n, spec.style_dim, generator=g)
+    z = torch.randn(n, spec.style_dim, generator=g).to(P["input.input"].device)   # the oracle may be run on a GPU (fp32, TF32 off) for the large cases
     return mapping(P, spec, z).mean(0, keepdim=True)
 
 
