@@ -1731,6 +1731,19 @@ extern "C" int sfk_igemm_run(const sfk_igemm_plan* plan, sfk_stream_t stream) {
   SFK_REQUIRE(plan != nullptr, SFK_E_ARG, "igemm_run: null plan");
   return launch_plan(reinterpret_cast<const IgemmPlan*>(plan), stream);
 }
+// What the planner decided, for tests and for the launch <-> ncu-row map under profiles/:
+//   [0] two M tiles per stage  [1] halo loads  [2] resident weights  [3] depth-to-space out  [4] space-to-depth in  [5] passes
+//   [6] pipeline stages  [7] block_n  [8] compile-time variant (-1 run time)  [9] epilogue flags  [10] grid.x  [11] grid.y
+//   [12] dynamic smem bytes  [13] fp32 storage  [14] CUDA-core kernel  [15] accumulator stages
+extern "C" int sfk_igemm_plan_info(const sfk_igemm_plan* plan, int32_t* out16) {
+  SFK_REQUIRE(plan != nullptr && out16 != nullptr, SFK_E_ARG, "igemm_plan_info: null");
+  const IgemmPlan* P = reinterpret_cast<const IgemmPlan*>(plan);
+  const Igemm2Args& k = P->k;
+  const int v[16] = {k.m2, k.TWB != k.TW ? 1 : 0, k.b_resident, k.out_d2s, k.a_s2d, k.passes, k.stages, k.block_n, P->var, P->fct,
+                     static_cast<int>(P->grid.x), static_cast<int>(P->grid.y), static_cast<int>(P->smem), P->f32, P->use_ref, k.acc_stages};
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
+  return 0;
+}
 extern "C" int sfk_igemm_destroy(sfk_igemm_plan* plan) {
   free(plan);
   return 0;

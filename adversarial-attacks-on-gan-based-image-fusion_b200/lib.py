@@ -49,7 +49,7 @@ class SfkIgemmDesc(C.Structure):
 
 # every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
-    "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_prepare", "sfk_igemm_run", "sfk_igemm_destroy", "sfk_set_conv_math", "sfk_get_conv_math",
+    "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_prepare", "sfk_igemm_run", "sfk_igemm_destroy", "sfk_igemm_plan_info", "sfk_set_conv_math", "sfk_get_conv_math",
     "sfk_igemm_workspace_bytes", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
         _lib.sfk_igemm_workspace_bytes.restype = C.c_size_t
         _lib.sfk_igemm_run.argtypes = [C.c_void_p, C.c_void_p]
         _lib.sfk_igemm_destroy.argtypes = [C.c_void_p]
+        _lib.sfk_igemm_plan_info.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -226,6 +227,22 @@ def _igemm_launch(desc: SfkIgemmDesc, ref: bool, v1: bool, oneshot: bool):
     if p is None or p.key[0] != mode_key() or (desc._need and _WS.get(desc._dev) is not p.ws):
         p = desc._plan = _Plan(desc)
     _chk(L.sfk_igemm_run(p.h, _stream()), "sfk_igemm_run")
+
+
+PLAN_INFO_KEYS = ("m2", "halo", "resident", "d2s", "s2d", "passes", "stages", "block_n", "variant", "flags", "grid_x", "grid_y", "smem",
+                  "f32", "cuda_cores", "acc_stages")
+
+
+def plan_info(desc: SfkIgemmDesc) -> dict:
+    """what the planner decided for this descriptor under the current modes (prepares the plan if needed)"""
+    p = desc._plan
+    if p is None or p.key[0] != mode_key() or (desc._need and _WS.get(desc._dev) is not p.ws):
+        p = desc._plan = _Plan(desc)
+    buf = (C.c_int32 * 16)()
+    _chk0(load().sfk_igemm_plan_info(p.h, buf), "sfk_igemm_plan_info")
+    d = dict(zip(PLAN_INFO_KEYS, list(buf)))
+    d.update(shape=(desc.n_img, desc.out_h, desc.out_w, desc.a_c, desc.out_c), taps=desc.num_taps, num_acc=desc.num_acc)
+    return d
 
 
 def igemm(desc: SfkIgemmDesc, ref: bool = False, v1: bool = False, oneshot: bool = False):

@@ -335,6 +335,24 @@ def run_ours(args):
                 "algorithmic_gflop_per_iter_image": fl["attack"] / 1e9,
                 "step_frac_of_roofline": (fl["attack"] * B / (step_ms * 1e-3)) / (peaks["bf16_tflops"] * 1e12)}
 
+    # -------- optional diagnostics (never part of a reported number): per-launch conv timings with the planner's decisions, and a
+    # per-kernel time table of one eager step from torch's profiler
+    if rank == 0 and args.dump_launches:
+        rows = [dict(us=1e3 * ms_, gflop=f / 1e9, tflops=(f / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0), n=shp[0], out_h=shp[1], out_w=shp[2],
+                     cin=shp[3], cout=shp[4], taps=shp[5], num_acc=shp[6]) for ms_, f, shp in prof["per_launch"]]
+        infos = []
+        for st in (eng.enc, eng.vgg):
+            infos += [lib.plan_info(d) for d in list(st._fwd_desc.values()) + list(st._bwd_desc.values())]
+        for e in eng.syn.L:
+            infos += [lib.plan_info(e[k_]) for k_ in ("fwd", "bwd") if k_ in e]
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as tp_:
+            step()
+            torch.cuda.synchronize(dev)
+        table = sorted(((ev.key, ev.count, ev.device_time_total) for ev in tp_.key_averages()), key=lambda r: -r[2])
+        json.dump(dict(step_ms=step_ms, conv_launches=rows, plans=infos, kernel_table=[dict(name=n_[:120], count=c_, us=u_) for n_, c_, u_ in table]),
+                  open(args.dump_launches, "w"), indent=1)
+
     # -------- final gather of adversarial examples + metrics (the only collective; outside the loop)
     gather_ms = None
     if world > 1:
@@ -381,6 +399,7 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="diagnostics: write per-launch conv timings + a per-kernel time table (JSON)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel eagerly instead of replaying the step / the e2e iterations from captured CUDA graphs")
     args = ap.parse_args()

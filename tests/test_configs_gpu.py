@@ -1,8 +1,8 @@
 """BASELINE.json configurations at their real sizes.
   C1  FGSM, eps = 8/255, one 256x256 pair, StyleGAN2-256 (config-f widths), style (spatial) fusion + VGG loss, batch 1:
       checked against the CPU oracle -- fp32 parity mode to north_star's 1e-3, bf16 product path to its stated tolerance.
-  C2/C3  1024x1024: size-independent properties (the oracle needs minutes per iteration there): eps-ball and [0,1] invariants,
-      monotone untargeted loss, idempotent projection, linearity of the style-gradient reduction.
+  C2/C3  1024x1024: size-independent properties at batch 2: eps-ball and [0,1] invariants, monotone untargeted loss, idempotent
+      projection, linearity of the style-gradient reduction (the oracle comparison at 1024 is tests/test_fullsize_gpu.py).
   C4  patch 161x161 on StyleGAN2-512: nothing outside the mask moves, clean-range clamp, raw-gradient and sign steps.
   C5  L2 ball at 1024 with the perceptual regulariser on the inputs: ball + [0,1] invariants, rising loss."""
 import math
@@ -30,7 +30,7 @@ def _pairs(B, size, seed):
     return mk(), mk(), mk(), mk(), g
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32-cuda-cores", "tf32", "bf16"])
 def test_c1_fgsm_256_style_fusion_vs_oracle(mode):
     from oracle.pipeline import AttackCfg as OCfg, LossCfg as OLoss, OraclePipeline, run_attack as oracle_run
     from sfattack import lib
@@ -44,12 +44,18 @@ def test_c1_fgsm_256_style_fusion_vs_oracle(mode):
     pipe = OraclePipeline(spec, GP, es, EP, vsd, FP, fusion="spatial")
     rec = []
     want = oracle_run(pipe, xa, xb, ocfg, target=(ta, tb), record=rec)
-    lib.set_activation_dtype(torch.float32 if mode == "fp32" else torch.bfloat16)
+    conv_math = {"fp32": "tf32x3", "fp32-cuda-cores": "cuda_cores", "tf32": "tf32"}.get(mode)
+    lib.set_activation_dtype(torch.bfloat16 if mode == "bf16" else torch.float32)
+    if conv_math:
+        lib.set_conv_math(conv_math)
+    plain_tf32 = mode == "tf32"
+    mode = "bf16" if mode == "bf16" else "fp32"
     try:
         eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion="spatial", batch=1, device=DEV, loss=LossCfg(1.0, 1.0))
         got = run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind="linf", steps=1, eps=eps, alpha=eps, random_start=False, targeted=True),
                          target=(ta.to(DEV), tb.to(DEV)))
     finally:
+        lib.set_conv_math("auto")
         lib.set_activation_dtype(torch.bfloat16)
     X0 = torch.cat([xa, xb])
     x_adv, x_ref = got["x_adv"].cpu(), want["x_adv"]
@@ -61,9 +67,14 @@ def test_c1_fgsm_256_style_fusion_vs_oracle(mode):
     fused_err = (got["fused_adv"].cpu() - want["fused_adv"]).abs().max().item()
     ref_err = (got["fused_ref"].cpu() - want["fused_ref"]).abs().max().item()
     loss_rel = ((got["losses"][0].cpu() - want["losses"][0]).abs() / want["losses"][0].abs()).max().item()
-    print(f"[C1 {mode}] perturbation within 1e-3: {frac_band:.4f} (outside tie band, band excludes {(~band).float().mean():.4f}); "
+    print(f"[C1 {mode}{' plain-tf32' if plain_tf32 else ''} conv={conv_math}] perturbation within 1e-3: {frac_band:.4f} (outside tie band, band excludes {(~band).float().mean():.4f}); "
           f"fused max-abs err {fused_err:.2e}; reference fusion err {ref_err:.2e}; loss rel err {loss_rel:.2e}")
-    if mode == "fp32":
+    if plain_tf32:
+        # one-pass kind::tf32 (10-bit mantissa operands) through 14 conv layers: stated tolerance 2e-3 of the image range on the
+        # fused image, >= 97 % of the perturbation within 1e-3 outside the tie band, loss within 1 %
+        scale = max(1.0, want["fused_ref"].abs().max().item())
+        assert frac_band > 0.97 and ref_err < 2e-3 * scale and fused_err < 2e-2 * scale and loss_rel < 1e-2, (frac_band, ref_err, fused_err, loss_rel)
+    elif mode == "fp32":
         # north_star: 1e-3 max-abs on images in [-1, 1]; the random-init generator's fused image spans +-scale (9.4 here), so the
         # bound on the fused image is 1e-3 of that range (measured 0.85e-3 .. 1.1e-3 absolute = 1.1e-4 of the range)
         scale = max(1.0, want["fused_ref"].abs().max().item())
@@ -77,7 +88,7 @@ def test_c1_fgsm_256_style_fusion_vs_oracle(mode):
     # identical attack outcome: targeted attack moved the fusion towards the target by the same amount
     d_ref = ((want["fused_adv"] - want["fused_ref"]) ** 2).mean().item()
     d_got = ((got["fused_adv"] - got["fused_ref"]) ** 2).mean().item()
-    assert abs(d_got - d_ref) <= (0.02 if mode == "fp32" else 0.2) * d_ref
+    assert abs(d_got - d_ref) <= (0.05 if plain_tf32 else 0.02 if mode == "fp32" else 0.2) * d_ref
 
 
 def test_c2_c3_full_size_properties_1024():

@@ -240,16 +240,21 @@ def test_other_update_rules_vs_oracle(kind):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# fp32 parity mode: the SAME kernel schedules with fp32 activation storage (sfk_set_activation_dtype(1); the conv then runs
-# the CUDA-core kernel).  This is the configuration held to north_star's tolerance: fused image and perturbation within 1e-3
-# max-abs of the oracle, identical attack outcome.
-@pytest.fixture
-def fp32_mode():
+# fp32 parity mode: the SAME kernel schedules with fp32 activation storage (sfk_set_activation_dtype(1)); the conv is the SAME
+# tcgen05 kernel with kind::tf32 MMAs over hi/lo-split operands (tests/test_tf32_gpu.py holds it to 2e-5 per launch).  This is
+# the configuration held to north_star's tolerance: fused image and perturbation within 1e-3 max-abs of the oracle, identical
+# attack outcome.
+@pytest.fixture(params=["tf32x3", "cuda_cores"])
+def fp32_mode(request):
+    """fp32 storage with the conv on the tensor cores (split tf32: three kind::tf32 passes, the default of the parity mode) and,
+    as the third opinion, on CUDA cores"""
     from sfattack import lib
     lib.set_activation_dtype(torch.float32)
+    lib.set_conv_math(request.param)
     try:
-        yield
+        yield request.param
     finally:
+        lib.set_conv_math("auto")
         lib.set_activation_dtype(torch.bfloat16)
 
 
