@@ -459,6 +459,7 @@ struct __align__(64) Igemm2Args {
   int TH, TW, TWB, tiles_h, tiles_w, n_blocks;   // TWB = box width = row pitch of the M index; TW <= TWB useful columns
   int KC, num_cblk, block_n, num_acc, num_taps, num_groups, stages, acc_stages;
   int b_per_sample, b_resident, dual_issue;
+  int ksplit;              // fp32 storage: k-blocks rotate over `ksplit` partial accumulators that the epilogue sums (see the MMA warp)
   int passes, b_samples;   // passes == 3: split-tf32 (A.hi*B.hi + A.lo*B.hi + A.hi*B.lo); the lo halves sit n_img images / b_samples weight sets further on
   int out_d2s, a_s2d, cpa, cq_log2;   // fused resampling (see sfk.h); cpa = k-blocks per row phase of the space-to-depth input
   int a_stage_bytes, b_tap_bytes, b_stage_bytes, row_bytes;
@@ -704,9 +705,16 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         if (!mbar_wait(&tmem_empty_bar[as], aph ^ 1, a.err)) break;
         if (prof) t_wa += clock64() - ta0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * m2n * a.num_acc * a.block_n);
+        // The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest (measured: the error of a split-tf32
+        // conv grows linearly with K, -1.2e-8 relative per accumulated element, tools/diag_tf32_accuracy.py), which would dominate
+        // the parity mode's error.  Under fp32 storage the k-blocks therefore rotate over `ksplit` partial accumulators, each seeing
+        // 1/ksplit of the additions; the epilogue sums them with ordinary fp32 adds.  bf16 storage: one accumulator (ksplit = 1).
+        const int ksplit = kF32 ? a.ksplit : 1;
+        const uint32_t tile_cols = static_cast<uint32_t>(m2n * a.num_acc * a.block_n);
+        const uint32_t tmem_tile = tmem_base + static_cast<uint32_t>(as * ksplit) * tile_cols;
         for (int cbx = 0; cbx < a.num_cblk * a.passes && ok; ++cbx) {
           const int cb = (a.passes == 3 && cbx >= 2 * a.num_cblk) ? cbx - a.num_cblk : (cbx % a.num_cblk);   // resident B slot: lo halves follow the hi ones
+          const uint32_t part = kF32 ? static_cast<uint32_t>(cbx % ksplit) * tile_cols : 0u;
           int t0 = 0;
           for (int g = 0; g < a.num_groups && ok; ++g, ++ks) {
             const int nt = a.groups[g].ntaps;
@@ -723,8 +731,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
               if (j < nt) {
                 AD[j] = s_adesc[a_row + j];
                 BD[j] = s_bdesc[b_row + j];
-                TC[j] = tmem_tile + static_cast<uint32_t>(s_colf[t0 + j] >> 1);
-                AF[j] = (cbx == 0 && (s_colf[t0 + j] & 1)) ? 0u : 1u;
+                TC[j] = tmem_tile + part + static_cast<uint32_t>(s_colf[t0 + j] >> 1);
+                AF[j] = (cbx < ksplit && (s_colf[t0 + j] & 1)) ? 0u : 1u;   // first k-block of each partial overwrites
               }
             }
             const long long td0 = prof ? clock64() : 0;
@@ -843,7 +851,9 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float nz = a.noise_w * nz_raw;
       const int h_w0 = h - lrow, w_0 = w - tw;   // first pixel of this warp's box (staged store)
-      uint32_t acc_col = static_cast<uint32_t>(as * m2n * a.num_acc * a.block_n);   // first TMEM column of the tile (half)
+      const uint32_t tile_cols = static_cast<uint32_t>(m2n * a.num_acc * a.block_n);
+      const int ksplit = kF32 ? a.ksplit : 1;
+      uint32_t acc_col = static_cast<uint32_t>(as * ksplit) * tile_cols;   // first TMEM column of the tile (half)
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
       auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
         constexpr int NC = decltype(nc_tag)::value;
@@ -866,6 +876,14 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                acc_col + static_cast<uint32_t>(acc * a.block_n + c0);
         if (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        if constexpr (kF32) {   // sum the partial accumulators (fp32 adds, round to nearest)
+          for (int p = 1; p < ksplit; ++p) {
+            float u[NC];
+            if (NC == 32) tmem_ld32(taddr + static_cast<uint32_t>(p) * tile_cols, u); else tmem_ld16(taddr + static_cast<uint32_t>(p) * tile_cols, u);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] += u[i];
+          }
+        }
         if (!(flags & SFK_EP_DSCALE) && (flags & (SFK_EP_NOISE | SFK_EP_BIAS))) {
           const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
 #pragma unroll
@@ -1456,8 +1474,9 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
   // weight tile (3 taps x 16 KB) then feeds 256 output rows instead of 128, which takes ~15 % off the shared-memory port
   // (TMA writes + tensor-core operand reads).  Needs both halves' accumulators double-buffered: 4 x 128 columns.
   static const int m2_env = env_int("SFK_M2", 1);
+  // (fp32 storage with a long K: the TMEM columns go to partial accumulators instead, see ksplit below)
   k.m2 = (m2_env && k.TW == 16 && !halo && !can_reside && d->block_n == 128 && d->num_acc == 1 &&
-          d->out_h >= 16 && row_bytes == 128) ? 1 : 0;
+          d->out_h >= 16 && row_bytes == 128 && !(P->f32 && d->a_c >= 512)) ? 1 : 0;
   if (k.m2) {
     k.TH = 16;
     k.tiles_h = (d->out_h + k.TH - 1) / k.TH;
@@ -1592,9 +1611,18 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
   SFK_REQUIRE(stages >= 1 && stages * stage_bytes + resident + staging + 1024 <= 220 * 1024, SFK_E_SHAPE, "igemm: tile does not fit shared memory");
   k.ts_off = stages * stage_bytes + resident;
   k.stages = stages;
-  k.acc_stages = (2 * cols <= (per_sm == 2 ? 256 : 512)) ? 2 : 1;
+  const int tmem_limit = per_sm == 2 ? 256 : 512;
+  k.acc_stages = (2 * cols <= tmem_limit) ? 2 : 1;
+  k.ksplit = 1;
+  if (P->f32) {   // partial accumulators against the truncating fp32 accumulation of the tensor core: as many as TMEM holds, up to 8
+    static const int ksplit_env = env_int("SFK_KSPLIT", 8);
+    int p = ksplit_env < 1 ? 1 : ksplit_env;
+    while (p > 1 && (p * cols > tmem_limit || p > k.num_cblk * k.passes || (p & (p - 1)))) --p;
+    k.ksplit = p;
+    k.acc_stages = (2 * p * cols <= tmem_limit) ? 2 : 1;
+  }
   k.dual_issue = (k.acc_stages == 2 && stages >= 2 * k.num_cblk * k.passes * ng) ? 1 : 0;
-  const int want = k.acc_stages * cols;
+  const int want = k.acc_stages * cols * k.ksplit;
   k.tmem_cols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
 
   for (int sp = 0; sp <= max_span; ++sp)
@@ -1734,13 +1762,13 @@ extern "C" int sfk_igemm_run(const sfk_igemm_plan* plan, sfk_stream_t stream) {
 // What the planner decided, for tests and for the launch <-> ncu-row map under profiles/:
 //   [0] two M tiles per stage  [1] halo loads  [2] resident weights  [3] depth-to-space out  [4] space-to-depth in  [5] passes
 //   [6] pipeline stages  [7] block_n  [8] compile-time variant (-1 run time)  [9] epilogue flags  [10] grid.x  [11] grid.y
-//   [12] dynamic smem bytes  [13] fp32 storage  [14] CUDA-core kernel  [15] accumulator stages
+//   [12] dynamic smem bytes  [13] fp32 storage  [14] CUDA-core kernel  [15] accumulator stages * 16 + partial accumulators
 extern "C" int sfk_igemm_plan_info(const sfk_igemm_plan* plan, int32_t* out16) {
   SFK_REQUIRE(plan != nullptr && out16 != nullptr, SFK_E_ARG, "igemm_plan_info: null");
   const IgemmPlan* P = reinterpret_cast<const IgemmPlan*>(plan);
   const Igemm2Args& k = P->k;
   const int v[16] = {k.m2, k.TWB != k.TW ? 1 : 0, k.b_resident, k.out_d2s, k.a_s2d, k.passes, k.stages, k.block_n, P->var, P->fct,
-                     static_cast<int>(P->grid.x), static_cast<int>(P->grid.y), static_cast<int>(P->smem), P->f32, P->use_ref, k.acc_stages};
+                     static_cast<int>(P->grid.x), static_cast<int>(P->grid.y), static_cast<int>(P->smem), P->f32, P->use_ref, k.acc_stages * 16 + k.ksplit};
   for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return 0;
 }

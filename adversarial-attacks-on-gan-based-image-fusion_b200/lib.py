@@ -241,6 +241,7 @@ def plan_info(desc: SfkIgemmDesc) -> dict:
     buf = (C.c_int32 * 16)()
     _chk0(load().sfk_igemm_plan_info(p.h, buf), "sfk_igemm_plan_info")
     d = dict(zip(PLAN_INFO_KEYS, list(buf)))
+    d["ksplit"], d["acc_stages"] = d["acc_stages"] % 16, d["acc_stages"] // 16
     d.update(shape=(desc.n_img, desc.out_h, desc.out_w, desc.a_c, desc.out_c), taps=desc.num_taps, num_acc=desc.num_acc)
     return d
 

@@ -115,9 +115,11 @@ int sfk_igemm_run(const sfk_igemm_plan* plan, sfk_stream_t stream);
 int sfk_igemm_destroy(sfk_igemm_plan* plan);
 /* planner decisions of a prepared launch (tests, profiling): out16 = { two M tiles per stage, halo loads, resident weights,
  * depth-to-space out, space-to-depth in, passes, stages, block_n, compile-time variant, epilogue flags, grid.x, grid.y,
- * dynamic smem bytes, fp32 storage, CUDA-core kernel, accumulator stages } */
+ * dynamic smem bytes, fp32 storage, CUDA-core kernel, accumulator stages * 16 + partial accumulators } */
 int sfk_igemm_plan_info(const sfk_igemm_plan* plan, int32_t* out16);
-/* Arithmetic of the tensor-core conv when the activation storage is fp32 (sfk_set_activation_dtype(1)):
+/* Arithmetic of the tensor-core conv when the activation storage is fp32 (sfk_set_activation_dtype(1)).  In every tensor-core
+ * mode the k-blocks rotate over up to 8 partial TMEM accumulators that the epilogue sums: the tensor core adds into its fp32
+ * accumulator with truncation, which would otherwise cost ~1.2e-8 relative per accumulated element.
  *   0 / 2  split tf32: three kind::tf32 passes over hi/lo-split operands (A.hi*B.hi + A.lo*B.hi + A.hi*B.lo), products accurate to
  *          ~2^-21 relative -- the mode held to north_star's 1e-3 tolerance;   needs desc.ws
  *   1      plain kind::tf32 (10-bit mantissa operands, fp32 accumulate)

@@ -2,9 +2,10 @@
 product path, as one pass (plain tf32) or three passes over hi/lo-split operands (split tf32, the default), against fp64
 references.  Per-kernel tolerances (max-abs error / max-abs of the reference), stated here and in DESIGN.md section 6:
 
-    split tf32 (tf32x3)   2e-5     products accurate to ~2^-21; what remains is fp32 accumulation order
-    plain tf32            3e-3     operands carry 10 mantissa bits (2^-11 relative per product)
-    CUDA cores            2e-5     fp32 FMA loops (the third opinion)
+    split tf32 (tf32x3)   2e-5     measured 0.8e-6 .. 2.0e-6: products accurate to ~2^-21, k-blocks spread over partial accumulators
+                                   (the tensor core's fp32 accumulation truncates: one accumulator costs 1.2e-8 per element of K)
+    plain tf32            3e-3     measured 5.1e-4 .. 8.2e-4: operands truncated to 10 mantissa bits
+    CUDA cores            1e-5     measured 4.4e-7 .. 1.1e-6: fp32 FMA loops (the third opinion)
 
 Every launch variant the product path uses is driven through the fp32 kernel here: resident weights + halo loads, streamed
 weights with two M tiles per stage, per-sample weights, the 4-accumulator transposed conv and its transpose, the depth-to-space
@@ -18,7 +19,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"tf32x3": 2e-5, "tf32": 3e-3, "cuda_cores": 2e-5}
+TOL = {"tf32x3": 2e-5, "tf32": 3e-3, "cuda_cores": 1e-5}
 MODES = ["tf32x3", "tf32", "cuda_cores"]
 
 
@@ -46,6 +47,7 @@ def _check(got, want, tol, what):
     want = want.double()
     scale = want.abs().max().item() + 1e-30
     err = (got.double() - want).abs().max().item()
+    print(f"  {what}: rel err {err / scale:.2e} (tol {tol:.0e})")
     assert math.isfinite(err) and err <= tol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e} > {tol:.0e})"
     return err / scale
 
