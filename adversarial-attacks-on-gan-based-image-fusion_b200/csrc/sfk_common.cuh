@@ -76,6 +76,12 @@ __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ void from_f32(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 __device__ __forceinline__ void from_f32(float* p, float v) { *p = v; }
 
+// Streaming (cp.async.bulk ring) form of sfk_act_bwd (wrgb == nullptr) / sfk_act_torgb_bwd, csrc/sfk_stream.cu.
+// Returns -1000 when the shape is outside its domain (the caller then launches the register kernel), else the launch status.
+int sfk_act_stream_launch(const void* out, const void* gin, void* gz, const float* d, const float* noise, float noise_w, const float* bias,
+                          float* gdacc, const float* wrgb, const float* s_rgb, int s_stride, const float* grgb, float* gs_rgb, int gs_stride,
+                          const float* s_in, float* gs_in, int in_stride, int gin_stride, int n, int hw, int c, cudaStream_t st);
+
 // activation storage mode of the library: 0 = bf16 (default), 1 = fp32 (parity mode; tensor-core conv unavailable)
 int sfk_act_f32();
 #define SFK_ACT_DISPATCH(CALL_BF16, CALL_F32) \

@@ -1894,6 +1894,11 @@ int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, con
                 const float* s_in, float* gs_in, int vec_stride, int n, int h, int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(out && gout && gz && d && bias && gdacc && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG, "act_bwd: bad args");
   {
+    const int rc = sfk_act_stream_launch(out, gout, gz, d, noise, noise_w, bias, gdacc, nullptr, nullptr, 0, nullptr, nullptr, 0, s_in, gs_in,
+                                         vec_stride, vec_stride, n, h * w, c, S_(st));
+    if (rc != -1000) return rc;
+  }
+  {
     auto run = [&](auto tag) {
       using T = decltype(tag);
       act_bwd_kernel<T><<<dim3(per_sample_blocks(static_cast<long>(h) * w * (c / 8), n), n), kBlock, c * sizeof(float), S_(st)>>>(
@@ -1939,6 +1944,11 @@ int sfk_act_torgb_bwd(const void* out, const void* gin, void* gz, const float* d
                       const float* s_in, float* gs_in, int n, int h, int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(out && gz && d && bias && gdacc && wrgb && sv && grgb && gs && c % 8 == 0 && (c / 8) <= kBlock && kBlock % (c / 8) == 0, SFK_E_ARG,
               "act_torgb_bwd: bad args");
+  {
+    const int rc = sfk_act_stream_launch(out, gin, gz, d, noise, noise_w, bias, gdacc, wrgb, sv, s_stride, grgb, gs, gs_stride, s_in, gs_in,
+                                         s_stride, gs_stride, n, h * w, c, S_(st));
+    if (rc != -1000) return rc;
+  }
   {
     auto run = [&](auto tag) {
       using T = decltype(tag);

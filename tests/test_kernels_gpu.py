@@ -419,11 +419,12 @@ def test_style_space_batched_matches_per_layer():
     assert torch.equal(gs, gs_ref)
 
 
-def test_act_bwd_and_torgb():
+@pytest.mark.parametrize("n,c,h", [(2, 64, 12), (2, 32, 128), (2, 128, 64), (1, 512, 32)])
+def test_act_bwd_and_torgb(n, c, h):
+    """(2,64,12) runs the register kernels; the larger shapes the cp.async.bulk ring kernels of csrc/sfk_stream.cu."""
     from oracle import stylegan2 as sg
     from sfattack import lib
     g = _gen(9)
-    n, c, h = 2, 64, 12
     z = _rb(n, c, h, h, g=g)
     dsc = torch.rand(n, c, generator=g, device=_dev()) + 0.5
     noise = torch.randn(h, h, generator=g, device=_dev())
