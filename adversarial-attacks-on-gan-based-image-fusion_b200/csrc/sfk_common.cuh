@@ -82,6 +82,9 @@ int sfk_act_stream_launch(const void* out, const void* gin, void* gz, const floa
                           float* gdacc, const float* wrgb, const float* s_rgb, int s_stride, const float* grgb, float* gs_rgb, int gs_stride,
                           const float* s_in, float* gs_in, int in_stride, int gin_stride, int n, int hw, int c, cudaStream_t st);
 
+int sfk_torgb_stream_launch(const void* x, const float* wrgb, const float* s, int s_stride, const float* bias, const float* skip, float* rgb,
+                            int n, int h, int w, int c, cudaStream_t st);
+
 // activation storage mode of the library: 0 = bf16 (default), 1 = fp32 (parity mode; tensor-core conv unavailable)
 int sfk_act_f32();
 #define SFK_ACT_DISPATCH(CALL_BF16, CALL_F32) \

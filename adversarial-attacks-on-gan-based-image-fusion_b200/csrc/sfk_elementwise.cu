@@ -1912,6 +1912,10 @@ int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, con
 int sfk_torgb_fwd(const void* x, const float* wrgb, const float* sv, int s_stride, const float* bias, const float* skip, float* rgb, int n, int h,
                   int w, int c, sfk_stream_t st) {
   SFK_REQUIRE(x && wrgb && sv && bias && rgb && c % 8 == 0, SFK_E_ARG, "torgb_fwd: bad args");
+  {
+    const int rc = sfk_torgb_stream_launch(x, wrgb, sv, s_stride, bias, skip, rgb, n, h, w, c, S_(st));
+    if (rc != -1000) return rc;
+  }
   int lp = 1;
   while (lp < 32 && lp * 16 <= c / 8) lp *= 2;   // C<=128: one thread per pixel (full 64-256 B reads, coalesced planar stores)
   {

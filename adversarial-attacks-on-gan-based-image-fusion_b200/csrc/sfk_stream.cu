@@ -227,6 +227,152 @@ __global__ void __launch_bounds__(kThreads, 2) act_stream_kernel(const __grid_co
   if (a.gs_in != nullptr) flush(rin, a.gs_in + static_cast<long>(n) * a.gin_stride);
 }
 
+// ---------------------------------------------------------------------------------------------
+// ToRGB forward, streamed: rgb[n][c][p] = bias[c] + sum_i (wrgb[c][i] s[n][i]) x[n][p][i] + upsample2(skip)[n][c][p]
+// for the two layers that carry 3/4 of its bytes (C = 32 at 1024^2, C = 64 at 512^2).
+// One consumer thread owns one pixel of a 128-pixel chunk (the chunk is one piece of an image row), so there is no cross-lane
+// reduction and a warp stores 128 contiguous bytes per colour plane.  The chunk sits in shared memory exactly as in HBM (rows of
+// C*2 bytes), so lane l walks its pixel's 16-byte vectors in the rotated order v = (j + rot(l)) mod C/8, which puts the eight
+// lanes of every LDS.128 phase on eight different bank groups; the matching weight vectors are [3][8] floats at a 112-byte pitch
+// (28 banks: eight consecutive vectors never collide).  The 12 skip taps are fetched before the wait for the chunk.
+constexpr int kTgPix = 128;                // pixels per chunk = consumer threads
+constexpr int kTgThreads = kTgPix + 32;    // + producer warp
+constexpr int kTgWPitch = 28;              // floats between the weight blocks of consecutive channel vectors
+constexpr int kTgSkipCols = 72;            // skip columns staged per chunk: [w0/2 - 4, w0/2 + 68) covers every tap of 128 fine pixels
+constexpr int kTgSkipBytes = 1792;         // 3 colours x 2 rows x 72 floats (1728 B), padded to a multiple of 128
+
+struct TorgbStreamK {
+  const __nv_bfloat16* x;
+  const float* wrgb;    // [3][C]
+  const float* s;       // + n * s_stride
+  const float* bias;    // [3]
+  const float* skip;    // [n][3][H/2][W/2] or null
+  float* rgb;           // [n][3][H][W]
+  int s_stride, H, W, C, chunks, chunk_bytes;
+};
+
+// upfirdn2d(skip, k*4, up=2, pad=(2,1)) at fine pixel (o,p): rows (i0, i0+1) x cols (j0, j0+1) with weights (a0, 1-a0) x (b0, 1-b0);
+// even o -> (o/2-1: 1/4, o/2: 3/4); odd o -> ((o-1)/2: 3/4, (o+1)/2: 1/4).  The two skip rows of a chunk ride in the ring next to
+// the activations (rows outside the image are not copied and are masked here).
+__device__ __forceinline__ float skip_from_ring(uint32_t rows /* [2][kTgSkipCols] floats of one colour */, int jl /* j0 - first staged column */,
+                                                bool vi0, bool vi1, bool vj0, bool vj1, float a0, float b0) {
+  const float t00 = (vi0 && vj0) ? lds32(rows + jl * 4) : 0.f, t01 = (vi0 && vj1) ? lds32(rows + jl * 4 + 4) : 0.f;
+  const float t10 = (vi1 && vj0) ? lds32(rows + (kTgSkipCols + jl) * 4) : 0.f, t11 = (vi1 && vj1) ? lds32(rows + (kTgSkipCols + jl) * 4 + 4) : 0.f;
+  const float b1 = 1.f - b0;
+  return a0 * (b0 * t00 + b1 * t01) + (1.f - a0) * (b0 * t10 + b1 * t11);
+}
+
+template <int VECS>   // C / 8
+__global__ void __launch_bounds__(kTgThreads, 3) torgb_stream_kernel(const __grid_constant__ TorgbStreamK a) {
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  const uint32_t ring = (s_u32(sm_raw) + 127u) & ~127u;
+  const int stage_bytes = a.chunk_bytes + kTgSkipBytes;
+  float* const sw = reinterpret_cast<float*>(sm_raw + (ring - s_u32(sm_raw)) + kStages * stage_bytes);   // [VECS] blocks of [3][8], pitch 28 floats
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y, C = VECS * 8;
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mb_init(&full_bar[i], 1);
+      mb_init(&empty_bar[i], kTgPix / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 3 * C; i += kTgThreads) {
+    const int col = i / C, c = i % C;
+    sw[(c >> 3) * kTgWPitch + col * 8 + (c & 7)] = a.wrgb[i] * a.s[static_cast<long>(n) * a.s_stride + c];
+  }
+  __syncthreads();
+  const long HW = static_cast<long>(a.H) * a.W;
+  if (warp == kTgPix / 32) {
+    if (lane == 0) {
+      int it = 0;
+      for (int ch = blockIdx.x; ch < a.chunks; ch += gridDim.x, ++it) {
+        const int st = it % kStages;
+        mb_wait(&empty_bar[st], ((it / kStages) & 1) ^ 1);
+        const uint32_t base = ring + st * stage_bytes;
+        // skip rows i0, i0+1 of this image row, columns [w0/2 - 4, w0/2 + 68) clipped to the image (16-byte granules both ends)
+        const int p0 = ch * kTgPix, h = p0 / a.W, w0 = p0 - h * a.W;
+        const int hs = a.H / 2, ws = a.W / 2;
+        const int i0 = (h & 1) ? (h - 1) / 2 : h / 2 - 1, jstart = w0 / 2 - 4;
+        const int cs = jstart < 0 ? 0 : jstart, ce = jstart + kTgSkipCols > ws ? ws : jstart + kTgSkipCols;
+        const int nrows = a.skip ? ((i0 >= 0 ? 1 : 0) + (i0 + 1 < hs ? 1 : 0)) : 0;
+        mb_expect_tx(&full_bar[st], static_cast<uint32_t>(a.chunk_bytes + 3 * nrows * (ce - cs) * 4));
+        bulk_g2s(base, a.x + (static_cast<long>(n) * HW + p0) * C, a.chunk_bytes, &full_bar[st]);
+        if (a.skip) {
+          for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 2; ++r) {
+              const int i = i0 + r;
+              if (i < 0 || i >= hs) continue;
+              bulk_g2s(base + a.chunk_bytes + ((c * 2 + r) * kTgSkipCols + (cs - jstart)) * 4,
+                       a.skip + ((static_cast<long>(n) * 3 + c) * hs + i) * ws + cs, (ce - cs) * 4, &full_bar[st]);
+            }
+        }
+      }
+    }
+    return;
+  }
+  const int rot = VECS == 4 ? (lane >> 1) : lane;
+  const uint32_t sw_u = s_u32(sw);
+  const int hs = a.H / 2, ws = a.W / 2;
+  const bool has_skip = a.skip != nullptr;
+  float* const dst = a.rgb + static_cast<long>(n) * 3 * HW;
+  const float bias0 = a.bias[0], bias1 = a.bias[1], bias2 = a.bias[2];
+  int it = 0;
+  for (int ch = blockIdx.x; ch < a.chunks; ch += gridDim.x, ++it) {
+    const int st = it % kStages;
+    const int p0 = ch * kTgPix;                 // a chunk lies inside one image row (W % 128 == 0)
+    const int h = p0 / a.W, w0 = p0 - h * a.W, w = w0 + tid;
+    const uint32_t px = ring + st * stage_bytes + tid * (VECS * 16);
+    mb_wait(&full_bar[st], (it / kStages) & 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (has_skip) {      // the skip contribution first (its shared-memory reads precede the release of the slot)
+      const int i0 = (h & 1) ? (h - 1) / 2 : h / 2 - 1, j0 = (w & 1) ? (w - 1) / 2 : w / 2 - 1;
+      const bool vi0 = i0 >= 0, vi1 = i0 + 1 < hs, vj0 = j0 >= 0, vj1 = j0 + 1 < ws;
+      const float fa = (h & 1) ? 0.75f : 0.25f, fb = (w & 1) ? 0.75f : 0.25f;
+      const int jl = j0 - (w0 / 2 - 4);
+      const uint32_t srow = ring + st * stage_bytes + a.chunk_bytes;
+      a0 = skip_from_ring(srow, jl, vi0, vi1, vj0, vj1, fa, fb);
+      a1 = skip_from_ring(srow + 2 * kTgSkipCols * 4, jl, vi0, vi1, vj0, vj1, fa, fb);
+      a2 = skip_from_ring(srow + 4 * kTgSkipCols * 4, jl, vi0, vi1, vj0, vj1, fa, fb);
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < VECS; j0 += 4) {
+      uint4 xr[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) xr[jj] = lds128(px + (((j0 + jj + rot) & (VECS - 1)) << 4));
+      if (j0 + 4 >= VECS) {          // last read of the slot
+        __syncwarp();
+        if (lane == 0) mb_arrive(&empty_bar[st]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const uint32_t wp = sw_u + ((j0 + jj + rot) & (VECS - 1)) * (kTgWPitch * 4);
+        const uint4 r0 = lds128(wp), r1 = lds128(wp + 16), q0 = lds128(wp + 32), q1 = lds128(wp + 48), b0 = lds128(wp + 64), b1 = lds128(wp + 80);
+        float xv[8];
+        unpack8(xr[jj], xv);
+        const float wr[8] = {__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r0.w),
+                             __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w)};
+        const float wg[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
+                             __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
+        const float wb[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                             __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a0 = fmaf(xv[i], wr[i], a0);
+          a1 = fmaf(xv[i], wg[i], a1);
+          a2 = fmaf(xv[i], wb[i], a2);
+        }
+      }
+    }
+    float r0 = a0 + bias0, r1 = a1 + bias1, r2 = a2 + bias2;
+    float* o = dst + p0 + tid;
+    o[0] = r0;
+    o[HW] = r1;
+    o[2 * HW] = r2;
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -272,4 +418,31 @@ int sfk_act_stream_launch(const void* out, const void* gin, void* gz, const floa
   if (wrgb != nullptr) return gin ? launch<true, true>(k, n, st) : launch<true, false>(k, n, st);
   if (gin == nullptr) return -1000;
   return launch<false, true>(k, n, st);
+}
+
+// ToRGB forward; same convention (-1000 = not handled)
+int sfk_torgb_stream_launch(const void* x, const float* wrgb, const float* s, int s_stride, const float* bias, const float* skip, float* rgb,
+                            int n, int h, int w, int c, cudaStream_t st) {
+  static const int enabled = env_int("SFK_STREAM", 1);
+  if (!enabled || sfk_act_f32()) return -1000;
+  if (c != 32 && c != 64) return -1000;
+  const long hw = static_cast<long>(h) * w;
+  if (w % kTgPix != 0 || hw * c * 2 < (1L << 20) || !sfk_aligned16(x) || (h & 1)) return -1000;
+  TorgbStreamK k;
+  k.x = static_cast<const __nv_bfloat16*>(x);
+  k.wrgb = wrgb; k.s = s; k.bias = bias; k.skip = skip; k.rgb = rgb;
+  k.s_stride = s_stride; k.H = h; k.W = w; k.C = c; k.chunks = static_cast<int>(hw / kTgPix); k.chunk_bytes = kTgPix * c * 2;
+  const size_t smem = static_cast<size_t>(kStages) * (k.chunk_bytes + kTgSkipBytes) + 128 + static_cast<size_t>(c / 8) * kTgWPitch * sizeof(float);
+  const void* fn = c == 32 ? reinterpret_cast<const void*>(&torgb_stream_kernel<4>) : reinterpret_cast<const void*>(&torgb_stream_kernel<8>);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int per_image = (3 * sfk_num_sms() + n - 1) / n;
+  if (per_image > k.chunks) per_image = k.chunks;
+  void* args[1] = {&k};
+  e = cudaLaunchKernel(fn, dim3(static_cast<unsigned>(per_image), static_cast<unsigned>(n)), dim3(kTgThreads), args, smem, st);
+  if (e != cudaSuccess) {
+    sfk_set_error(cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return sfk_check_launch("torgb_stream");
 }
