@@ -36,8 +36,11 @@ class AttackCfg:
 
 def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: AttackCfg, start_noise: Optional[torch.Tensor] = None,
                target: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, mask: Optional[torch.Tensor] = None,
-               patch0: Optional[torch.Tensor] = None, compute_final: bool = True, record: Optional[list] = None):
-    """xa, xb: (B,3,S,S) in [0,1] on the engine's device.  Returns dict(x_adv, fused_adv, fused_ref, losses, [patch])."""
+               patch0: Optional[torch.Tensor] = None, compute_final: bool = True, record: Optional[list] = None,
+               seed: Optional[int] = None):
+    """xa, xb: (B,3,S,S) in [0,1] on the engine's device.  Returns dict(x_adv, fused_adv, fused_ref, losses, [patch]).
+    Random start (interpolation.py:74-76): from `start_noise` (U(-1,1) values supplied by the caller: what the parity tests share
+    with the oracle) or, when `seed` is given, drawn on the device by sfk_attack_random_start."""
     B, dev = eng.B, eng.dev
     direction = -1.0 if cfg.targeted else 1.0
     eng.set_inputs(xa, xb)
@@ -58,6 +61,8 @@ def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: Attac
         lib.attack_update_patch(eng.x, eng.x0, patch, mask, zero_g, 0.0, direction, False, lo, hi, gscale, None, k)
     elif cfg.random_start and start_noise is not None and cfg.kind in ("linf", "l2"):
         eng.x.copy_(torch.clamp(eng.x0 + cfg.eps * start_noise.reshape(eng.x0.shape).to(dev), 0.0, 1.0))   # interpolation.py:74-76
+    elif cfg.random_start and seed is not None and cfg.kind in ("linf", "l2"):
+        lib.attack_random_start(eng.x, eng.x0, cfg.eps, seed)
     if cfg.kind == "adam":
         m = torch.zeros_like(eng.x)
         v = torch.zeros_like(eng.x)
@@ -109,3 +114,116 @@ def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: Attac
         out["patch"] = patch
     eng.check()
     return out
+
+
+def run_attack_stream(eng: AttackEngine, batches, cfg: AttackCfg, seed: int = 0, out_x=None, out_loss=None, gather_into=None):
+    """Attack a sequence of host-resident batches with the copies hidden behind the compute.
+
+    `batches`: sequence of (xa_h, xb_h) PINNED host tensors, each (B,3,S,S) fp32 in [0,1] (B = eng.B).  Returns (out_x, out_loss):
+    lists of pinned host tensors, out_x[i] (2B,3,S,S) = adversarial pairs of batch i (rows [:B] = a, [B:] = b), out_loss[i]
+    (steps,B) = the loss of every iteration.  While batch i runs on the current stream, batch i+1 is copied host->device and the
+    results of batch i-1 device->host on two side streams through double-buffered staging tensors (the per-sample attack is
+    unchanged: this is run_attack with the random start drawn on the device from seed + i).  linf / l2 only.
+    gather_into: optional DEVICE tensor (len(batches)*2B,3,S,S) that also receives every batch's adversarial pairs (the operand of
+    the final all-gather across ranks, parallel.gather_results)."""
+    assert cfg.kind in ("linf", "l2"), "run_attack_stream: linf / l2 attacks"
+    B, dev = eng.B, eng.dev
+    S = eng.S
+    nb = len(batches)
+    comp = torch.cuda.current_stream(dev)
+    st = eng.__dict__.get("_stream_state")
+    if st is None or st["steps"] != cfg.steps:
+        st = dict(h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), steps=cfg.steps,
+                  xin=[torch.empty(2 * B, 3, S, S, device=dev) for _ in range(2)],
+                  xout=[torch.empty(2 * B, 3, S, S, device=dev) for _ in range(2)],
+                  lout=[torch.empty(cfg.steps, B, device=dev) for _ in range(2)])
+        eng.__dict__["_stream_state"] = st
+    h2d, d2h = st["h2d"], st["d2h"]
+    if out_x is None:
+        out_x = [torch.empty(2 * B, 3, S, S).pin_memory() for _ in range(nb)]
+    if out_loss is None:
+        out_loss = [torch.empty(cfg.steps, B).pin_memory() for _ in range(nb)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]          # staging buffer holds batch i
+    ev_taken = [torch.cuda.Event() for _ in range(2)]       # engine has copied the staging buffer
+    ev_res = [torch.cuda.Event() for _ in range(2)]         # result staging holds batch i
+    ev_out = [torch.cuda.Event() for _ in range(2)]         # result staging has been copied to the host
+
+    def upload(i):
+        b = i % 2
+        with torch.cuda.stream(h2d):
+            if i >= 2:
+                h2d.wait_event(ev_taken[b])
+            xa_h, xb_h = batches[i]
+            st["xin"][b][:B].copy_(xa_h, non_blocking=True)
+            st["xin"][b][B:].copy_(xb_h, non_blocking=True)
+            ev_in[b].record(h2d)
+
+    h2d.wait_stream(comp)
+    upload(0)
+    for i in range(nb):
+        b = i % 2
+        comp.wait_event(ev_in[b])
+        xin = st["xin"][b]
+        eng.set_inputs(xin[:B], xin[B:])
+        ev_taken[b].record(comp)
+        if i + 1 < nb:
+            upload(i + 1)
+        o = _attack_resident(eng, cfg, seed + i)
+        if i >= 2:
+            comp.wait_event(ev_out[b])
+        st["xout"][b].copy_(eng.x)
+        st["lout"][b].copy_(o)
+        if gather_into is not None:
+            gather_into[i * 2 * B:(i + 1) * 2 * B].copy_(eng.x)
+        ev_res[b].record(comp)
+        with torch.cuda.stream(d2h):
+            d2h.wait_event(ev_res[b])
+            out_x[i].copy_(st["xout"][b], non_blocking=True)
+            out_loss[i].copy_(st["lout"][b], non_blocking=True)
+            ev_out[b].record(d2h)
+    comp.wait_stream(d2h)
+    eng.check()
+    return out_x, out_loss
+
+
+def _attack_resident(eng: AttackEngine, cfg: AttackCfg, seed: int) -> torch.Tensor:
+    """run_attack's body for inputs already placed with eng.set_inputs (untargeted linf / l2): reference fusion, device random
+    start, cfg.steps iterations (graph replay as in run_attack).  Returns the (steps, B) loss buffer (engine-cached)."""
+    B, dev, k = eng.B, eng.dev, eng.k_in
+    eng.compute_reference(None)
+    if cfg.random_start:
+        lib.attack_random_start(eng.x, eng.x0, cfg.eps, seed)
+    key = ("losses", cfg.steps)
+    losses = eng.__dict__.setdefault("_loss_bufs", {}).get(key)
+    if losses is None:
+        losses = torch.zeros(cfg.steps, B, device=dev)
+        eng.__dict__["_loss_bufs"][key] = losses
+    if cfg.kind == "l2":
+        norms = eng.__dict__.setdefault("_l2_norms", torch.zeros(2 * B, device=dev))
+        dn = eng.__dict__.setdefault("_l2_dn", torch.zeros(2 * B, device=dev))
+
+    def iteration():
+        _, g = eng.forward_backward()
+        if cfg.kind == "linf":
+            lib.attack_update_linf(eng.x, eng.x0, g, cfg.alpha, cfg.eps, 1.0, 0.0, 1.0, eng.stats, k)
+        else:
+            norms.zero_()
+            dn.zero_()
+            for ph in range(3):
+                lib.attack_update_l2(eng.x, eng.x0, g, norms, dn, cfg.alpha, cfg.eps, 1.0, 0.0, 1.0, ph, k)
+
+    cache = eng.__dict__.setdefault("_iter_graphs", {})
+    gkey = (cfg.kind, float(cfg.alpha), float(cfg.eps), 1.0)
+    graph = cache.get(gkey) if cfg.graph else None
+    for it in range(cfg.steps):
+        if cfg.graph and (it >= 1 or graph is not None):
+            if graph is None:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    iteration()
+                cache[gkey] = graph
+            graph.replay()
+        else:
+            iteration()
+        losses[it].copy_(eng.loss)
+    return losses

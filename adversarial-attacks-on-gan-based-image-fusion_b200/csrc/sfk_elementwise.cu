@@ -1440,6 +1440,29 @@ __global__ void update_linf_kernel(float* __restrict__ x, const float* __restric
   block_add(dsum, stats ? stats + n : nullptr);
 }
 
+// PGD random start on the device (code/attack/interpolation.py:74-76): x = clamp(x0 + eps * U(-1,1), lo, hi) with a counter-based
+// generator (one 64-bit SplitMix finaliser per float4: a pure function of (seed, element index), so the result does not depend on
+// the grid, the rank layout or the replay count)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void random_start_kernel(float4* __restrict__ x, const float4* __restrict__ x0, float eps, float lo, float hi, uint64_t seed, long n4) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const uint64_t a = splitmix64(seed ^ (static_cast<uint64_t>(i) * 2ull)), b = splitmix64(seed ^ (static_cast<uint64_t>(i) * 2ull + 1ull));
+    const float sc = eps * (2.0f / 16777216.0f);       // 24-bit mantissa uniforms in [0,1) -> [-eps, eps)
+    const float4 c = __ldg(x0 + i);
+    float4 v;
+    v.x = fminf(fmaxf(c.x + (static_cast<float>(static_cast<uint32_t>(a) >> 8) * sc - eps), lo), hi);
+    v.y = fminf(fmaxf(c.y + (static_cast<float>(static_cast<uint32_t>(a >> 32) >> 8) * sc - eps), lo), hi);
+    v.z = fminf(fmaxf(c.z + (static_cast<float>(static_cast<uint32_t>(b) >> 8) * sc - eps), lo), hi);
+    v.w = fminf(fmaxf(c.w + (static_cast<float>(static_cast<uint32_t>(b >> 32) >> 8) * sc - eps), lo), hi);
+    x[i] = v;
+  }
+}
+
 __global__ void update_patch_kernel(float* __restrict__ x, const float* __restrict__ x0, float* __restrict__ patch, const float* __restrict__ mask,
                                     const float* __restrict__ gpool, float lr, float dir, int use_sign, const float* __restrict__ lo,
                                     const float* __restrict__ hi, float gscale, float* __restrict__ stats, int S, int k) {
@@ -2035,6 +2058,13 @@ int sfk_attack_update_linf(float* x, const float* x0, const float* gpool, float 
   SFK_REQUIRE(x && x0 && gpool && size % k == 0 && size % 4 == 0, SFK_E_ARG, "attack_update_linf: bad args");
   update_linf_kernel<<<dim3(per_sample_blocks(3L * size * size / 4, n), n), kBlock, 0, S_(st)>>>(x, x0, gpool, alpha, eps, dir, lo, hi, stats, size, k);
   return sfk_check_launch("attack_update_linf");
+}
+
+int sfk_attack_random_start(float* x, const float* x0, float eps, float lo, float hi, unsigned long long seed, long count, sfk_stream_t st) {
+  SFK_REQUIRE(x && x0 && count > 0 && count % 4 == 0 && sfk_aligned16(x) && sfk_aligned16(x0), SFK_E_ARG, "attack_random_start: bad args");
+  random_start_kernel<<<grid_for(count / 4), kBlock, 0, S_(st)>>>(reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(x0), eps, lo, hi,
+                                                                 static_cast<uint64_t>(seed), count / 4);
+  return sfk_check_launch("attack_random_start");
 }
 
 int sfk_attack_update_patch(float* x, const float* x0, float* patch, const float* mask, const float* gpool, float lr, float dir, int use_sign,

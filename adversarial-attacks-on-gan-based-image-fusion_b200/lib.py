@@ -55,7 +55,7 @@ EXPORTS = [
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_demod_fwd_batched", "sfk_modulate_weights_batched", "sfk_demod_bwd_batched", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
-    "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_update_patch",
+    "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_random_start", "sfk_attack_update_patch",
     "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample", "sfk_patch_grad_reduce", "sfk_patch_apply_shared",
     "sfk_ssim_gray7",
 ]
@@ -520,6 +520,13 @@ def attack_update_linf(x, x0, gpool, alpha, eps, direction, lo, hi, stats, k):
     _check_update_args(x, gpool, k, x0=x0)
     _chk(load().sfk_attack_update_linf(_p(x), _p(x0), _p(gpool), _f(alpha), _f(eps), _f(direction), _f(lo), _f(hi), _p(stats), n, s, k,
                                        _stream()), "attack_update_linf")
+
+
+def attack_random_start(x, x0, eps, seed, lo=0.0, hi=1.0):
+    """x <- clamp(x0 + eps*U(-1,1), lo, hi) on the device (interpolation.py:74-76); element i depends on (seed, i) only."""
+    assert x.shape == x0.shape and x.is_contiguous() and x0.is_contiguous() and x.dtype == torch.float32
+    _chk(load().sfk_attack_random_start(_p(x), _p(x0), _f(eps), _f(lo), _f(hi), C.c_ulonglong(int(seed) & (2 ** 64 - 1)), C.c_long(x.numel()),
+                                        _stream()), "attack_random_start")
 
 
 def _check_update_args(x, gpool, k, **same_shape):

@@ -5,11 +5,14 @@
   python bench.py --impl reference [--steps K] [--warmup W]      the CPU oracle port of the same step (rank 0 only)
 
 A "step" is ONE PGD iteration (encoder -> fusion -> StyleGAN2 synthesis -> VGG+pixel loss -> backward ->
-fused sign/projection/clamp update) over this GPU's batch of independent image pairs.  Workload at every N:
-BASELINE.json configs[1] -- PGD L-inf (eps 8/255, alpha 2/255, random start), StyleGAN2-1024 (config-f,
-random-init), arithmetic (mean W+) fusion, 8 pairs per GPU, bf16 activations / fp32 accumulate.  Weak scaling:
-pairs are independent, each rank owns 8, no collective inside the loop; one NCCL all-gather of the adversarial
-examples after the timed region.
+fused sign/projection/clamp update) over this GPU's shard of independent image pairs.
+  N = 1: BASELINE.json configs[1] -- PGD L-inf (eps 8/255, alpha 2/255, random start), StyleGAN2-1024 (config-f, random-init),
+         arithmetic (mean W+) fusion, 8 pairs resident, bf16 activations / fp32 accumulate.
+  N > 1: BASELINE.json configs[2] -- the same attack on spatial (StyleSpace gate) fusion, global batch 64 sharded contiguously over
+         the ranks (64/N pairs per GPU, attacked as resident batches of 8); strong scaling, with the weak-scaled number (8 pairs per
+         GPU) in `weak_scaled`.  Pairs are independent: no collective inside the loop; one NCCL all-gather of the adversarial examples
+         after it (inside the end-to-end region).
+`value` is device-timed with the shard resident in HBM; `e2e` goes through attack_loop.run_attack_stream from pinned host buffers.
 """
 from __future__ import annotations
 
@@ -149,12 +152,14 @@ def measured_peaks() -> dict:
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_iteration_rate(size: int, iters: int, warm: int = 1):
+def cpu_oracle_iteration_rate(size: int, iters: int, warm: int = 1, fusion: str = "arithmetic"):
     """The oracle port (oracle/pipeline.py) on the host cores: PGD iterations on ONE pair of the same workload."""
     from oracle.pipeline import LossCfg as OLoss, OraclePipeline, linf_step
     torch.set_num_threads(os.cpu_count() or 1)
     spec, GP, es, EP, vsd = build_models(size)
-    pipe = OraclePipeline(spec, GP, es, EP, vsd, None, fusion="arithmetic")
+    from sfattack.params import make_fusion_params
+    FP = make_fusion_params(spec.s_dim) if fusion == "spatial" else None
+    pipe = OraclePipeline(spec, GP, es, EP, vsd, FP, fusion=fusion)
     xa, xb = synthetic_pairs(1, size)
     nz = start_noise(1, size)
     with torch.no_grad():
@@ -171,14 +176,25 @@ def cpu_oracle_iteration_rate(size: int, iters: int, warm: int = 1):
     return len(times) / sum(times), times
 
 
+GLOBAL_PAIRS_C3 = 64   # BASELINE.json configs[2]: batch 64 sharded across 2/4/8 GPUs
+
+
 def workload_config(steps, size, pairs, world):
-    """the `config` both arms print: the same workload, whoever executes it"""
+    """the `config` both arms print: the same workload, whoever executes it.  N = 1: BASELINE.json configs[1]; N > 1: configs[2]."""
+    loss = "pixel+VGG(conv1_1,conv1_2,pool2,conv4_2) loss at 256x256, encoder stand-in on the gradient path"
+    l2 = "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"
+    if world == 1:
+        return {"workload": f"PGD-{steps} Linf eps=8/255 alpha=2/255 random-start, StyleGAN2-{size} config-f random-init, "
+                            f"arithmetic (mean W+) fusion of pairs, {loss}; BASELINE.json configs[1]",
+                "pairs_per_gpu": pairs, "global_pairs": pairs, "image_size": size, "attack": "linf-pgd", "fusion": "arithmetic",
+                "parallelism": "dp1 (independent pairs, no in-loop collective)", "l2_policy": l2}
+    per = GLOBAL_PAIRS_C3 // world
     return {"workload": f"PGD-{steps} Linf eps=8/255 alpha=2/255 random-start, StyleGAN2-{size} config-f random-init, "
-                        f"arithmetic (mean W+) fusion of pairs, pixel+VGG(conv1_1,conv1_2,pool2,conv4_2) loss at 256x256, "
-                        f"encoder stand-in on the gradient path; BASELINE.json configs[1]",
-            "pairs_per_gpu": pairs, "global_pairs": pairs * world, "image_size": size, "attack": "linf-pgd",
-            "parallelism": f"dp{world} (independent pairs, no in-loop collective)",
-            "l2_policy": "working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+                        f"spatial (StyleSpace gate) fusion of pairs, {loss}; BASELINE.json configs[2]: global batch {GLOBAL_PAIRS_C3} "
+                        f"sharded over {world} GPUs ({per} pairs per GPU, attacked in resident batches of {pairs})",
+            "pairs_per_gpu": per, "global_pairs": GLOBAL_PAIRS_C3, "image_size": size, "attack": "linf-pgd", "fusion": "spatial",
+            "parallelism": f"dp{world} (independent pairs sharded contiguously, no in-loop collective; one NCCL all-gather of the "
+                           f"adversarial examples after the loop, inside the e2e region)", "l2_policy": l2}
 
 
 def run_reference(args):
@@ -186,13 +202,17 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    rate, times = cpu_oracle_iteration_rate(SIZE, args.steps, args.warmup)
+    world = max(1, args.gpus)
+    fusion = "arithmetic" if world == 1 else "spatial"
+    rate, times = cpu_oracle_iteration_rate(SIZE, args.steps, args.warmup, fusion=fusion)
     cores = os.cpu_count() or 1
-    sample = f"{args.steps} PGD iterations on 1 of the {PAIRS_PER_GPU} pairs at {SIZE}x{SIZE} (fp32 PyTorch CPU oracle port, params frozen)"
+    sample = (f"{args.steps} PGD iterations on 1 pair of the workload at {SIZE}x{SIZE}, {fusion} fusion "
+              f"(fp32 PyTorch CPU oracle port, params frozen)")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.steps, SIZE, PAIRS_PER_GPU, max(1, args.gpus)),
+            "config": workload_config(args.steps, SIZE, PAIRS_PER_GPU, world),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -203,8 +223,9 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from sfattack import lib
-    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.attack_loop import AttackCfg, _attack_resident, run_attack_stream
     from sfattack.engine import AttackEngine, LossCfg
+    from sfattack.params import make_fusion_params
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -216,13 +237,22 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
     B = args.pairs
-    spec, GP, es, EP, vsd = build_models(args.size)
-    eng = AttackEngine(spec, GP, es, EP, vsd, None, fusion="arithmetic", batch=B, device=str(dev), loss=LossCfg(1.0, 1.0))
-    # this rank's shard of the (weak-scaled) pair range, in pinned host memory
-    xa_h, xb_h = synthetic_pairs(B, args.size, first_index=rank * B)
-    nz_h = start_noise(B, args.size, first_index=rank * B)
-    xa_h, xb_h, nz_h = xa_h.pin_memory(), xb_h.pin_memory(), nz_h.pin_memory()
-    xa, xb, nz = xa_h.to(dev, non_blocking=True), xb_h.to(dev, non_blocking=True), nz_h.to(dev, non_blocking=True)
+    S = args.size
+    spec, GP, es, EP, vsd = build_models(S)
+    # N = 1: configs[1] (arithmetic fusion, one resident batch of 8 pairs).  N > 1: configs[2] (spatial fusion, global batch 64
+    # sharded contiguously: 64/N pairs per rank, attacked as 64/(N*8) resident batches of 8 pairs)
+    fusion = "arithmetic" if world == 1 else "spatial"
+    n_local = B if world == 1 else max(B, GLOBAL_PAIRS_C3 // world)
+    n_batches = n_local // B
+    FP = make_fusion_params(spec.s_dim) if fusion == "spatial" else None
+    eng = AttackEngine(spec, GP, es, EP, vsd, FP, fusion=fusion, batch=B, device=str(dev), loss=LossCfg(1.0, 1.0))
+    first = rank * n_local
+    host = []
+    for b in range(n_batches):       # this rank's shard of the pair range, in pinned host memory
+        xa_h, xb_h = synthetic_pairs(B, S, first_index=first + b * B)
+        host.append((xa_h.pin_memory(), xb_h.pin_memory()))
+    resident = [(xa_h.to(dev, non_blocking=True), xb_h.to(dev, non_blocking=True)) for xa_h, xb_h in host]
+    cfg = AttackCfg(kind="linf", steps=args.steps, eps=EPS, alpha=ALPHA, random_start=True, graph=args.graph)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -230,11 +260,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # -------- device-resident timing: inputs already in HBM, K PGD iterations
-    eng.set_inputs(xa, xb)
-    eng.compute_reference()
-    eng.x.copy_(torch.clamp(eng.x0 + EPS * nz.reshape(eng.x0.shape), 0.0, 1.0))
+    # -------- device-resident timing: every pair of the shard already in HBM; K PGD iterations on each resident batch
     k = eng.k_in
+    eng.set_inputs(*resident[0])
+    eng.compute_reference()
+    lib.attack_random_start(eng.x, eng.x0, EPS, 4321 + first)
 
     def step():
         _, g = eng.forward_backward()
@@ -249,33 +279,49 @@ def run_ours(args):
     step_graph = None
     if os.environ.get("SFK_NCU_RANGE") == "1":
         args.graph = False                                # profile plain launches
+        cfg.graph = False
+    lib.LAUNCHES = 0
     if args.graph:                                        # same launches, recorded once (after the warm-up ran them eagerly)
-        lib.LAUNCHES = 0
         step_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(step_graph, capture_error_mode="thread_local"):
             step()
-        launches_per_step = lib.LAUNCHES
         step_graph.replay()                               # one untimed replay: the GPU is busy again when the clock window opens
         torch.cuda.synchronize(dev)
-    barrier()
-    sampler.mark_begin()
-    lib.LAUNCHES = 0
-    profiled = os.environ.get("SFK_NCU_RANGE") == "1"     # ncu --profile-from-start off: capture only the timed steps
-    if profiled:
-        torch.cuda.profiler.start()
-    ev0.record()
-    for _ in range(args.steps):
+    else:
+        step()
+        torch.cuda.synchronize(dev)
+    launches_per_step = lib.LAUNCHES
+
+    def run_step():
         if step_graph is not None:
             step_graph.replay()
         else:
             step()
+
+    barrier()
+    sampler.mark_begin()
+    profiled = os.environ.get("SFK_NCU_RANGE") == "1"     # ncu --profile-from-start off: capture only the timed steps
+    if profiled:
+        torch.cuda.profiler.start()
+    lib.LAUNCHES = 0
+    ev0.record()
+    if n_batches == 1:
+        for _ in range(args.steps):
+            run_step()
+    else:
+        for xa_d, xb_d in resident:                       # per resident batch: place it, reference fusion, random start, K iterations
+            eng.set_inputs(xa_d, xb_d)
+            eng.compute_reference()
+            lib.attack_random_start(eng.x, eng.x0, EPS, 4321 + first)
+            for _ in range(args.steps):
+                run_step()
     ev1.record()
     if profiled:
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
     barrier()
     sampler.mark_end()
-    launches = lib.LAUNCHES if step_graph is None else launches_per_step * args.steps
+    launches = lib.LAUNCHES + (launches_per_step * args.steps * n_batches if step_graph is not None else 0)
     clocks = sampler.stop()
     eng.check()
     ms = ev0.elapsed_time(ev1)
@@ -283,30 +329,43 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = args.steps * B * world / (ms * 1e-3)
+    value = args.steps * n_local * world / (ms * 1e-3)
+    step_ms = ms / args.steps                             # one PGD iteration over the rank's whole shard
+    weak = None
+    if world > 1:       # beside the sharded configs[2] number: the weak-scaled one (one resident batch of B pairs per GPU, K iterations)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(args.steps):
+            run_step()
+        w1.record()
+        barrier()
+        tw = torch.tensor([w0.elapsed_time(w1)], device=dev)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        weak = {"value": args.steps * B * world / (float(tw.item()) * 1e-3), "unit": UNIT, "pairs_per_gpu": B,
+                "ms_per_step": float(tw.item()) / args.steps, "scaling": "weak"}
 
-    # -------- end to end through the public call with HOST buffers: H2D pairs, PGD-K, D2H adversarial examples + losses
-    cfg = AttackCfg(kind="linf", steps=args.steps, eps=EPS, alpha=ALPHA, random_start=True, graph=args.graph)
-    out_h = torch.empty(2 * B, 3, args.size, args.size).pin_memory()
-    loss_h = torch.empty(args.steps, B).pin_memory()
-    e2e_calls = max(1, args.e2e_calls)
+    # -------- end to end through the public call with HOST buffers (attack_loop.run_attack_stream): per resident batch H2D of the
+    # pairs from pinned memory, reference fusion, device random start, PGD-K, D2H of adversarial examples + per-iteration losses;
+    # the copies of neighbouring batches overlap the compute on side streams.  N > 1: + the final NCCL all-gather.
+    e2e_rounds = max(1, args.e2e_calls // n_batches) if n_batches > 1 else 1
+    e2e_batches = host * e2e_rounds if n_batches > 1 else host * max(1, args.e2e_calls)
+    out_x = [torch.empty(2 * B, 3, S, S).pin_memory() for _ in range(len(e2e_batches))]
+    out_l = [torch.empty(args.steps, B).pin_memory() for _ in range(len(e2e_batches))]
+    x_local = torch.empty(len(e2e_batches) * 2 * B, 3, S, S, device=dev) if world > 1 else None
+    x_all = torch.empty(world * len(e2e_batches) * 2 * B, 3, S, S, device=dev) if world > 1 else None
 
     def e2e_call():
-        xa_d = xa_h.to(dev, non_blocking=True)
-        xb_d = xb_h.to(dev, non_blocking=True)
-        nz_d = nz_h.to(dev, non_blocking=True)
-        o = run_attack(eng, xa_d, xb_d, cfg, start_noise=nz_d, compute_final=False)
-        out_h.copy_(o["x_adv"], non_blocking=True)
-        loss_h.copy_(o["losses"], non_blocking=True)
+        run_attack_stream(eng, e2e_batches, cfg, seed=4321 + first, out_x=out_x, out_loss=out_l, gather_into=x_local)
+        if world > 1:                                     # the only collective: adversarial examples of every rank, after the loop
+            dist.all_gather_into_tensor(x_all, x_local)
         torch.cuda.synchronize(dev)
 
-    e2e_call()  # warm
+    e2e_call()  # warm (allocates the staging buffers, captures nothing new)
     barrier()
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(e2e_calls):
-        e2e_call()
+    e2e_call()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -314,9 +373,10 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e_value = e2e_calls * args.steps * B * world / (e2e_ms * 1e-3)
-    h2d = (xa_h.numel() + xb_h.numel() + nz_h.numel()) * 4 / args.steps
-    d2h = (out_h.numel() + loss_h.numel()) * 4 / args.steps
+    e2e_value = len(e2e_batches) * B * args.steps * world / (e2e_ms * 1e-3)
+    steps_total = len(e2e_batches) * args.steps / max(1, n_batches if n_batches > 1 else 1)
+    h2d = sum(a.numel() + b.numel() for a, b in e2e_batches) * 4 / steps_total
+    d2h = (sum(o.numel() for o in out_x) + sum(o.numel() for o in out_l)) * 4 / steps_total
 
     # -------- roofline of the dominant kernel (the tcgen05 implicit-GEMM conv): per-launch CUDA-event timing of one step
     peaks = measured_peaks()
@@ -324,16 +384,16 @@ def run_ours(args):
     tc_flops, tc_ms, n_tc = prof["flops"], prof["ms"], prof["launches"]
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     fl = flops_per_iter_image(spec, es)
-    step_ms = ms / args.steps
+    batch_step_ms = step_ms / n_batches                   # one PGD iteration on one resident batch of B pairs
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "igemm_traffic_r1.json")
-    if os.path.exists(tp) and args.size == SIZE and B == PAIRS_PER_GPU:
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # ncu --set full, dram read+write per launch (profiles/igemm_full_r1.md)
+    tp = os.path.join(ROOT, "profiles", "igemm_traffic_r2.json")
+    if os.path.exists(tp) and S == SIZE and B == PAIRS_PER_GPU:
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # ncu --set full, dram read+write per launch (profiles/igemm_full_r2.md)
     roofline = {"bound": "tensor", "kernel": "igemm_tc2_kernel", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peaks["source"] + " (sustained bf16)",
-                "launches_per_step": n_tc, "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / step_ms if step_ms else None,
+                "launches_per_step": n_tc, "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / batch_step_ms if batch_step_ms else None,
                 "algorithmic_gflop_per_iter_image": fl["attack"] / 1e9,
-                "step_frac_of_roofline": (fl["attack"] * B / (step_ms * 1e-3)) / (peaks["bf16_tflops"] * 1e12)}
+                "step_frac_of_roofline": (fl["attack"] * B / (batch_step_ms * 1e-3)) / (peaks["bf16_tflops"] * 1e12)}
 
     # -------- optional diagnostics (never part of a reported number): per-launch conv timings with the planner's decisions, and a
     # per-kernel time table of one eager step from torch's profiler
@@ -350,38 +410,30 @@ def run_ours(args):
             step()
             torch.cuda.synchronize(dev)
         table = sorted(((ev.key, ev.count, ev.device_time_total) for ev in tp_.key_averages()), key=lambda r: -r[2])
-        json.dump(dict(step_ms=step_ms, conv_launches=rows, plans=infos, kernel_table=[dict(name=n_[:120], count=c_, us=u_) for n_, c_, u_ in table]),
+        json.dump(dict(step_ms=batch_step_ms, conv_launches=rows, plans=infos, kernel_table=[dict(name=n_[:120], count=c_, us=u_) for n_, c_, u_ in table]),
                   open(args.dump_launches, "w"), indent=1)
-
-    # -------- final gather of adversarial examples + metrics (the only collective; outside the loop)
-    gather_ms = None
-    if world > 1:
-        x_all = torch.empty(world * 2 * B, 3, args.size, args.size, device=dev)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather_into_tensor(x_all, eng.x)
-        g1.record()
-        torch.cuda.synchronize(dev)
-        gather_ms = g0.elapsed_time(g1)
 
     if rank == 0:
         cpu = None
         if world > 1:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only (rank 0 of the 1-GPU run)"}
         elif not args.no_cpu_baseline:
-            rate, times = cpu_oracle_iteration_rate(args.size, args.cpu_iters, 1)
+            rate, times = cpu_oracle_iteration_rate(S, args.cpu_iters, 1)
             cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"{args.cpu_iters} PGD iteration(s) on 1 of the {B} pairs at {args.size}x{args.size} (oracle/pipeline.py, fp32, "
+                   "sample": f"{args.cpu_iters} PGD iteration(s) on 1 of the {B} pairs at {S}x{S} (oracle/pipeline.py, fp32, "
                              f"{sum(times):.1f}s)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic",
-                "config": workload_config(args.steps, args.size, B, world),
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args.steps, S, B, world),
                 "clocks": clocks, "gpu_launches": launches, "cuda_graph": bool(args.graph),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "what": f"{e2e_calls} call(s) of attack_loop.run_attack from pinned host buffers: H2D pairs+start noise, reference "
-                                f"fusion, PGD-{args.steps}, D2H adversarial examples + per-iteration losses"},
-                "roofline": roofline, "cpu_baseline": cpu, "final_gather_ms": gather_ms,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms": e2e_ms,
+                        "what": f"attack_loop.run_attack_stream over {len(e2e_batches)} batch(es) of {B} pairs from pinned host buffers: "
+                                f"H2D pairs, reference fusion, device random start, PGD-{args.steps}, D2H adversarial examples + per-iteration "
+                                f"losses (copies of neighbouring batches overlap the compute)"
+                                + (", then the NCCL all-gather of all adversarial examples" if world > 1 else "")},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "per_gpu_iter_img_per_s": value / world, "weak_scaled": weak,
                 "encoder_gflop_per_iter_image": 2 * fl["encoder_fwd_pair"] / 1e9}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -396,7 +448,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
-    ap.add_argument("--e2e-calls", type=int, default=2)
+    ap.add_argument("--e2e-calls", type=int, default=4, help="resident batches in the timed end-to-end region (N = 1)")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-launches", default=None, help="diagnostics: write per-launch conv timings + a per-kernel time table (JSON)")

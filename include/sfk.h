@@ -257,6 +257,9 @@ int sfk_nhwc_bf16_to_nchw(const void* x, float* y, int n, int c, int h, int w, s
  * stats[n] += sum |x_new - x0| (a cheap on-device progress metric reduced with warp shuffles). */
 int sfk_attack_update_linf(float* x, const float* x0, const float* gpool, float alpha, float eps, float dir,
                            float lo, float hi, float* stats, int n, int size, int k, sfk_stream_t st);
+/* PGD random start (interpolation.py:74-76): x = clamp(x0 + eps*U(-1,1), lo, hi), counter-based generator: element i of the
+ * flattened tensor depends on (seed, i) only.  count % 4 == 0. */
+int sfk_attack_random_start(float* x, const float* x0, float eps, float lo, float hi, unsigned long long seed, long count, sfk_stream_t st);
 int sfk_attack_update_patch(float* x, const float* x0, float* patch, const float* mask, const float* gpool,
                             float lr, float dir, int use_sign, const float* lo, const float* hi, float gscale,
                             float* stats, int n, int size, int k, sfk_stream_t st);

@@ -1,0 +1,85 @@
+"""The host-buffer pipeline (attack_loop.run_attack_stream) and the device random start it uses, against the resident-input path
+and the oracle's update rule.  The per-sample arithmetic is the same kernels in both paths, so results must agree up to the
+ordering noise of the floating-point atomics (a sign flip moves a pixel by 2*alpha; such pixels are counted, not tolerated)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _small_setup(size=32, B=2, seed=0):
+    from sfattack.params import EncSpec, gen_spec, make_encoder_params, make_fusion_params, make_generator_params, make_vgg_state_dict
+    spec = gen_spec(size, style_dim=64, n_mlp=2, channels={4: 64, 8: 64, 16: 32, 32: 32, 64: 16})
+    GP = make_generator_params(spec, seed=seed)
+    es = EncSpec(n_latent=spec.n_latent, style_dim=64, widths=(16, 32, 64), in_res=size)
+    EP = make_encoder_params(es, seed=seed + 1)
+    vsd = make_vgg_state_dict(seed + 2, width_div=4)
+    FP = make_fusion_params(spec.s_dim, seed + 3)
+    return spec, GP, es, EP, vsd, FP, None, None
+
+
+def test_random_start_kernel_properties():
+    """interpolation.py:74-76: x = clamp(x0 + U(-eps, eps), 0, 1); element i must depend on (seed, i) only."""
+    from sfattack import lib
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(4, 3, 64, 64, generator=g).to(DEV)
+    eps = 8 / 255
+    a, b, c = torch.empty_like(x0), torch.empty_like(x0), torch.empty_like(x0)
+    lib.attack_random_start(a, x0, eps, 11)
+    lib.attack_random_start(b, x0, eps, 11)
+    lib.attack_random_start(c, x0, eps, 12)
+    assert torch.equal(a, b), "same seed must reproduce bit for bit"
+    assert not torch.equal(a, c)
+    d = a - x0
+    assert float(d.abs().max()) <= eps + 1e-7 and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    inner = (x0 > eps) & (x0 < 1 - eps)                      # where the clamp is inactive the offset is uniform on [-eps, eps)
+    u = (d[inner] / eps).double()
+    n = u.numel()
+    assert abs(float(u.mean())) < 4 / (3 * n) ** 0.5 + 1e-3     # mean 0, var 1/3
+    assert abs(float((u * u).mean()) - 1 / 3) < 0.02
+    hist = torch.histc(u.float(), bins=16, min=-1, max=1) / n
+    assert float((hist - 1 / 16).abs().max()) < 0.01
+    # a prefix of the tensor is the same stream: element i depends on (seed, i), not on the launch size
+    e = torch.empty(1, 3, 64, 64, device=DEV)
+    lib.attack_random_start(e, x0[:1].contiguous(), eps, 11)
+    assert torch.equal(e, a[:1])
+    # lag-1 correlation of neighbouring elements
+    v = u[: n // 2 * 2].view(-1, 2)
+    assert abs(float((v[:, 0] * v[:, 1]).mean())) < 0.01
+
+
+@pytest.mark.parametrize("kind", ["linf", "l2"])
+def test_run_attack_stream_matches_resident_path(kind):
+    from sfattack.attack_loop import AttackCfg, run_attack, run_attack_stream
+    from sfattack.engine import AttackEngine, LossCfg
+    size, B, nb = 32, 2, 3
+    spec, GP, es, EP, vsd, FP, _, _ = _small_setup(size=size, B=B)
+    eng = AttackEngine(spec, GP, es, EP, vsd, None, batch=B, device=DEV, loss=LossCfg(1.0, 1.0), vgg_res=size, vgg_width_div=4)
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.rand(B, 3, size, size, generator=g).pin_memory(), torch.rand(B, 3, size, size, generator=g).pin_memory()) for _ in range(nb)]
+    eps = 8 / 255 if kind == "linf" else 0.5
+    cfg = AttackCfg(kind=kind, steps=4, eps=eps, alpha=eps / 4, random_start=True, graph=False)
+    out_x, out_l = run_attack_stream(eng, batches, cfg, seed=100)
+    torch.cuda.synchronize()
+    gather = torch.empty(nb * 2 * B, 3, size, size, device=DEV)
+    cfg_g = AttackCfg(kind=kind, steps=4, eps=eps, alpha=eps / 4, random_start=True, graph=True)
+    out_x2, out_l2 = run_attack_stream(eng, batches, cfg_g, seed=100, gather_into=gather)      # graph replay + second use of the staging
+    torch.cuda.synchronize()
+    for i, (xa, xb) in enumerate(batches):
+        want = run_attack(eng, xa.to(DEV), xb.to(DEV), cfg, seed=100 + i, compute_final=False)
+        x0 = torch.cat([xa, xb]).to(DEV)
+        for got_x, got_l in ((out_x[i], out_l[i]), (out_x2[i], out_l2[i])):
+            gx = got_x.to(DEV)
+            assert float(gx.min()) >= 0 and float(gx.max()) <= 1
+            if kind == "linf":
+                assert float((gx - x0).abs().max()) <= eps + 1e-6
+            else:
+                assert float((gx - x0).flatten(1).norm(dim=1).max()) <= eps * (1 + 1e-4)
+            same = float(((gx - want["x_adv"]).abs() < 1e-6).float().mean())
+            assert same > 0.98, f"batch {i}: only {same:.4f} of the pixels agree with the resident path"
+            assert torch.allclose(got_l.to(DEV), want["losses"], rtol=2e-2, atol=1e-7), (got_l, want["losses"])
+        assert torch.equal(gather[i * 2 * B:(i + 1) * 2 * B].cpu(), out_x2[i])
+    # distinct batches really were attacked (not one batch three times)
+    assert not torch.equal(out_x[0], out_x[1])
