@@ -77,8 +77,12 @@ def test_run_attack_stream_matches_resident_path(kind):
                 assert float((gx - x0).abs().max()) <= eps + 1e-6
             else:
                 assert float((gx - x0).flatten(1).norm(dim=1).max()) <= eps * (1 + 1e-4)
-            same = float(((gx - want["x_adv"]).abs() < 1e-6).float().mean())
-            assert same > 0.98, f"batch {i}: only {same:.4f} of the pixels agree with the resident path"
+            if kind == "linf":       # discontinuous update: identical except where atomics-order noise flips a gradient sign
+                same = float(((gx - want["x_adv"]).abs() < 1e-6).float().mean())
+                assert same > 0.98, f"batch {i}: only {same:.4f} of the pixels agree with the resident path"
+            else:                    # continuous update (g / |g|): agreement to the noise of the floating-point atomics
+                err = (gx - want["x_adv"]).abs()
+                assert float(err.max()) < 2e-3 and float(err.mean()) < 5e-5, (float(err.max()), float(err.mean()))
             assert torch.allclose(got_l.to(DEV), want["losses"], rtol=2e-2, atol=1e-7), (got_l, want["losses"])
         assert torch.equal(gather[i * 2 * B:(i + 1) * 2 * B].cpu(), out_x2[i])
     # distinct batches really were attacked (not one batch three times)
