@@ -85,6 +85,10 @@ int sfk_act_stream_launch(const void* out, const void* gin, void* gz, const floa
 int sfk_torgb_stream_launch(const void* x, const float* wrgb, const float* s, int s_stride, const float* bias, const float* skip, float* rgb,
                             int n, int h, int w, int c, cudaStream_t st);
 
+// Streaming form of sfk_blur_act_fwd / sfk_blur_act_bwd, csrc/sfk_blur_stream.cu (same -1000 convention)
+int sfk_blur_stream_launch(bool bwd, const void* a0, const void* a1, void* dst, const float* d, const float* noise, float noise_w, const float* bias,
+                           float* gdacc, const float* s_in, float* gs_in, int in_stride, int n, int h, int w, int c, cudaStream_t st);
+
 // activation storage mode of the library: 0 = bf16 (default), 1 = fp32 (parity mode; tensor-core conv unavailable)
 int sfk_act_f32();
 #define SFK_ACT_DISPATCH(CALL_BF16, CALL_F32) \

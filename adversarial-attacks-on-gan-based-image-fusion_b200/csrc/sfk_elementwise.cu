@@ -754,7 +754,7 @@ __global__ void blur_simple_fwd_kernel(const T* __restrict__ Tn_, T* __restrict_
 template <typename T>
 __global__ void blur_simple_bwd_kernel(const T* __restrict__ out, const T* __restrict__ gout, T* __restrict__ gT, const float* __restrict__ d,
                                        const float* __restrict__ noise, float noise_w, const float* __restrict__ bias, float* __restrict__ gdacc,
-                                       int H, int W, int C) {
+                                       const float* __restrict__ s_in, float* __restrict__ gs_in, int in_stride, int H, int W, int C) {
   const int n = blockIdx.y;
   const int vecs = C / 8, Ho = 2 * H, Wo = 2 * W, Hp = H + 1, Wp = W + 1, Hq = 2 * H + 2, Wq = 2 * W + 2;
   const long total = static_cast<long>(Hq) * Wq * vecs;
@@ -787,11 +787,14 @@ __global__ void blur_simple_bwd_kernel(const T* __restrict__ out, const T* __res
         load8(on + off, ov);
         load8(gn + off, gv);
         const float nz = noise ? noise_w * noise[static_cast<long>(q) * Wo + r] : 0.f;
-        for (int i = 0; i < 8; ++i)
-          atomicAdd(gdacc + static_cast<long>(n) * C + v * 8 + i, gv[i] * lrelu_slope(ov[i]) * (lrelu_inv(ov[i]) - nz - bias[v * 8 + i]));
+        for (int i = 0; i < 8; ++i) {
+          const float si = s_in ? s_in[static_cast<long>(n) * in_stride + v * 8 + i] : 1.f;
+          atomicAdd(gdacc + static_cast<long>(n) * C + v * 8 + i, si * gv[i] * lrelu_slope(ov[i]) * (lrelu_inv(ov[i]) - nz - bias[v * 8 + i]));
+          if (gs_in) atomicAdd(gs_in + static_cast<long>(n) * in_stride + v * 8 + i, ov[i] * gv[i]);
+        }
       }
     }
-    for (int i = 0; i < 8; ++i) acc[i] *= d[static_cast<long>(n) * C + v * 8 + i];
+    for (int i = 0; i < 8; ++i) acc[i] *= d[static_cast<long>(n) * C + v * 8 + i] * (s_in ? s_in[static_cast<long>(n) * in_stride + v * 8 + i] : 1.f);
     store8(gTn + ((static_cast<long>((q & 1) * 2 + (r & 1)) * Hp + (q >> 1)) * Wp + (r >> 1)) * C + v * 8, acc);
   }
 }
@@ -813,7 +816,8 @@ template <bool BWD>
 __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restrict__ src0 /* fwd: T (phase planar) ; bwd: out */,
                                                         const bf16* __restrict__ src1 /* bwd: gout */, bf16* __restrict__ dst,
                                                         const float* __restrict__ d, const float* __restrict__ noise, float noise_w,
-                                                        const float* __restrict__ bias, float* __restrict__ gdacc, int H, int W, int C) {
+                                                        const float* __restrict__ bias, float* __restrict__ gdacc, const float* __restrict__ s_in,
+                                                        float* __restrict__ gs_in, int in_stride, int H, int W, int C) {
   extern __shared__ uint4 tile[];
   __shared__ float sred[32];
   const int n = blockIdx.y, cg = blockIdx.z;
@@ -826,12 +830,14 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
   const int tiles_r = (rows_out + 15) / 16, tiles_c = (cols_out + TC - 1) / TC;
   const int v = threadIdx.x % CV, cvec = cg * CV + v;       // this thread's channel vector (fixed for the whole kernel)
   const int b = threadIdx.x / CV, jb = b % bc, ib = b / bc;  // its 2x4 block inside a tile
-  float dv[8], bv[8], racc[8];
+  float dv[8], bv[8], racc[8], si[8], rin[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     dv[c] = d[static_cast<long>(n) * C + cvec * 8 + c];
     bv[c] = bias[cvec * 8 + c];
     racc[c] = 0.f;
+    rin[c] = 0.f;
+    si[c] = (BWD && s_in) ? s_in[static_cast<long>(n) * in_stride + cvec * 8 + c] : 1.f;   // the gradient arrives without its style factor
   }
   const bf16* s0 = BWD ? src0 + static_cast<long>(n) * Ho * Wo * C : src0 + static_cast<long>(n) * 4 * Hp * Wp * C;
   const bf16* s1 = BWD ? src1 + static_cast<long>(n) * Ho * Wo * C : nullptr;
@@ -857,9 +863,14 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
           float ov[8], gv[8];
           load8(s0 + off, ov);
           load8(s1 + off, gv);
+          const bool mine = r >= 2 && r < 18 && c >= 2 && c < 2 + TC;   // the tile's own pixels: reductions
+          if (mine) {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) gv[cc] *= lrelu_slope(ov[cc]);
-          if (r >= 2 && r < 18 && c >= 2 && c < 2 + TC) {   // the tile's own pixels: demodulation reduction
+            for (int cc = 0; cc < 8; ++cc) rin[cc] = fmaf(ov[cc], gv[cc], rin[cc]);
+          }
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) gv[cc] *= si[cc] * lrelu_slope(ov[cc]);
+          if (mine) {
             const float nz = noise ? noise_w * __ldg(noise + static_cast<long>(q) * Wo + rr) : 0.f;
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) racc[cc] = fmaf(gv[cc], lrelu_inv(ov[cc]) - nz - bv[cc], racc[cc]);
@@ -910,6 +921,19 @@ __global__ void __launch_bounds__(256, 2) blur_tile_kernel(const bf16* __restric
     }
     __syncthreads();
     if (threadIdx.x < CV * 8) atomicAdd(gdacc + static_cast<long>(n) * C + cg * CV * 8 + threadIdx.x, facc[threadIdx.x]);
+    if (gs_in != nullptr) {   // style gradient of the conv that consumes this layer's output: sum x * gx~
+      __syncthreads();
+      if (threadIdx.x < CV * 8) facc[threadIdx.x] = 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float x = rin[c];
+        for (int o = 16; o >= CV; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) < CV) atomicAdd(&facc[v * 8 + c], x);
+      }
+      __syncthreads();
+      if (threadIdx.x < CV * 8) atomicAdd(gs_in + static_cast<long>(n) * in_stride + cg * CV * 8 + threadIdx.x, facc[threadIdx.x]);
+    }
   }
   (void)sred;
 }
@@ -1865,11 +1889,15 @@ int sfk_modulate_weights(const float* wbase, const float* sv, int s_stride, void
 }
 
 static int blur_launch(bool bwd, const void* a0, const void* a1, void* dst, const float* d, const float* noise, float noise_w, const float* bias,
-                       float* gdacc, int n, int h, int w, int c, sfk_stream_t st) {
+                       float* gdacc, const float* s_in, float* gs_in, int in_stride, int n, int h, int w, int c, sfk_stream_t st) {
+  {
+    const int rc = sfk_blur_stream_launch(bwd, a0, a1, dst, d, noise, noise_w, bias, gdacc, s_in, gs_in, in_stride, n, h, w, c, S_(st));
+    if (rc != -1000) return rc;
+  }
   if (sfk_act_f32()) {
     if (bwd)
       blur_simple_bwd_kernel<float><<<dim3(per_sample_blocks(static_cast<long>(2 * h + 2) * (2 * w + 2) * (c / 8), n), n), kBlock, 0, S_(st)>>>(
-          static_cast<const float*>(a0), static_cast<const float*>(a1), static_cast<float*>(dst), d, noise, noise_w, bias, gdacc, h, w, c);
+          static_cast<const float*>(a0), static_cast<const float*>(a1), static_cast<float*>(dst), d, noise, noise_w, bias, gdacc, s_in, gs_in, in_stride, h, w, c);
     else
       blur_simple_fwd_kernel<float><<<dim3(per_sample_blocks(4L * h * w * (c / 8), n), n), kBlock, 0, S_(st)>>>(
           static_cast<const float*>(a0), static_cast<float*>(dst), d, noise, noise_w, bias, h, w, c);
@@ -1894,23 +1922,23 @@ static int blur_launch(bool bwd, const void* a0, const void* a1, void* dst, cons
   dim3 grid(static_cast<unsigned>(bx), n, cgs);
   if (bwd)
     blur_tile_kernel<true><<<grid, 256, smem, S_(st)>>>(static_cast<const bf16*>(a0), static_cast<const bf16*>(a1), static_cast<bf16*>(dst), d, noise,
-                                                        noise_w, bias, gdacc, h, w, c);
+                                                        noise_w, bias, gdacc, s_in, gs_in, in_stride, h, w, c);
   else
     blur_tile_kernel<false><<<grid, 256, smem, S_(st)>>>(static_cast<const bf16*>(a0), nullptr, static_cast<bf16*>(dst), d, noise, noise_w, bias,
-                                                         nullptr, h, w, c);
+                                                         nullptr, nullptr, nullptr, 0, h, w, c);
   return sfk_check_launch(bwd ? "blur_act_bwd" : "blur_act_fwd");
 }
 
 int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias, int n, int h, int w, int c,
                      sfk_stream_t st) {
   SFK_REQUIRE(T && out && d && bias && c % 8 == 0, SFK_E_ARG, "blur_act_fwd: bad args");
-  return blur_launch(false, T, nullptr, out, d, noise, noise_w, bias, nullptr, n, h, w, c, st);
+  return blur_launch(false, T, nullptr, out, d, noise, noise_w, bias, nullptr, nullptr, nullptr, 0, n, h, w, c, st);
 }
 
 int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d, const float* noise, float noise_w, const float* bias,
-                     float* gdacc, int n, int h, int w, int c, sfk_stream_t st) {
-  SFK_REQUIRE(out && gout && gT && d && bias && gdacc && c % 8 == 0, SFK_E_ARG, "blur_act_bwd: bad args");
-  return blur_launch(true, out, gout, gT, d, noise, noise_w, bias, gdacc, n, h, w, c, st);
+                     float* gdacc, const float* s_in, float* gs_in, int vec_stride, int n, int h, int w, int c, sfk_stream_t st) {
+  SFK_REQUIRE(out && gout && gT && d && bias && gdacc && c % 8 == 0 && (gs_in == nullptr || s_in != nullptr), SFK_E_ARG, "blur_act_bwd: bad args");
+  return blur_launch(true, out, gout, gT, d, noise, noise_w, bias, gdacc, s_in, gs_in, vec_stride, n, h, w, c, st);
 }
 
 int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w, const float* bias, float* gdacc,

@@ -325,9 +325,9 @@ class SynthesisEngine:
                 gx_dst = prev_conv["gout"] if prev_conv is not None else self.gx_scratch
                 # The style modulation (x s) and style gradient (sum x*gx~) of a data gradient are finished by the kernel that
                 # consumes it (act_bwd / act_torgb_bwd stream both tensors anyway) wherever such a consumer exists; the launch
-                # itself then has the plain epilogue.  Exceptions: conv1 (no consumer) and convs fed by an unfused up-layer
-                # (consumer is the blur kernel).
-                e["deferred"] = prev_conv is not None and prev_conv["fused_up"]
+                # itself then has the plain epilogue.  Exception: conv1 (no consumer).  (The consumer of a conv fed by an unfused
+                # up-layer is the blur backward, which finishes the gradient the same way.)
+                e["deferred"] = prev_conv is not None
                 if e["deferred"]:
                     e["bwd"] = lib.make_igemm_desc(
                         e["gout"], B, l.res, l.res, l.cout, 1, e["wT"], 1, 9 * l.cin, gx_dst, l.res, l.res, l.cin, 1,
@@ -436,7 +436,8 @@ class SynthesisEngine:
                 lib.act_bwd(up["out"], up["gout"], up["gout"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"],
                             s_in=s, gs_in=self.gs, in_off=conv["l"].s_off)
             else:
-                lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"])
+                lib.blur_act_bwd(up["out"], up["gout"], up["T"], up["d"], up["noise"], up["noise_w"], up["bias"], up["gdacc"],
+                                 s_in=s, gs_in=self.gs, in_off=conv["l"].s_off)
             lib.rgb_down(grgb, below_rgb["grgb"])
             grgb = below_rgb["grgb"]
             conv_tail(up)                              # first writer of below_conv["gout"]

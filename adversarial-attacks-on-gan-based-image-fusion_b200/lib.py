@@ -443,10 +443,13 @@ def blur_act_fwd(T, out, d, noise, noise_w, bias):
          "blur_act_fwd")
 
 
-def blur_act_bwd(out, gout, gT, d, noise, noise_w, bias, gdacc):
+def blur_act_bwd(out, gout, gT, d, noise, noise_w, bias, gdacc, s_in=None, gs_in=None, in_off=0):
+    """s_in / gs_in (B, s_dim) + in_off: finish a flags-0 data gradient of the conv that consumes `out` (as act_bwd does)."""
     n, ho, wo, c = out.shape
-    _chk(load().sfk_blur_act_bwd(_p(out), _p(gout), _p(gT), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc), n, ho // 2, wo // 2,
-                                 c, _stream()), "blur_act_bwd")
+    _chk(load().sfk_blur_act_bwd(_p(out), _p(gout), _p(gT), _p(d), _p(noise), _f(noise_w), _p(bias), _p(gdacc),
+                                 _sub(s_in, in_off) if s_in is not None else C.c_void_p(0),
+                                 _sub(gs_in, in_off) if gs_in is not None else C.c_void_p(0),
+                                 s_in.shape[1] if s_in is not None else 0, n, ho // 2, wo // 2, c, _stream()), "blur_act_bwd")
 
 
 def act_bwd(out, gout, gz, d, noise, noise_w, bias, gdacc, s_in=None, gs_in=None, in_off=0):

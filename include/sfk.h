@@ -204,9 +204,12 @@ int sfk_demod_bwd_batched(const float* s, int s_stride, const float* q_cat, cons
  * demod * . + noise + bias, leaky_relu*sqrt2.  T: [n][4][h+1][w+1][c] -> out [n][2h][2w][c]. */
 int sfk_blur_act_fwd(const void* T, void* out, const float* d, const float* noise, float noise_w, const float* bias,
                      int n, int h, int w, int c, sfk_stream_t st);
-/* backward of the above: gT (phase-planar) = blur^T(d * act'(out) * gout); gdacc[n][c] += sum gy*y */
+/* backward of the above: gT (phase-planar) = blur^T(d * act'(out) * g); gdacc[n][c] += sum gy*y.
+ * s_in == NULL: g = gout.  Otherwise gout is the plain (flags 0) data gradient gx~ of the conv that consumes `out`, and this
+ * kernel finishes it as sfk_act_bwd does: g = s_in[n][c] * gout, gs_in[n][c] += sum_hw out * gout (rows of vec_stride floats). */
 int sfk_blur_act_bwd(const void* out, const void* gout, void* gT, const float* d, const float* noise, float noise_w,
-                     const float* bias, float* gdacc, int n, int h, int w, int c, sfk_stream_t st);
+                     const float* bias, float* gdacc, const float* s_in, float* gs_in, int vec_stride, int n, int h, int w,
+                     int c, sfk_stream_t st);
 /* backward of FusedLeakyReLU+noise+demod for non-upsampling layers: gz = d*act'(out)*gout (in place ok) */
 int sfk_act_bwd(const void* out, const void* gout, void* gz, const float* d, const float* noise, float noise_w,
                 const float* bias, float* gdacc, const float* s_in, float* gs_in, int vec_stride, int n, int h, int w, int c,

