@@ -17,6 +17,8 @@
 // the style, accumulate sum x*gx~ -- the same consumer-side finishing sfk_act_bwd does).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "sfk_common.cuh"
 
 namespace {
@@ -28,31 +30,33 @@ __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<ui
 __device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+// the barrier helpers take shared-window addresses formed ONCE per thread (forming one costs an S2R in the hot loop otherwise)
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+__device__ __forceinline__ void mb_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mb_try(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mb_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(s_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {   // bounded: a stuck ring traps instead of hanging the GPU
+__device__ __noinline__ void mb_wait(uint32_t bar, uint32_t parity) {   // bounded: a stuck ring traps instead of hanging the GPU
+#pragma unroll 1
   for (long i = 0; i < (1L << 28); ++i)
     if (mb_try(bar, parity)) return;
   __trap();
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(s_u32(bar))
+               "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -115,11 +119,13 @@ __device__ __forceinline__ void clear(F4 (&D)[2]) {   // an input row outside th
     for (int i = 0; i < 2; ++i) D[b].p[i] = make_float2(0.f, 0.f);
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(const __grid_constant__ BlurStreamK a) {
+// MINB: CTAs per SM the register budget is planned for (3: forward with 256 consumers, 2: backward with 256, 1: 512 consumers)
+template <bool BWD, int MINB>
+__global__ void __launch_bounds__(MINB == 1 ? kMaxConsumers + 32 : 288, MINB) blur_stream_kernel(const __grid_constant__ BlurStreamK a) {
   extern __shared__ __align__(128) uint8_t sm_raw[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   const int kStages = a.stages;
+  const uint32_t full0 = s_u32(&full_bar[0]), empty0 = s_u32(&empty_bar[0]);
   const uint32_t ring = (s_u32(sm_raw) + 127u) & ~127u;
   uint8_t* const ring_p = sm_raw + (ring - s_u32(sm_raw));
   float* const sacc = reinterpret_cast<float*>(ring_p + kStages * a.stage_bytes);   // [C] (backward reductions)
@@ -173,6 +179,9 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
   float rin[4], rg[4], rgn[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) rin[i] = rg[i] = rgn[i] = 0.f;
+  float2 rin2[2], rg2[2], rgn2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) rin2[i] = rg2[i] = rgn2[i] = make_float2(0.f, 0.f);
 
   if (warp == consumers / 32) {
     // ===================== producer =====================
@@ -187,7 +196,8 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
           st = 0;
           ph ^= 1u;
         }
-        mb_wait(&empty_bar[st], ph ^ 1u);
+        if (!mb_try(empty0 + st * 8, ph ^ 1u)) mb_wait(empty0 + st * 8, ph ^ 1u);
+        const uint32_t fb = full0 + st * 8;
         const uint32_t base = ring + st * a.stage_bytes;
         const bool row_ok = r >= 0 && r < in_rows;
         const int nr = BWD ? r : r - e_off;    // noise row
@@ -195,21 +205,21 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
         uint32_t tx = 0;
         if (row_ok) tx += static_cast<uint32_t>((c_hi0 - c_lo) + (c_hi1 - c_lo)) * px_bytes;
         if (nz_ok) tx += static_cast<uint32_t>(nz_c1 - nz_c0) * 4;
-        mb_expect_tx(&full_bar[st], tx);
+        mb_expect_tx(fb, tx);
         if (row_ok) {
           const uint32_t doff = static_cast<uint32_t>(c_lo - c_first) * px_bytes;
           if (BWD) {
             const long off = ((static_cast<long>(n) * 2 * H + r) * 2 * W + c_lo) * C;
-            bulk_g2s(base + doff, a.src0 + off, static_cast<uint32_t>(c_hi0 - c_lo) * px_bytes, &full_bar[st]);
-            bulk_g2s(base + a.chunk_bytes + doff, a.src1 + off, static_cast<uint32_t>(c_hi1 - c_lo) * px_bytes, &full_bar[st]);
+            bulk_g2s(base + doff, a.src0 + off, static_cast<uint32_t>(c_hi0 - c_lo) * px_bytes, fb);
+            bulk_g2s(base + a.chunk_bytes + doff, a.src1 + off, static_cast<uint32_t>(c_hi1 - c_lo) * px_bytes, fb);
           } else {
             const long p0 = ((static_cast<long>(n) * 4 + (r & 1) * 2) * Hp + (r >> 1)) * Wp;      // even-column plane of this row
             const long p1 = p0 + static_cast<long>(Hp) * Wp;                                       // odd-column plane
-            bulk_g2s(base + doff, a.src0 + (p0 + c_lo) * C, static_cast<uint32_t>(c_hi0 - c_lo) * px_bytes, &full_bar[st]);
-            bulk_g2s(base + a.chunk_bytes + doff, a.src0 + (p1 + c_lo) * C, static_cast<uint32_t>(c_hi1 - c_lo) * px_bytes, &full_bar[st]);
+            bulk_g2s(base + doff, a.src0 + (p0 + c_lo) * C, static_cast<uint32_t>(c_hi0 - c_lo) * px_bytes, fb);
+            bulk_g2s(base + a.chunk_bytes + doff, a.src0 + (p1 + c_lo) * C, static_cast<uint32_t>(c_hi1 - c_lo) * px_bytes, fb);
           }
         }
-        if (nz_ok) bulk_g2s(base + 2 * a.chunk_bytes, a.noise + static_cast<long>(nr) * 2 * W + nz_c0, static_cast<uint32_t>(nz_c1 - nz_c0) * 4, &full_bar[st]);
+        if (nz_ok) bulk_g2s(base + 2 * a.chunk_bytes, a.noise + static_cast<long>(nr) * 2 * W + nz_c0, static_cast<uint32_t>(nz_c1 - nz_c0) * 4, fb);
       }
     }
   } else {
@@ -232,39 +242,44 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
       }
     }
     const float nw = BWD ? a.noise_w : a.noise_w * SFK_SQRT2;
+    const bool has_noise = a.noise != nullptr;
     const bool own = j < W;                     // bwd: this thread's two fine pixels exist (the last strip holds only column W)
-    const uint32_t my = static_cast<uint32_t>((BWD ? 2 * col : col) * px_bytes + cv * 8);
-    const uint32_t nz_at = static_cast<uint32_t>(2 * a.chunk_bytes + col * 8);
+    const bool writer = active && (!BWD || j <= W);
+    const bool edge = BWD && j == W;            // bwd: T column 2W+1 does not exist (its slot is written as zero)
     const int Hp = H + 1, Wp = W + 1;
+    const uint32_t sb = static_cast<uint32_t>(a.stage_bytes), cb = static_cast<uint32_t>(a.chunk_bytes), pb = static_cast<uint32_t>(px_bytes);
+    const uint32_t my = static_cast<uint32_t>((BWD ? 2 * col : col) * px_bytes + cv * 8);
+    const uint32_t nz_off = 2 * cb + static_cast<uint32_t>(col * 8);
+    // element strides of the destination rows
+    const long fwd_row = static_cast<long>(2 * W) * C;
+    __nv_bfloat16* const fwd_base = a.dst + (static_cast<long>(n) * 2 * H * 2 * W + 2 * j) * C + cv * 4;                 // + er * fwd_row
+    __nv_bfloat16* const bwd_base = a.dst + ((static_cast<long>(n) * 4 * Hp) * Wp + j) * C + cv * 4;                     // + ((plane * Hp + m) * Wp) * C
     F4 S0[2], S1[2], S2[2], S3[2];
     clear(S0); clear(S1); clear(S2); clear(S3);
-    int st_next = 0;
-    uint32_t ph = 0;
-    auto step = [&](int r, F4 (&A)[2], F4 (&B)[2], F4 (&Cc)[2], F4 (&D)[2]) {
-      const int st = st_next;
-      const uint32_t base = ring + st * a.stage_bytes;
-      mb_wait(&full_bar[st], ph);
-      if (++st_next == kStages) {
-        st_next = 0;
-        ph ^= 1u;
-      }
-      const bool row_ok = r >= 0 && r < in_rows;
+    int st = 0;
+    uint32_t ph = 0, base = ring;
+    // FULL: the row is inside the tensor, the completed row is one of this CTA's, reductions are this CTA's (steady state of the march)
+    auto step = [&](int r, auto full_tag, F4 (&A)[2], F4 (&B)[2], F4 (&Cc)[2], F4 (&D)[2]) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      if (!mb_try(full0 + st * 8, ph)) mb_wait(full0 + st * 8, ph);
+      const uint32_t sbase = base;
       const int er = r - e_off;                  // row completed by this step
-      const bool emit = er >= e_lo && er < e_hi;
+      const bool row_ok = FULL || (r >= 0 && r < in_rows);
+      const bool emit = FULL || (er >= e_lo && er < e_hi);
+      const bool red = own && (FULL || (r >= e_lo && r < 2 * (i0 + a.TI)));   // halo rows belong to the neighbouring row block's reductions
       float2 nz = make_float2(0.f, 0.f);
-      const bool red = own && r >= e_lo && r < 2 * (i0 + a.TI);   // halo rows belong to the neighbouring row block's reductions
       if (row_ok && active) {
         F4 h[2];
         const float2 q = bc2(0.25f), t = bc2(0.75f);
         if (BWD) {
           // five fine pixels 2j-2 .. 2j+2 of the gradient row: g' = gout * (out > 0 ? kp : 0.2 kp); filtered on the fly:
           //   T column 2j   = 1/4 g(2j-2) + 3/4 g(2j-1) + 3/4 g(2j) + 1/4 g(2j+1);   2j+1: the same one pixel to the right
-          if (a.noise) nz = lds64f(base + nz_at);
+          if (has_noise) nz = lds64f(sbase + nz_off);
           uint2 ov[5], gv[5];
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
-            ov[k] = lds64(base + my + k * px_bytes);
-            gv[k] = lds64(base + a.chunk_bytes + my + k * px_bytes);
+            ov[k] = lds64(sbase + my + k * pb);
+            gv[k] = lds64(sbase + cb + my + k * pb);
           }
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
@@ -272,7 +287,8 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
             F4 g;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const float2 m = make_float2(o.p[i].x > 0.f ? kp[i].x : 0.2f * kp[i].x, o.p[i].y > 0.f ? kp[i].y : 0.2f * kp[i].y);
+              const float2 kn = __fmul2_rn(kp[i], bc2(0.2f));
+              const float2 m = make_float2(o.p[i].x > 0.f ? kp[i].x : kn.x, o.p[i].y > 0.f ? kp[i].y : kn.y);
               g.p[i] = __fmul2_rn(gg.p[i], m);
               if (k == 0) h[0].p[i] = __fmul2_rn(q, g.p[i]);
               if (k == 1) { h[0].p[i] = __ffma2_rn(t, g.p[i], h[0].p[i]); h[1].p[i] = __fmul2_rn(q, g.p[i]); }
@@ -281,23 +297,20 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
               if (k == 4) h[1].p[i] = __ffma2_rn(q, g.p[i], h[1].p[i]);
             }
             if ((k == 2 || k == 3) && red) {     // own pixels 2j, 2j+1: style gradient sum x*gx~ and the demodulation sums
-              const float nzk = k == 2 ? nz.x : nz.y;
+              const float2 nzk = bc2(k == 2 ? nz.x : nz.y);
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
-                rin[2 * i] = fmaf(o.p[i].x, gg.p[i].x, rin[2 * i]);
-                rin[2 * i + 1] = fmaf(o.p[i].y, gg.p[i].y, rin[2 * i + 1]);
-                rg[2 * i] += g.p[i].x;
-                rg[2 * i + 1] += g.p[i].y;
-                rgn[2 * i] = fmaf(g.p[i].x, nzk, rgn[2 * i]);
-                rgn[2 * i + 1] = fmaf(g.p[i].y, nzk, rgn[2 * i + 1]);
+                rin2[i] = __ffma2_rn(o.p[i], gg.p[i], rin2[i]);
+                rg2[i] = __fadd2_rn(rg2[i], g.p[i]);
+                rgn2[i] = __ffma2_rn(g.p[i], nzk, rgn2[i]);
               }
             }
           }
         } else {
           // even-column plane at j, j+1 (slots col+1, col+2), odd-column plane at j-1, j, j+1 (slots col, col+1, col+2)
-          const uint2 re0 = lds64(base + my + px_bytes), re1 = lds64(base + my + 2 * px_bytes);
-          const uint2 rom = lds64(base + a.chunk_bytes + my), ro0 = lds64(base + a.chunk_bytes + my + px_bytes),
-                      ro1 = lds64(base + a.chunk_bytes + my + 2 * px_bytes);
+          const uint2 re0 = lds64(sbase + my + pb), re1 = lds64(sbase + my + 2 * pb);
+          const uint2 rom = lds64(sbase + cb + my), ro0 = lds64(sbase + cb + my + pb), ro1 = lds64(sbase + cb + my + 2 * pb);
+          if (emit && has_noise) nz = lds64f(sbase + nz_off);
           const F4 e0 = unpack(re0), e1 = unpack(re1), om = unpack(rom), o0 = unpack(ro0), o1 = unpack(ro1);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
@@ -309,43 +322,71 @@ __global__ void __launch_bounds__(kMaxConsumers + 32, 1) blur_stream_kernel(cons
         scatter(h, A, B, Cc, D);
       } else {
         clear(D);
+        if (!BWD && emit && has_noise && active) nz = lds64f(sbase + nz_off);
       }
-      if (!BWD && emit && a.noise && active) nz = lds64f(base + nz_at);
       __syncwarp();
-      if (lane == 0) mb_arrive(&empty_bar[st]);   // every shared-memory read of the stage is done
-      if (emit && active) {
+      if (lane == 0) mb_arrive(empty0 + st * 8);   // every shared-memory read of the stage is done
+      base += sb;
+      if (++st == kStages) {
+        st = 0;
+        ph ^= 1u;
+        base = ring;
+      }
+      if (emit && writer) {
         if (BWD) {
-          const int m = er >> 1;
-          if (j <= W) {
+          const bool zrow = !FULL && er > 2 * H;   // row 2H+1 does not exist either
+          __nv_bfloat16* const o0 = bwd_base + (static_cast<long>((er & 1) * 2 * Hp + (er >> 1)) * Wp) * C;
+          const long plane = static_cast<long>(Hp) * Wp * C;
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const bool zero = er > 2 * H || (b == 1 && j == W);   // slots outside the (2H+1) x (2W+1) grid
-              uint2 o;
-              o.x = zero ? 0u : pack2(A[b].p[0].x, A[b].p[0].y);
-              o.y = zero ? 0u : pack2(A[b].p[1].x, A[b].p[1].y);
-              *reinterpret_cast<uint2*>(a.dst + (((static_cast<long>(n) * 4 + (er & 1) * 2 + b) * Hp + m) * Wp + j) * C + cv * 4) = o;
-            }
+          for (int b = 0; b < 2; ++b) {
+            const bool zero = zrow || (b == 1 && edge);
+            uint2 o;
+            o.x = zero ? 0u : pack2(A[b].p[0].x, A[b].p[0].y);
+            o.y = zero ? 0u : pack2(A[b].p[1].x, A[b].p[1].y);
+            *reinterpret_cast<uint2*>(o0 + b * plane) = o;
           }
         } else {
           // the two fine pixels of this thread are neighbours in memory: out[er][2j + b][cv*4 ..]
-          __nv_bfloat16* const o0 = a.dst + ((static_cast<long>(n) * 2 * H + er) * 2 * W + 2 * j) * C + cv * 4;
+          __nv_bfloat16* const o0 = fwd_base + er * fwd_row;
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             const float2 nb = bc2(nw * (b == 0 ? nz.x : nz.y));
-            uint2 w;
             const float2 u0 = __ffma2_rn(A[b].p[0], dv[0], __fadd2_rn(nb, bv[0])), u1 = __ffma2_rn(A[b].p[1], dv[1], __fadd2_rn(nb, bv[1]));
-            w.x = pack2(fmaxf(u0.x, 0.2f * u0.x), fmaxf(u0.y, 0.2f * u0.y));
-            w.y = pack2(fmaxf(u1.x, 0.2f * u1.x), fmaxf(u1.y, 0.2f * u1.y));
+            const float2 l0 = __fmul2_rn(u0, bc2(0.2f)), l1 = __fmul2_rn(u1, bc2(0.2f));
+            uint2 w;
+            w.x = pack2(fmaxf(u0.x, l0.x), fmaxf(u0.y, l0.y));
+            w.y = pack2(fmaxf(u1.x, l1.x), fmaxf(u1.y, l1.y));
             *reinterpret_cast<uint2*>(o0 + b * C) = w;
           }
         }
       }
     };
-    for (int r = r_lo; r <= r_hi; r += 4) {
-      step(r, S0, S1, S2, S3);
-      if (r + 1 <= r_hi) step(r + 1, S1, S2, S3, S0);
-      if (r + 2 <= r_hi) step(r + 2, S2, S3, S0, S1);
-      if (r + 3 <= r_hi) step(r + 3, S3, S0, S1, S2);
+    auto step_role = [&](int r, int role, auto tag) {
+      switch (role) {
+        case 0: step(r, tag, S0, S1, S2, S3); break;
+        case 1: step(r, tag, S1, S2, S3, S0); break;
+        case 2: step(r, tag, S2, S3, S0, S1); break;
+        default: step(r, tag, S3, S0, S1, S2); break;
+      }
+    };
+    // steady-state rows [rs, re): inside the tensor, completing one of this CTA's rows, reductions owned by this CTA
+    int rs = max(max(0, e_lo + e_off), r_lo), re = min(min(in_rows, e_hi + e_off), r_hi + 1);
+    if (BWD) re = min(re, 2 * (i0 + a.TI));
+    rs += (4 - ((rs - r_lo) & 3)) & 3;           // role 0 at the start of the unrolled loop
+    int r = r_lo;
+    for (; r <= r_hi && r < rs; ++r) step_role(r, (r - r_lo) & 3, std::false_type{});
+    for (; r + 3 < re; r += 4) {
+      step(r, std::true_type{}, S0, S1, S2, S3);
+      step(r + 1, std::true_type{}, S1, S2, S3, S0);
+      step(r + 2, std::true_type{}, S2, S3, S0, S1);
+      step(r + 3, std::true_type{}, S3, S0, S1, S2);
+    }
+    for (; r <= r_hi; ++r) step_role(r, (r - r_lo) & 3, std::false_type{});
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      rin[2 * i] = rin2[i].x; rin[2 * i + 1] = rin2[i].y;
+      rg[2 * i] = rg2[i].x; rg[2 * i + 1] = rg2[i].y;
+      rgn[2 * i] = rgn2[i].x; rgn[2 * i + 1] = rgn2[i].y;
     }
   }
   if (BWD) {
@@ -409,19 +450,20 @@ int sfk_blur_stream_launch(bool bwd, const void* a0, const void* a1, void* dst, 
   k.stage_bytes = ((2 * k.chunk_bytes + 2 * TJ * 4 + 127) / 128) * 128;
   // row blocks: one wave of CTAs where the layer is large enough, at least 8 coarse rows per block
   const int rows = bwd ? h + 1 : h;
-  const int per_sm = consumers == 256 ? 2 : 1;
+  const int per_sm = consumers == 256 ? (bwd ? 2 : 3) : 1;
   const int slots = per_sm * sfk_num_sms();
   int rblocks = slots / (n * k.strips);
   if (rblocks < 1) rblocks = 1;
   if (rblocks > (rows + 7) / 8) rblocks = (rows + 7) / 8;
   k.TI = (rows + rblocks - 1) / rblocks;
   k.rblocks = (rows + k.TI - 1) / k.TI;
-  const int budget = (per_sm == 2 ? 100 : 200) * 1024 - 128 - c * static_cast<int>(sizeof(float));
+  const int budget = (per_sm == 3 ? 68 : per_sm == 2 ? 100 : 200) * 1024 - 128 - c * static_cast<int>(sizeof(float));
   k.stages = budget / k.stage_bytes;
   if (k.stages > kMaxStages) k.stages = kMaxStages;
   if (k.stages < 3) return -1000;
   const size_t smem = static_cast<size_t>(k.stages) * k.stage_bytes + 128 + static_cast<size_t>(c) * sizeof(float);
-  const void* fn = bwd ? reinterpret_cast<const void*>(&blur_stream_kernel<true>) : reinterpret_cast<const void*>(&blur_stream_kernel<false>);
+  const void* fn = per_sm == 1 ? (bwd ? reinterpret_cast<const void*>(&blur_stream_kernel<true, 1>) : reinterpret_cast<const void*>(&blur_stream_kernel<false, 1>))
+                               : (bwd ? reinterpret_cast<const void*>(&blur_stream_kernel<true, 2>) : reinterpret_cast<const void*>(&blur_stream_kernel<false, 3>));
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return static_cast<int>(e);
   void* args[1] = {&k};

@@ -448,6 +448,13 @@ struct KGroup {
   int a16[kMaxGroupTaps], b16[kMaxGroupTaps], col[kMaxGroupTaps];
 };
 
+// what the kernel reads of a load group (the argument block must stay below 4 KB: beyond that the parameters leave the fast
+// constant bank -- measured: every launch 10-25 % slower with a 4156-byte block)
+struct KGroupDev {
+  int plane, dx_min, dy_min, map, bytes, ntaps;
+  int brow[kMaxGroupTaps], bidx[kMaxGroupTaps];
+};
+
 struct __align__(64) Igemm2Args {
   CUtensorMap mapA[4];  // box height TH + 0..3 rows
   CUtensorMap mapB;
@@ -473,10 +480,16 @@ struct __align__(64) Igemm2Args {
   const float* colscale;
   float* gs;
   int* err;
-  KGroup groups[kMaxGroups];
+  KGroupDev groups[kMaxGroups];
   // taps flattened in issue order for the MMA warp (kept in registers): operand offsets (16 B units), TMEM column,
   // flags bit0 = first MMA into its accumulator, bit1 = first tap of a load group (wait for data), bit2 = last (release slot)
   int f_a16[SFK_MAX_TAPS], f_b16[SFK_MAX_TAPS], f_col[SFK_MAX_TAPS], f_flags[SFK_MAX_TAPS];
+  // Merged taps (build_plan): taps of one load group that read the SAME activation operand and whose accumulators sit in adjacent
+  // TMEM column blocks are issued as ONE tcgen05.mma of f_wm * block_n columns over their adjacent weight tiles (f_wm = 0: folded
+  // into the tap before it).  acc_blk maps an accumulator (= output plane) to its TMEM column block.
+  int f_wm[SFK_MAX_TAPS];
+  int acc_blk[4];
+  int merged;   // any f_wm != 1
 };
 
 // role-level cycle accounting (only when SFK_EP_PROFILE is set): [0] producer waiting for a free slot, [1] producer total,
@@ -503,7 +516,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // quad-transposed stores; never the staged TMA store), so that the per-tile code of the hot launches carries none of the other
 // variants' branches and address arithmetic (source-level profile, round 1: ~640 instructions per 32-column tile, 160 of them
 // arithmetic); VAR < 0: read from the arguments at run time.
-constexpr int kVarD2S = 1, kVarM2 = 2, kVarXS = 4;
+constexpr int kVarD2S = 1, kVarM2 = 2, kVarXS = 4, kVarMG = 8;   // kVarMG: merged taps (per-tap MMA widths, permuted accumulator blocks)
 template <int FCT, typename T, int VAR>
 __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_constant__ Igemm2Args a) {
   constexpr bool kF32 = std::is_same<T, float>::value;
@@ -511,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   const bool v_m2 = VAR >= 0 ? (VAR & kVarM2) != 0 : a.m2 != 0;
   const bool v_xs = VAR >= 0 ? (VAR & kVarXS) != 0 : a.xs != 0;
   const bool v_ts = VAR >= 0 ? false : a.ts != 0;
+  const bool v_mg = VAR >= 0 ? (VAR & kVarMG) != 0 : a.merged != 0;
   const int m2n = v_m2 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
@@ -528,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
   __shared__ uint64_t s_adesc[kMaxStages * SFK_MAX_TAPS];
   __shared__ uint64_t s_bdesc[kMaxStages * SFK_MAX_TAPS];
   __shared__ int s_colf[SFK_MAX_TAPS];   // (TMEM column << 1) | first-MMA-into-accumulator
+  __shared__ int s_wm[SFK_MAX_TAPS];     // merged taps: width multiplier (0 = issued as part of the tap before it)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -559,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
     s_adesc[threadIdx.x] = da;
     s_bdesc[threadIdx.x] = db;
     if (slot == 0) s_colf[t] = t < a.num_taps ? ((a.f_col[t] << 1) | (a.f_flags[t] & 1)) : 0;
+    if (slot == 1) s_wm[t] = t < a.num_taps ? a.f_wm[t] : 0;
   }
   if (threadIdx.x < a.block_n) {
     const int c = n0 + threadIdx.x;
@@ -723,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             // gather every descriptor of this load group BEFORE the first MMA: operands of an in-flight tcgen05.mma stay
             // pinned in their (uniform) registers, so descriptors formed one tap at a time would serialise issue and execution
             uint64_t AD[kMaxGroupTaps], BD[kMaxGroupTaps];
-            uint32_t TC[kMaxGroupTaps], AF[kMaxGroupTaps];
+            uint32_t TC[kMaxGroupTaps], AF[kMaxGroupTaps], ID[kMaxGroupTaps];
             const int a_row = stage * SFK_MAX_TAPS + t0;
             const int b_row = (a.b_resident ? cb : stage) * SFK_MAX_TAPS + t0;
 #pragma unroll
@@ -733,6 +749,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                 BD[j] = s_bdesc[b_row + j];
                 TC[j] = tmem_tile + part + static_cast<uint32_t>(s_colf[t0 + j] >> 1);
                 AF[j] = (cbx < ksplit && (s_colf[t0 + j] & 1)) ? 0u : 1u;   // first k-block of each partial overwrites
+                if (v_mg) {   // (only the merged variant keeps per-tap instruction descriptors live: uniform registers are scarce here)
+                  const uint32_t wm = static_cast<uint32_t>(s_wm[t0 + j]);
+                  ID[j] = wm ? idesc + ((wm - 1u) * static_cast<uint32_t>(a.block_n >> 3) << 17) : 0u;
+                }
               }
             }
             const long long td0 = prof ? clock64() : 0;
@@ -742,18 +762,19 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             if (leader && ok) {
 #pragma unroll
               for (int j = 0; j < kMaxGroupTaps; ++j) {
-                if (j < nt) {
-                  umma_t<T>(TC[j], AD[j], BD[j], idesc, AF[j]);
+                if (j < nt && (!v_mg || ID[j] != 0u)) {
+                  const uint32_t idj = v_mg ? ID[j] : idesc;
+                  umma_t<T>(TC[j], AD[j], BD[j], idj, AF[j]);
 #pragma unroll
                   for (int k = 1; k < 4; ++k)
-                    if (k < kslices) umma_t<T>(TC[j], AD[j] + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                    if (k < kslices) umma_t<T>(TC[j], AD[j] + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idj, 1u);
                   if (v_m2) {   // second M tile: rows 8..15 of the box (8 * TWB smem rows further down), its own accumulator
                     const uint64_t ad2 = AD[j] + m2_a16;
                     const uint32_t tc2 = TC[j] + m2_col;
-                    umma_t<T>(tc2, ad2, BD[j], idesc, AF[j]);
+                    umma_t<T>(tc2, ad2, BD[j], idj, AF[j]);
 #pragma unroll
                     for (int k = 1; k < 4; ++k)
-                      if (k < kslices) umma_t<T>(tc2, ad2 + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idesc, 1u);
+                      if (k < kslices) umma_t<T>(tc2, ad2 + static_cast<uint64_t>(2 * k), BD[j] + static_cast<uint64_t>(2 * k), idj, 1u);
                   }
                 }
               }
@@ -874,7 +895,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           }
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               acc_col + static_cast<uint32_t>(acc * a.block_n + c0);
+                               acc_col + static_cast<uint32_t>((v_mg ? a.acc_blk[acc] : acc) * a.block_n + c0);
         if (NC == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         if constexpr (kF32) {   // sum the partial accumulators (fp32 adds, round to nearest)
           for (int p = 1; p < ksplit; ++p) {
@@ -1368,7 +1389,7 @@ const void* kernel_for(int fct, int var) {
   if (!std::is_same<T, float>::value && var >= 0) {
     switch ((fct << 4) | var) {
 #define SFK_CASE(F, V) case (((F) << 4) | (V)): return reinterpret_cast<const void*>(&igemm_tc2_kernel<F, __nv_bfloat16, V>)
-      SFK_CASE(0, 0); SFK_CASE(0, kVarM2); SFK_CASE(0, kVarXS); SFK_CASE(0, kVarXS | kVarM2);
+      SFK_CASE(0, 0); SFK_CASE(0, kVarM2); SFK_CASE(0, kVarXS); SFK_CASE(0, kVarXS | kVarM2); SFK_CASE(0, kVarMG); SFK_CASE(0, kVarXS | kVarMG); SFK_CASE(0, kVarM2 | kVarMG); SFK_CASE(0, kVarXS | kVarM2 | kVarMG);
       SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU, 0); SFK_CASE(SFK_EP_BIAS | SFK_EP_RELU, kVarM2);
       SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, 0); SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, kVarM2);
       SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, kVarD2S); SFK_CASE(SFK_EP_NOISE | SFK_EP_BIAS | SFK_EP_LRELU_RAW, kVarD2S | kVarXS);
@@ -1403,6 +1424,8 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
   EncodeTiledFn enc = get_encode_fn();
   SFK_REQUIRE(enc != nullptr, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   Igemm2Args& k = P->k;
+  KGroup hg[kMaxGroups];   // host-side view of the load groups; the kernel's part is copied into k.groups at the end
+  memset(hg, 0, sizeof(hg));
   const int es = P->f32 ? 4 : 2;
   k.passes = (P->f32 && g_conv_math != 1) ? 3 : 1;
   k.b_samples = d->b_samples;
@@ -1475,7 +1498,11 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
   // (TMA writes + tensor-core operand reads).  Needs both halves' accumulators double-buffered: 4 x 128 columns.
   static const int m2_env = env_int("SFK_M2", 1);
   // (fp32 storage with a long K: the TMEM columns go to partial accumulators instead, see ksplit below)
-  k.m2 = (m2_env && k.TW == 16 && !halo && !can_reside && d->block_n == 128 && d->num_acc == 1 &&
+  // (The 4-accumulator transposed conv at 2 x 4 x 64 columns was tried too, SFK_M2_TCONV=1: its accumulators are then single-buffered
+  //  and only the 17^2 layer gains (78 -> 67 us); 129^2 158 -> 171 us, 257^2 148 -> 181 us.  Off.)
+  static const int m2t_env = env_int("SFK_M2_TCONV", 0);
+  const bool m2_shape = (d->block_n == 128 && d->num_acc == 1) || (m2t_env && !P->f32 && d->num_acc == 4 && d->block_n == 64 && d->a_c >= 128);
+  k.m2 = (m2_env && k.TW == 16 && !halo && !can_reside && m2_shape &&
           d->out_h >= 16 && row_bytes == 128 && !(P->f32 && d->a_c >= 512)) ? 1 : 0;
   if (k.m2) {
     k.TH = 16;
@@ -1489,7 +1516,7 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
     int g = -1;
     if (share) {
       for (int q = 0; q < ng; ++q) {
-        if (k.groups[q].plane != tp.plane || k.groups[q].ntaps >= kMaxGroupTaps) continue;
+        if (hg[q].plane != tp.plane || hg[q].ntaps >= kMaxGroupTaps) continue;
         if (!halo && dxmin[q] != tp.dx) continue;
         const int lo = tp.dy < dymin[q] ? tp.dy : dymin[q], hi = tp.dy > dymax[q] ? tp.dy : dymax[q];
         const int xlo = tp.dx < dxmin[q] ? tp.dx : dxmin[q], xhi = tp.dx > dxmax[q] ? tp.dx : dxmax[q];
@@ -1499,10 +1526,10 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
     if (g < 0) {
       SFK_REQUIRE(ng < kMaxGroups, SFK_E_SHAPE, "igemm: too many tap groups");
       g = ng++;
-      k.groups[g].plane = tp.plane; k.groups[g].ntaps = 0;
+      hg[g].plane = tp.plane; hg[g].ntaps = 0;
       dymin[g] = dymax[g] = tp.dy; dxmin[g] = dxmax[g] = tp.dx;
     }
-    KGroup& G = k.groups[g];
+    KGroup& G = hg[g];
     if (tp.dy < dymin[g]) dymin[g] = tp.dy;
     if (tp.dy > dymax[g]) dymax[g] = tp.dy;
     if (tp.dx < dxmin[g]) dxmin[g] = tp.dx;
@@ -1520,7 +1547,7 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
   bool seen[32] = {false};
   int max_rows_extra = 0, max_gt = 0;
   for (int g = 0; g < ng; ++g) {
-    KGroup& G = k.groups[g];
+    KGroup& G = hg[g];
     G.dy_min = dymin[g];
     G.dx_min = dxmin[g];
     const int extra = (dymax[g] - dymin[g]) + ((dxmax[g] - dxmin[g]) > 0 ? 1 : 0);   // +1 row: the M index runs past the last row
@@ -1535,24 +1562,117 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
     }
   }
   const int max_span = max_rows_extra;
+  // ---- merged taps.  Taps of one load group with the same operand offset read the SAME activation rows; if their accumulators
+  // occupy adjacent TMEM column blocks and their weight tiles are adjacent in shared memory they are ONE tcgen05.mma with a
+  // multiple of block_n columns: the activation operand is then read from shared memory once instead of once per tap.  The
+  // 4-phase transposed conv has 4 distinct shifts for its 9 taps (accumulator sets {0,1,2,3}, {0,1}, {0,2}, {0}): with the column
+  // order (1,0,2,3) it becomes 4 MMAs of 256/128/128/64 columns -- 34 KB instead of 54 KB of operand reads per 16-deep k-slice,
+  // against 288 tensor cycles (these launches were bound by the shared-memory port).
+  int wm[kMaxGroups][kMaxGroupTaps];
+  for (int g = 0; g < kMaxGroups; ++g)
+    for (int j = 0; j < kMaxGroupTaps; ++j) wm[g][j] = 1;
+  for (int i = 0; i < 4; ++i) k.acc_blk[i] = i;
+  static const int merge_env = env_int("SFK_TAP_MERGE", 1);
+  const int max_run = 256 / d->block_n;
+  if (merge_env && d->num_acc > 1 && d->num_acc <= 4 && (d->block_n * k.row_bytes) % 1024 == 0 && max_run >= 2) {
+    const int na = d->num_acc;
+    int perm[4] = {0, 1, 2, 3}, best_perm[4] = {0, 1, 2, 3}, best = 1 << 30;
+    // MMAs needed under a given accumulator -> column-block map (perm[acc] = block)
+    auto count_mmas = [&](const int* pm) {
+      int total = 0;
+      for (int g = 0; g < ng; ++g) {
+        const KGroup& G = hg[g];
+        bool done[kMaxGroupTaps] = {false};
+        for (int j = 0; j < G.ntaps; ++j) {
+          if (done[j]) continue;
+          bool used[4] = {false, false, false, false};   // column blocks of the taps sharing roff[j]
+          int dup = 0;
+          for (int q = j; q < G.ntaps; ++q)
+            if (!done[q] && G.roff[q] == G.roff[j]) {
+              done[q] = true;
+              if (used[pm[G.acc[q]]]) ++dup; else used[pm[G.acc[q]]] = true;
+            }
+          int run = 0;
+          for (int c = 0; c < na; ++c) {
+            if (used[c]) { if (run == 0 || run == max_run) { ++total; run = 0; } ++run; } else run = 0;
+          }
+          total += dup;
+        }
+      }
+      return total;
+    };
+    // all permutations of na <= 4 blocks (Heap's algorithm is overkill: enumerate base-na digits and keep the bijections)
+    int lim = 1;
+    for (int i = 0; i < na; ++i) lim *= na;
+    for (int code = 0; code < lim; ++code) {
+      int c = code, msk = 0;
+      for (int i = 0; i < na; ++i) { perm[i] = c % na; c /= na; msk |= 1 << perm[i]; }
+      if (msk != (1 << na) - 1) continue;
+      const int cnt = count_mmas(perm);
+      if (cnt < best) { best = cnt; for (int i = 0; i < na; ++i) best_perm[i] = perm[i]; }
+    }
+    if (best < d->num_taps) {
+      for (int i = 0; i < na; ++i) k.acc_blk[i] = best_perm[i];
+      // reorder the taps of every group: operands in order of first appearance, column blocks ascending inside an operand
+      bool seen2[4] = {false, false, false, false};
+      for (int g = 0; g < ng; ++g) {
+        KGroup& G = hg[g];
+        int order[kMaxGroupTaps], no = 0;
+        bool done[kMaxGroupTaps] = {false};
+        for (int j = 0; j < G.ntaps; ++j) {
+          if (done[j]) continue;
+          for (int c = 0; c < na; ++c)
+            for (int q = j; q < G.ntaps; ++q)
+              if (!done[q] && G.roff[q] == G.roff[j] && k.acc_blk[G.acc[q]] == c) { done[q] = true; order[no++] = q; }
+        }
+        KGroup R = G;
+        for (int j = 0; j < G.ntaps; ++j) {
+          const int q = order[j];
+          R.roff[j] = G.roff[q]; R.acc[j] = G.acc[q]; R.brow[j] = G.brow[q];
+        }
+        G = R;
+        for (int j = 0; j < G.ntaps; ++j) {
+          G.first[j] = seen2[G.acc[j]] ? 0 : 1;
+          seen2[G.acc[j]] = true;
+        }
+        // runs: consecutive taps, same operand, column blocks c, c+1, ..., the same accumulate-or-overwrite status
+        for (int j = 0; j < G.ntaps;) {
+          int len = 1;
+          while (j + len < G.ntaps && len < max_run && G.roff[j + len] == G.roff[j] &&
+                 k.acc_blk[G.acc[j + len]] == k.acc_blk[G.acc[j]] + len && G.first[j + len] == G.first[j])
+            ++len;
+          wm[g][j] = len;
+          for (int q = 1; q < len; ++q) wm[g][j + q] = 0;
+          j += len;
+        }
+      }
+    }
+  }
+  {   // shared-memory slot of every tap's weight tile = its position in issue order (adjacent for merged taps)
+    int t = 0;
+    for (int g = 0; g < ng; ++g)
+      for (int j = 0; j < hg[g].ntaps; ++j, ++t) hg[g].bidx[j] = t;
+  }
   // ---- shared memory plan
   k.b_tap_bytes = ((d->block_n * k.row_bytes + 1023) / 1024) * 1024;
   const int b_total = halves * k.num_cblk * k.num_taps * k.b_tap_bytes;
   k.b_resident = (b_total <= resident_limit && halves * k.num_cblk <= kMaxStages) ? 1 : 0;
   for (int g = 0; g < ng; ++g)
-    for (int j = 0; j < k.groups[g].ntaps; ++j) {
-      k.groups[g].a16[j] = (k.groups[g].roff[j] * k.row_bytes) >> 4;
-      k.groups[g].b16[j] = ((k.b_resident ? k.groups[g].bidx[j] : j) * k.b_tap_bytes) >> 4;
-      k.groups[g].col[j] = k.groups[g].acc[j] * d->block_n;
+    for (int j = 0; j < hg[g].ntaps; ++j) {
+      hg[g].a16[j] = (hg[g].roff[j] * k.row_bytes) >> 4;
+      hg[g].b16[j] = ((k.b_resident ? hg[g].bidx[j] : j) * k.b_tap_bytes) >> 4;
+      hg[g].col[j] = (d->num_acc <= 4 ? k.acc_blk[hg[g].acc[j]] : hg[g].acc[j]) * d->block_n;
     }
   {
     int t = 0;
     for (int g = 0; g < ng; ++g)
-      for (int j = 0; j < k.groups[g].ntaps; ++j, ++t) {
-        k.f_a16[t] = k.groups[g].a16[j];
-        k.f_b16[t] = k.groups[g].b16[j];
-        k.f_col[t] = k.groups[g].col[j];
-        k.f_flags[t] = (k.groups[g].first[j] ? 1 : 0) | (j == 0 ? 2 : 0) | (j == k.groups[g].ntaps - 1 ? 4 : 0);
+      for (int j = 0; j < hg[g].ntaps; ++j, ++t) {
+        k.f_a16[t] = hg[g].a16[j];
+        k.f_b16[t] = hg[g].b16[j];
+        k.f_col[t] = hg[g].col[j];
+        k.f_flags[t] = (hg[g].first[j] ? 1 : 0) | (j == 0 ? 2 : 0) | (j == hg[g].ntaps - 1 ? 4 : 0);
+        k.f_wm[t] = wm[g][j];
+        if (wm[g][j] != 1) k.merged = 1;
       }
   }
   k.a_stage_bytes = (((k.TH + max_span) * k.TWB * k.row_bytes + 1023) / 1024) * 1024;
@@ -1657,11 +1777,17 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SFK_REQUIRE(r == CUDA_SUCCESS, SFK_E_DRIVER, "igemm: cuTensorMapEncodeTiled(out) failed");
   }
+  for (int g = 0; g < ng; ++g) {
+    KGroupDev& D = k.groups[g];
+    D.plane = hg[g].plane; D.dx_min = hg[g].dx_min; D.dy_min = hg[g].dy_min; D.map = hg[g].map; D.bytes = hg[g].bytes; D.ntaps = hg[g].ntaps;
+    for (int j = 0; j < kMaxGroupTaps; ++j) { D.brow[j] = hg[g].brow[j]; D.bidx[j] = hg[g].bidx[j]; }
+  }
+  static_assert(sizeof(Igemm2Args) <= 4096, "kernel argument block must stay in the 4 KB constant bank window");
   P->smem = static_cast<size_t>(stages) * stage_bytes + resident + staging + 1024;
   P->grid = dim3(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
   P->fct = d->flags & ~SFK_EP_PROFILE;
   static const int spec_env = env_int("SFK_SPECIALIZE", 1);   // 0: always the run-time-variant kernels (A/B timing)
-  P->var = (k.ts || !spec_env || (d->flags & SFK_EP_PROFILE)) ? -1 : ((k.out_d2s ? kVarD2S : 0) | (k.m2 ? kVarM2 : 0) | (k.xs ? kVarXS : 0));
+  P->var = (k.ts || !spec_env || (d->flags & SFK_EP_PROFILE)) ? -1 : ((k.out_d2s ? kVarD2S : 0) | (k.m2 ? kVarM2 : 0) | (k.xs ? kVarXS : 0) | (k.merged ? kVarMG : 0));
   // opt in to > 48 KB of dynamic shared memory: per (kernel instance, device), idempotent
   const void* fn = P->f32 ? kernel_for<float>(P->fct, P->var) : kernel_for<__nv_bfloat16>(P->fct, P->var);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

@@ -197,10 +197,11 @@ class ConvStack:
 # =================================================================================================
 def _fused_up_min_res() -> int:
     """Up-layers at or above this output resolution run as ONE fused upsample-conv launch (2.25x the tensor FLOPs, but no
-    phase-plane round trip and no separate blur kernels); below it the 4-accumulator transposed conv + blur kernels are
-    cheaper because those layers are tensor-bound.  Measured on the 1024 model, 8 pairs (ms/step): none 14.0, >=1024 13.28,
-    >=512 12.79, >=256 12.63, >=128 12.75.  SFK_FUSED_UP_RES overrides (0 = all layers, large = none)."""
-    return int(os.environ.get("SFK_FUSED_UP_RES", "256"))
+    phase-plane round trip and no separate blur kernels); below it the 4-accumulator transposed conv + the streaming blur kernels
+    are cheaper.  Measured on the 1024 model, 8 pairs (ms/step): round 1 (tiled blur, 1.2 TB/s) none 14.0, >=1024 13.28,
+    >=512 12.79, >=256 12.63; round 2 (streaming blur, 3-4 TB/s) >=256 8.45, >=512 8.28, >=1024 8.20, none 8.23.
+    SFK_FUSED_UP_RES overrides (0 = all layers, large = none)."""
+    return int(os.environ.get("SFK_FUSED_UP_RES", "1024"))
 
 
 class SynthesisEngine:
