@@ -9,7 +9,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB = os.path.join(PKG_DIR, "libsfattack.so")
-SOURCES = ["sfk_core.cu", "sfk_igemm.cu", "sfk_elementwise.cu", "sfk_stream.cu", "sfk_blur_stream.cu"]
+SOURCES = ["sfk_core.cu", "sfk_igemm.cu", "sfk_elementwise.cu", "sfk_stream.cu", "sfk_blur_stream.cu", "sfk_wgrad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -57,7 +57,7 @@ EXPORTS = [
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
     "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_random_start", "sfk_attack_update_patch",
     "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample", "sfk_patch_grad_reduce", "sfk_patch_apply_shared",
-    "sfk_ssim_gray7",
+    "sfk_ssim_gray7", "sfk_conv3x3_wgrad", "sfk_bias_grad", "sfk_modconv_wgrad_finish",
 ]
 
 _lib = None
@@ -435,6 +435,36 @@ def demod_bwd_batched(s, q_cat, d_cat, gd_cat, gs, tab, max_cin):
     n, sd = s.shape
     _chk(load().sfk_demod_bwd_batched(_p(s), sd, _p(q_cat), _p(d_cat), _p(gd_cat), _p(gs), gs.shape[1], _p(tab), tab.shape[0], n, max_cin,
                                       _stream()), "demod_bwd_batched")
+
+
+def conv3x3_wgrad(x, gz, dw=None, per_sample=False, ref=False, err=None):
+    """dw (S,9,cout,cin) fp32 += sum gz (x) x shifted by the tap; x (n,h,w,cin), gz (n,h,w,cout) NHWC activations (sfk.h).
+    Returns dw (allocated and zeroed when not given)."""
+    n, h, w, cin = x.shape
+    cout = gz.shape[3]
+    if dw is None:
+        dw = torch.zeros((n if per_sample else 1), 9, cout, cin, device=x.device, dtype=torch.float32)
+    _chk(load().sfk_conv3x3_wgrad(_p(x), _p(gz), _p(dw), n, h, w, cin, cout, int(per_sample), int(ref),
+                                  _p(err) if err is not None else C.c_void_p(0), _stream()), "conv3x3_wgrad")
+    return dw
+
+
+def bias_grad(gz, db=None):
+    n, h, w, c = gz.shape
+    if db is None:
+        db = torch.zeros(c, device=gz.device, dtype=torch.float32)
+    _chk(load().sfk_bias_grad(_p(gz), _p(db), n, h * w, c, _stream()), "bias_grad")
+    return db
+
+
+def modconv_wgrad_finish(G, wbase, s, s_off, d, gdacc, demodulate=True):
+    """G (n,9,cout,cin) from conv3x3_wgrad(per_sample=True) -> gradient of the shared base weight (9,cout,cin)."""
+    n, _, cout, cin = G.shape
+    dwb = torch.empty(9, cout, cin, device=G.device, dtype=torch.float32)
+    _chk(load().sfk_modconv_wgrad_finish(_p(G), _p(wbase), _sub(s, s_off), s.shape[1], _p(d) if d is not None else C.c_void_p(0),
+                                         _p(gdacc) if gdacc is not None else C.c_void_p(0), _p(dwb), n, cout, cin, int(demodulate),
+                                         _stream()), "modconv_wgrad_finish")
+    return dwb
 
 
 def blur_act_fwd(T, out, d, noise, noise_w, bias):

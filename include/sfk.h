@@ -104,6 +104,25 @@ typedef struct {
   size_t ws_bytes;
 } sfk_igemm_desc;
 
+/* ---- weight gradients: the second backward GEMM of the 3x3 convolutions (north_star: "forward and both backward GEMMs").
+ * The reference leaves every parameter trainable (code/attack/attack_main2.py:301-304), so its autograd evaluates these on every
+ * iteration of the loops at attack_main2.py:584-671 / adversarial_patch.py:94-160 although only the pixel gradient is used.
+ *
+ * sfk_conv3x3_wgrad: dw[s][tap][co][ci] += sum_{n in s} sum_{h,w} gz[n][h][w][co] * x[n][h+dy][w+dx][ci], tap = (dy+1)*3 + (dx+1),
+ *   zero padding; x [n][h][w][cin], gz [n][h][w][cout] in the activation storage type, dw fp32 [S][9][cout][cin] with S = n
+ *   (per_sample, ModulatedConv2d) or 1 (shared weights, VGG / encoder); dw is ACCUMULATED into (zero it first).  tcgen05 kernel
+ *   (MN-major operands straight from the NHWC tensors, csrc/sfk_wgrad.cu) for bf16 storage, w >= 8, channels % 8 == 0; CUDA cores
+ *   otherwise or when use_ref != 0.  err: device int raised on an internal pipeline timeout (may be NULL).
+ * sfk_bias_grad: db[c] += sum_{n,h,w} gz (conv3x3+bias+ReLU; gz already carries the ReLU mask).
+ * sfk_modconv_wgrad_finish: from the per-sample GEMM result G [n][9][cout][cin] (gz = d * dL/dy, x the unmodulated input) to the
+ *   gradient of the shared base weight Wb = scale*W [9][cout][cin]:
+ *   dWb = sum_n s[n][ci] * (G[n] - gdacc[n][co] * d[n][co]^2 * Wb * s[n][ci])   (second term only if demodulate). */
+int sfk_conv3x3_wgrad(const void* x, const void* gz, float* dw, int n, int h, int w, int cin, int cout, int per_sample, int use_ref,
+                      int32_t* err, sfk_stream_t stream);
+int sfk_bias_grad(const void* gz, float* db, int n, int hw, int c, sfk_stream_t stream);
+int sfk_modconv_wgrad_finish(const float* G, const float* wb, const float* s, int s_stride, const float* d, const float* gdacc,
+                             float* dwb, int n, int cout, int cin, int demodulate, sfk_stream_t stream);
+
 /* One-shot launch: plans (tap grouping, shared-memory plan, tensor-map encoding) and launches.  Re-entrant: no static state. */
 int sfk_igemm(const sfk_igemm_desc* d, sfk_stream_t stream);
 /* Prepared launches: sfk_igemm_prepare does all the host-side work once and returns an immutable plan bound to the descriptor's
