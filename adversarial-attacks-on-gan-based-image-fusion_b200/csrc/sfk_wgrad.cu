@@ -276,6 +276,37 @@ __global__ void bias_grad_kernel(const T* __restrict__ gz, float* __restrict__ d
   }
 }
 
+// First conv of VGG / encoder (3 input channels, fp32 NCHW input): dw[co][ci][ky][kx] += sum gz[n][h][w][co] * x[n][ci][h+ky-1][w+kx-1].
+// One thread = one output channel, 27 accumulators in registers; a block walks a strip of pixels (the 27 input taps of a pixel are
+// the same for every thread: broadcast loads), then one atomicAdd per (thread, tap).
+template <typename T>
+__global__ void conv_c3_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ gz, float* __restrict__ dw, int n_img, int h, int w, int cout) {
+  const long pixels = static_cast<long>(n_img) * h * w;
+  const long per_block = (pixels + gridDim.x - 1) / gridDim.x;
+  const long p0 = blockIdx.x * per_block, p1 = min(pixels, p0 + per_block);
+  for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    float acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+    for (long p = p0; p < p1; ++p) {
+      const int n = p / (static_cast<long>(h) * w), r = p % (static_cast<long>(h) * w), py = r / w, px = r % w;
+      const float g = to_f32(gz[p * cout + co]);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = py + ky - 1, xx = px + kx - 1;
+            const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(x + ((static_cast<long>(n) * 3 + ci) * h + yy) * w + xx) : 0.f;
+            acc[(ci * 3 + ky) * 3 + kx] = fmaf(g, v, acc[(ci * 3 + ky) * 3 + kx]);
+          }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; ++i) atomicAdd(dw + static_cast<long>(co) * 27 + i, acc[i]);
+  }
+}
+
 // ModulatedConv2d: from the per-sample GEMM result G[n][tap][co][ci] = sum_p gz[n][p][co] x[n][p+tap][ci]  (gz = d * dL/dy, x the
 // UNmodulated input) to the gradient of the shared weight (oracle/stylegan2.py modulated_conv2d):
 //   w'[n] = Wb * s[n],  d[n][co] = rsqrt(sum w'^2 + eps),  y = d * conv(w', x)         (Wb = scale * W)
@@ -409,4 +440,18 @@ extern "C" int sfk_modconv_wgrad_finish(const float* G, const float* wb, const f
   modconv_wgrad_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(G, wb, s, s_stride, d, gdacc, dwb, n, cout, cin,
                                                                                                           demodulate);
   return sfk_check_launch("modconv_wgrad_finish_kernel");
+}
+
+extern "C" int sfk_conv_c3_wgrad(const float* x, const void* gz, float* dw, int n, int h, int w, int cout, sfk_stream_t stream) {
+  SFK_REQUIRE(x && gz && dw && n > 0 && h > 0 && w > 0 && cout > 0, SFK_E_ARG, "conv_c3_wgrad: bad args");
+  const long pixels = static_cast<long>(n) * h * w;
+  long blocks = (pixels + 255) / 256;
+  if (blocks > 8L * sfk_num_sms()) blocks = 8L * sfk_num_sms();
+  const int threads = cout >= 128 ? 128 : (cout >= 64 ? 64 : 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (sfk_act_f32())
+    conv_c3_wgrad_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, static_cast<const float*>(gz), dw, n, h, w, cout);
+  else
+    conv_c3_wgrad_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, static_cast<const __nv_bfloat16*>(gz), dw, n, h, w, cout);
+  return sfk_check_launch("conv_c3_wgrad_kernel");
 }

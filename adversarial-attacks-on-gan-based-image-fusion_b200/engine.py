@@ -149,6 +149,23 @@ class ConvStack:
     def tap_outputs(self) -> List[torch.Tensor]:
         return [self.out[i] for i in self.taps]
 
+    @_on_device
+    def weight_grads(self, x: torch.Tensor) -> Dict[int, Tuple[torch.Tensor, torch.Tensor]]:
+        """The second backward GEMM (the reference's autograd runs it because it never freezes parameters,
+        attack_main2.py:301-304): {layer index: (dW (cout,cin,3,3), db (cout,))} in fp32, from the buffers a forward(x) + backward()
+        left behind -- g[i] is dL/d(pre-activation) of conv i (the ReLU mask is applied by whoever wrote it), out[i-1] its input."""
+        res = {}
+        for i, l in enumerate(self.layers):
+            if l.kind == "c3":
+                dw = lib.conv_c3_wgrad(x, self.g[i])
+            elif l.kind == "conv":
+                dw = lib.conv3x3_wgrad(self.out[i - 1], self.g[i], err=self.err)[0]
+                dw = dw.view(3, 3, l.cout, l.cin).permute(2, 3, 0, 1).contiguous()
+            else:
+                continue
+            res[i] = (dw, lib.bias_grad(self.g[i]))
+        return res
+
     def _tap_coefs(self, i: int, coef: float):
         per = self.out[i].numel() // self.n
         return coef / per, 2.0 * coef / per
@@ -402,6 +419,23 @@ class SynthesisEngine:
     @property
     def image(self) -> torch.Tensor:
         return self.L[-1]["rgb"]
+
+    @_on_device
+    def weight_grads(self) -> Dict[str, torch.Tensor]:
+        """dL/dW (cout,cin,3,3) fp32 of every non-upsampling 3x3 ModulatedConv2d (conv1 and the second conv of each resolution),
+        from the buffers forward() + backward() left behind: x (unmodulated input), gout = d * dL/dy, gdacc, d, s -- per-sample
+        tensor-core GEMM + the modulation/demodulation chain rule (sfk_modconv_wgrad_finish).  Up-sampling convs and ToRGB are not
+        covered (their gradient buffers are scratch that later layers reuse)."""
+        res = {}
+        for e in self.L:
+            l = e["l"]
+            if l.kind != "conv":
+                continue
+            G = lib.conv3x3_wgrad(e["x"], e["gout"], per_sample=True, err=self.err)
+            dwb = lib.modconv_wgrad_finish(G, e["wbase"], self.s, l.s_off, e["d"], e["gdacc"])
+            scale = 1.0 / math.sqrt(l.cin * 9)
+            res[l.name] = (dwb * scale).view(3, 3, l.cout, l.cin).permute(2, 3, 0, 1).contiguous()
+        return res
 
     @_on_device
     def backward(self, g_img: torch.Tensor) -> torch.Tensor:

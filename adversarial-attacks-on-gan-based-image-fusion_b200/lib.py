@@ -57,7 +57,7 @@ EXPORTS = [
     "sfk_rgb_down", "sfk_linear_fwd", "sfk_linear_bwd", "sfk_fuse_spatial_fwd", "sfk_fuse_spatial_bwd", "sfk_axpby",
     "sfk_nchw_to_nhwc_bf16", "sfk_nhwc_bf16_to_nchw", "sfk_attack_update_linf", "sfk_attack_random_start", "sfk_attack_update_patch",
     "sfk_attack_update_adam", "sfk_attack_update_l2", "sfk_minmax_per_sample", "sfk_patch_grad_reduce", "sfk_patch_apply_shared",
-    "sfk_ssim_gray7", "sfk_conv3x3_wgrad", "sfk_bias_grad", "sfk_modconv_wgrad_finish",
+    "sfk_ssim_gray7", "sfk_conv3x3_wgrad", "sfk_bias_grad", "sfk_modconv_wgrad_finish", "sfk_conv_c3_wgrad",
 ]
 
 _lib = None
@@ -446,6 +446,16 @@ def conv3x3_wgrad(x, gz, dw=None, per_sample=False, ref=False, err=None):
         dw = torch.zeros((n if per_sample else 1), 9, cout, cin, device=x.device, dtype=torch.float32)
     _chk(load().sfk_conv3x3_wgrad(_p(x), _p(gz), _p(dw), n, h, w, cin, cout, int(per_sample), int(ref),
                                   _p(err) if err is not None else C.c_void_p(0), _stream()), "conv3x3_wgrad")
+    return dw
+
+
+def conv_c3_wgrad(x, gz, dw=None):
+    """x (n,3,h,w) fp32 NCHW, gz (n,h,w,cout) -> dw (cout,3,3,3) fp32 (torch layout), accumulated"""
+    n, _, h, w = x.shape
+    cout = gz.shape[3]
+    if dw is None:
+        dw = torch.zeros(cout, 3, 3, 3, device=x.device, dtype=torch.float32)
+    _chk(load().sfk_conv_c3_wgrad(_p(x), _p(gz), _p(dw), n, h, w, cout, _stream()), "conv_c3_wgrad")
     return dw
 
 

@@ -120,6 +120,8 @@ typedef struct {
 int sfk_conv3x3_wgrad(const void* x, const void* gz, float* dw, int n, int h, int w, int cin, int cout, int per_sample, int use_ref,
                       int32_t* err, sfk_stream_t stream);
 int sfk_bias_grad(const void* gz, float* db, int n, int hw, int c, sfk_stream_t stream);
+/* first conv (3 input channels, x fp32 NCHW as sfk_conv_c3_fwd takes it): dw [cout][3][3][3] (torch layout) += ... */
+int sfk_conv_c3_wgrad(const float* x, const void* gz, float* dw, int n, int h, int w, int cout, sfk_stream_t stream);
 int sfk_modconv_wgrad_finish(const float* G, const float* wb, const float* s, int s_stride, const float* d, const float* gdacc,
                              float* dwb, int n, int cout, int cin, int demodulate, sfk_stream_t stream);
 

@@ -138,3 +138,103 @@ def test_modulated_conv_weight_grad(n, h, cin, cout):
     dwb = lib.modconv_wgrad_finish(G, wb, s.contiguous(), 0, d.contiguous(), gdacc.contiguous())
     got = (dwb * scale).reshape(3, 3, cout, cin).permute(2, 3, 0, 1)                  # dL/dW = scale * dL/dWb
     _close(got, gW_ref[0], 1e-2, "modulated conv dW")      # gz passes through a bf16 buffer (2^-9 relative per element)
+
+
+def _cos(a, b):
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(params=["bf16", "fp32"])
+def storage(request):
+    """bf16 storage (product path: tensor-core wgrad) and the fp32 parity mode (CUDA-core wgrad on fp32 buffers)"""
+    from sfattack import lib
+    if request.param == "fp32":
+        lib.set_activation_dtype(torch.float32)
+    try:
+        yield request.param
+    finally:
+        lib.set_activation_dtype(torch.bfloat16)
+
+
+def test_vgg_stack_weight_grads_vs_reference_autograd(storage):
+    """ConvStack.weight_grads(): every conv of the executed VGG prefix (code/vgg.py:44-64), weights AND biases, against autograd
+    through the pinned oracle (oracle/vgg_ref.py) with the parameters left trainable, as the reference leaves them.
+    fp32 storage (split-tf32 convs): 5e-3 (measured 0.9e-3 weights, 2.9e-3 biases).  bf16 storage: the loss is the small difference of two bf16-rounded feature maps, so the stored gradients
+    carry ~2 % noise (cos 0.98 against the oracle, same as the input gradient of this stack) and the weight gradient, a
+    cancelling sum of them, 0.87-0.95 -- torch evaluating dW from the SAME buffers agrees with the kernel to 1.000000
+    (tools/diag_wgrad_stack.py), i.e. the floor is the storage, not the GEMM."""
+    from oracle.vgg_ref import vgg_forward
+    from sfattack.engine import ConvStack, vgg_layers
+    from sfattack.params import make_vgg_state_dict
+    sd = {k: v.clone().requires_grad_(True) for k, v in make_vgg_state_dict(3, width_div=2).items()}
+    n, res = 2, 64
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(n, 3, res, res, generator=g) * 2 - 1
+    with torch.no_grad():
+        refs = [t.detach() for t in vgg_forward(sd, (x + 0.05 * torch.randn(x.shape, generator=g)).clamp(-1, 1))]
+    taps = vgg_forward(sd, x)
+    L = sum(((t - r) ** 2).flatten(1).mean(1) for t, r in zip(taps, refs))
+    vals = list(sd.values())[:18]
+    grads = torch.autograd.grad(L.sum(), vals)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    st = ConvStack(vgg_layers(2), [(vals[2 * i].detach(), vals[2 * i + 1].detach()) for i in range(9)], n, res, torch.device(DEV), err)
+    xd = x.to(DEV)
+    st.forward(xd)
+    loss = torch.zeros(n, device=DEV)
+    act = torch.float32 if storage == "fp32" else torch.bfloat16
+    st.backward([r.permute(0, 2, 3, 1).contiguous().to(DEV).to(act) for r in refs], 1.0, loss)
+    wg = st.weight_grads(xd)
+    torch.cuda.synchronize()
+    assert err.item() == 0
+    conv_idx = [i for i, l in enumerate(st.layers) if l.kind != "pool"]
+    assert sorted(wg) == conv_idx and len(conv_idx) == 9
+    for k, i in enumerate(conv_idx):
+        dw, db = wg[i]
+        assert dw.shape == grads[2 * k].shape and db.shape == grads[2 * k + 1].shape
+        if storage == "fp32":
+            assert _relerr(dw, grads[2 * k]) < 5e-3 and _relerr(db, grads[2 * k + 1]) < 5e-3, (i, _relerr(dw, grads[2 * k]), _relerr(db, grads[2 * k + 1]))
+        else:
+            assert _cos(dw, grads[2 * k]) > 0.85 and _cos(db, grads[2 * k + 1]) > 0.85, (i, _cos(dw, grads[2 * k]), _cos(db, grads[2 * k + 1]))
+
+
+def test_synthesis_weight_grads_vs_oracle_autograd(storage):
+    """SynthesisEngine.weight_grads(): dL/dW of the non-upsampling 3x3 ModulatedConv2d layers against autograd through the oracle
+    generator with its conv weights left trainable."""
+    from oracle import stylegan2 as sg
+    from sfattack.engine import SynthesisEngine
+    from sfattack.params import gen_spec, make_generator_params
+    spec = gen_spec(64, style_dim=64, n_mlp=2, channels={4: 64, 8: 64, 16: 32, 32: 32, 64: 16})
+    GP = make_generator_params(spec, seed=0)
+    B = 2
+    g = torch.Generator().manual_seed(7)
+    w = torch.randn(B, spec.n_latent, spec.style_dim, generator=g)
+    names = [l.name for l in spec.layers if l.kind == "conv"]
+    GPt = dict(GP)
+    for nme in names:
+        GPt[f"{nme}.conv.weight"] = GP[f"{nme}.conv.weight"].clone().requires_grad_(True)
+    styles = sg.styles_from_wplus(GPt, spec, w)
+    img_ref = sg.synthesis_from_styles(GPt, spec, styles)
+    gimg = torch.randn(img_ref.shape, generator=g)
+    grads = torch.autograd.grad((img_ref * gimg).sum(), [GPt[f"{nme}.conv.weight"] for nme in names])
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    syn = SynthesisEngine(spec, GP, B, torch.device(DEV), err)
+    syn.styles_from_wplus(w.to(DEV))
+    syn.forward()
+    syn.backward(gimg.to(DEV))
+    wg = syn.weight_grads()
+    torch.cuda.synchronize()
+    assert err.item() == 0
+    assert sorted(wg) == sorted(names)
+    for nme, gr in zip(names, grads):
+        got = wg[nme]
+        assert got.shape == gr[0].shape
+        if storage == "fp32":
+            assert _relerr(got, gr[0]) < 2e-3, (nme, _relerr(got, gr[0]))
+        else:   # same bf16 floor as the style gradient of this engine (tests/test_engine_gpu.py): nearly-cancelling demodulation terms
+            assert _cos(got, gr[0]) > 0.99 and _relerr(got, gr[0]) < 0.15, (nme, _cos(got, gr[0]), _relerr(got, gr[0]))

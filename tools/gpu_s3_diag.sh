@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python tools/diag_blur_repeat.py > gpurun_out/s3_diag2.log 2>&1
+python tools/diag_wgrad_stack.py > gpurun_out/s3_diag3.log 2>&1
 echo done

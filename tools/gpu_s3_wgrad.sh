@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_wgrad_gpu.py -q --timeout 200 -x 2>&1 | tail -30 > gpurun_out/s3_wgrad_test.log
+timeout 600 python -m pytest tests/test_wgrad_gpu.py -q --timeout 200 2>&1 | tail -40 > gpurun_out/s3_wgrad_test.log
 echo done
