@@ -55,8 +55,11 @@ def launches(src, dst, cmd=""):
     print(f"{b - a} launches, {tot / 1e3:.2f} ms; igemm share {100 * ig / tot:.1f}%")
 
 
-def full(src, dst, cmd=""):
+def full(src, dst, cmd="", shapes_json=""):
+    """shapes_json: bench.py --dump-launches output of the same step (its conv_launches are in launch order): adds the GEMM shape,
+    the event-timed duration and the algorithmic TFLOP/s of every row (the launch <-> ncu-row map)."""
     H, data = _rows(src)
+    shapes = json.load(open(shapes_json))["conv_launches"] if shapes_json else None
 
     def col(suffix):
         if suffix in H:
@@ -107,9 +110,21 @@ def full(src, dst, cmd=""):
             f.write(f"Command (after the same command exited 0 without ncu): `{cmd}`\n\n")
         f.write(f"{n} launches: total {tot_t / 1e3:.2f} ms (cold-cache, serialised), DRAM traffic {tot_b / 1e9:.2f} GB = "
                 f"**{tot_b / n / 1e6:.1f} MB per launch** on average; registers/thread {regs:.0f}.\n\n")
-        f.write("| # | grid | us | DRAM MB (r+w) | DRAM % | tensor pipe % | L2 % |\n|---:|---|---:|---:|---:|---:|---:|\n")
-        for i, r in enumerate(rows):
-            f.write(f"| {i} | {r[0]} | {r[1]:.1f} | {r[2] / 1e6:.1f} | {r[3]:.1f} | {r[4]:.1f} | {r[5]:.1f} |\n")
+        if shapes and len(shapes) == n:
+            wt = sum(r[1] * r[4] for r in rows) / tot_t
+            f.write(f"Time-weighted tensor-pipe activity over the {n} launches: **{wt:.1f} %**.  `shape` = images x output grid, Cin->Cout "
+                    "(x4 accumulators for the 4-phase transposed conv; fused upsample convs list their 4*Cout columns); `event us` / "
+                    "`TFLOP/s` are the CUDA-event timings of the same launches inside an unprofiled step (bench.py --dump-launches).\n\n")
+            f.write("| # | shape | grid | ncu us | event us | alg. TFLOP/s | DRAM MB (r+w) | achieved GB/s | DRAM % | tensor pipe % | L2 % |\n"
+                    "|---:|---|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+            for i, (r, c) in enumerate(zip(rows, shapes)):
+                shp = f"{c['n']}x{c['out_h']}x{c['out_w']} {c['cin']}->{c['cout']}" + (f" x{c['num_acc']}acc" if c['num_acc'] > 1 else "")
+                f.write(f"| {i} | {shp} | {r[0]} | {r[1]:.1f} | {c['us']:.1f} | {c['tflops']:.0f} | {r[2] / 1e6:.1f} | {r[2] / r[1] / 1e3:.0f} | {r[3]:.1f} | "
+                        f"{r[4]:.1f} | {r[5]:.1f} |\n")
+        else:
+            f.write("| # | grid | us | DRAM MB (r+w) | DRAM % | tensor pipe % | L2 % |\n|---:|---|---:|---:|---:|---:|---:|\n")
+            for i, r in enumerate(rows):
+                f.write(f"| {i} | {r[0]} | {r[1]:.1f} | {r[2] / 1e6:.1f} | {r[3]:.1f} | {r[4]:.1f} | {r[5]:.1f} |\n")
     tr = dst.replace("igemm_full", "igemm_traffic") + ".json"
     json.dump({"kernel": "igemm_tc2_kernel", "launches_per_step": n, "dram_bytes_per_launch": tot_b / n, "dram_bytes_per_step": tot_b,
                "serialized_ms_per_step": tot_t / 1e3, "source": dst + ".md (ncu --set full, the conv launches of one step)"},
@@ -145,16 +160,17 @@ def elem(src, dst, cmd=""):
         if cmd:
             f.write(f"Command (after the same command exited 0 without ncu): `{cmd}`\n\n")
         f.write("Achieved GB/s = (dram__bytes_read + dram__bytes_write) / gpu__time_duration of that launch (cold-cache, serialised).\n\n")
-        f.write("| # | kernel | us | DRAM MB (r+w) | achieved GB/s | DRAM % of peak |\n|---:|---|---:|---:|---:|---:|\n")
+        f.write("| # | kernel | us | DRAM MB (r+w) | achieved GB/s | % of the measured copy peak (6547 GB/s) |\n|---:|---|---:|---:|---:|---:|\n")
         for i, r in enumerate(data):
             t = val(r, "gpu__time_duration.sum", tsc)
             by = val(r, "dram__bytes_read.sum", bsc) + val(r, "dram__bytes_write.sum", bsc)
             f.write(f"| {i} | `{_short(r[ci['Kernel Name']])}` | {t:.1f} | {by / 1e6:.1f} | {by / t / 1e3:.0f} | "
-                    f"{val(r, 'dram__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} |\n")
+                    f"{100 * by / t / 1e3 / 6547:.1f} |\n")
     print(f"{len(data)} launches -> {dst}.md")
 
 
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     cmd = sys.argv[4] if len(sys.argv) > 4 else ""
-    {"launches": launches, "full": full, "elem": elem}[mode](src, dst, cmd)
+    extra = sys.argv[5:6]
+    {"launches": launches, "full": full, "elem": elem}[mode](src, dst, cmd, *extra)

@@ -5,12 +5,16 @@ import collections, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "adversarial-attacks-on-gan-based-image-fusion_b200", "csrc")
-KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "LDG", "STG", "LDS", "STS", "FFMA", "SHFL"]
+KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "LDG", "STG", "LDS", "STS", "FFMA", "FFMA2", "REDG", "SHFL"]
 
 
 def demangle(names):
     out = subprocess.run(["cu++filt"] + names, capture_output=True, text=True).stdout.splitlines()
-    return [re.sub(r"\(anonymous namespace\)::|void |<unnamed>::", "", o).split("(")[0] for o in out]
+    names = []
+    for o in out:
+        o = re.sub(r"\(anonymous namespace\)::|void |<unnamed>::|\(bool\)|\(int\)", "", o)
+        names.append(o[:o.rfind("(")] if o.endswith(")") else o)      # drop the parameter list, keep template arguments
+    return names
 
 
 def main():
