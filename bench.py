@@ -413,6 +413,52 @@ def run_ours(args):
         json.dump(dict(step_ms=batch_step_ms, conv_launches=rows, plans=infos, kernel_table=[dict(name=n_[:120], count=c_, us=u_) for n_, c_, u_ in table]),
                   open(args.dump_launches, "w"), indent=1)
 
+    # -------- N = 1 only: the single-GPU point of the N > 1 workload (configs[2]: spatial fusion, all 64 pairs as 8 resident batches,
+    # per-batch reference fusion + random start inside the timed region exactly as the N > 1 arm times it), so that the strong-scaling
+    # efficiency of the 2/4/8-GPU lines has its own denominator (their `value` is not comparable with this line's configs[1] `value`)
+    c3_single = None
+    if world == 1 and not args.no_c3_line and S == SIZE and B == PAIRS_PER_GPU:
+        del prof
+        eng3 = AttackEngine(spec, GP, es, EP, vsd, make_fusion_params(spec.s_dim), fusion="spatial", batch=B, device=str(dev), loss=LossCfg(1.0, 1.0))
+        res3 = []
+        for b in range(GLOBAL_PAIRS_C3 // B):
+            xa_h, xb_h = synthetic_pairs(B, S, first_index=b * B)
+            res3.append((xa_h.to(dev), xb_h.to(dev)))
+        k3 = eng3.k_in
+
+        def step3():
+            _, g3 = eng3.forward_backward()
+            lib.attack_update_linf(eng3.x, eng3.x0, g3, ALPHA, EPS, 1.0, 0.0, 1.0, eng3.stats, k3)
+
+        eng3.set_inputs(*res3[0])
+        eng3.compute_reference()
+        lib.attack_random_start(eng3.x, eng3.x0, EPS, 4321)
+        for _ in range(args.warmup):
+            step3()
+        g3 = None
+        if args.graph:
+            g3 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g3, capture_error_mode="thread_local"):
+                step3()
+            g3.replay()
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for xa_d, xb_d in res3:
+            eng3.set_inputs(xa_d, xb_d)
+            eng3.compute_reference()
+            lib.attack_random_start(eng3.x, eng3.x0, EPS, 4321)
+            for _ in range(args.steps):
+                g3.replay() if g3 is not None else step3()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        eng3.check()
+        c3_ms = c0.elapsed_time(c1)
+        c3_single = {"value": args.steps * GLOBAL_PAIRS_C3 / (c3_ms * 1e-3), "unit": UNIT, "global_pairs": GLOBAL_PAIRS_C3, "ms_per_step": c3_ms / args.steps,
+                     "what": "BASELINE.json configs[2] on ONE GPU (spatial fusion, 64 pairs as 8 resident batches of 8; per-batch reference "
+                             "fusion and random start inside the timed region, as in the N > 1 lines): the denominator of their strong scaling"}
+        del eng3, res3
+
     if rank == 0:
         cpu = None
         if world > 1:
@@ -433,7 +479,10 @@ def run_ours(args):
                                 f"losses (copies of neighbouring batches overlap the compute)"
                                 + (", then the NCCL all-gather of all adversarial examples" if world > 1 else "")},
                 "roofline": roofline, "cpu_baseline": cpu,
-                "per_gpu_iter_img_per_s": value / world, "weak_scaled": weak,
+                "per_gpu_iter_img_per_s": value / world, "weak_scaled": weak, "config3_single_gpu": c3_single,
+                "scaling_note": None if world == 1 else "strong scaling of configs[2]: compare with config3_single_gpu.value of the N=1 line (the same "
+                                "64-pair workload on one GPU); the N=1 headline `value` is configs[1] (arithmetic fusion, no per-batch setup in the "
+                                "timed region) and `weak_scaled.value` is its N-GPU counterpart",
                 "encoder_gflop_per_iter_image": 2 * fl["encoder_fwd_pair"] / 1e9}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -451,6 +500,7 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=4, help="resident batches in the timed end-to-end region (N = 1)")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3-line", action="store_true", help="N = 1: skip the single-GPU point of the N > 1 workload (configs[2])")
     ap.add_argument("--dump-launches", default=None, help="diagnostics: write per-launch conv timings + a per-kernel time table (JSON)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch every kernel eagerly instead of replaying the step / the e2e iterations from captured CUDA graphs")
