@@ -191,6 +191,50 @@ __global__ void __launch_bounds__(kBlock) conv_c3_bwd_kernel(const T* __restrict
 }
 
 // ============================================================================================
+// 3-channel image <-> 16-channel NHWC bf16 operand of the tensor-core conv (first conv of VGG / the encoder on tcgen05).
+// A bf16 copy of the image would lose the perturbation (2/255 steps against 2^-8 relative precision), so the image is split
+// x = hi + lo (both bf16, error 2^-17 relative) and the weights likewise; the 16 K-channels carry
+//   operand  [x.hi(3) | x.lo(3) | x.hi(3) | 0 x 7]     weights  [W.hi(3) | W.hi(3) | W.lo(3) | 0 x 7]
+// so that one K = 16 MMA per tap accumulates x.hi*W.hi + x.lo*W.hi + x.hi*W.lo in fp32 (the lo*lo term, 2^-18, is dropped).
+__global__ void c3_pack_kernel(const float* __restrict__ x, uint4* __restrict__ xp, int N, int HW) {
+  const long total = static_cast<long>(N) * HW;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = idx / HW, p = idx - n * HW;
+    const float* xb = x + n * 3 * HW + p;
+    float hi[3], lo[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __ldg(xb + static_cast<long>(c) * HW);
+      hi[c] = __bfloat162float(__float2bfloat16(v));
+      lo[c] = v - hi[c];
+    }
+    uint4 a, b;
+    a.x = pack2(hi[0], hi[1]);
+    a.y = pack2(hi[2], lo[0]);
+    a.z = pack2(lo[1], lo[2]);
+    a.w = pack2(hi[0], hi[1]);
+    b.x = pack2(hi[2], 0.f);
+    b.y = b.z = b.w = 0u;
+    xp[2 * idx] = a;
+    xp[2 * idx + 1] = b;
+  }
+}
+
+// gradient of the same operand back to the image: gx[n][c][p] = gp[n][p][c] + gp[n][p][3 + c]  (the W.hi and W.lo rows of the
+// transposed weights; fp32 sum of the two bf16 parts)
+__global__ void c3_unpack_kernel(const uint4* __restrict__ gp, float* __restrict__ gx, int N, int HW) {
+  const long total = static_cast<long>(N) * HW;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = idx / HW, p = idx - n * HW;
+    float f[8];
+    unpack8(__ldg(gp + 2 * idx), f);
+    float* gb = gx + n * 3 * HW + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gb[static_cast<long>(c) * HW] = f[c] + f[3 + c];
+  }
+}
+
+// ============================================================================================
 // pools
 __global__ void avgpool_affine_kernel(const float* __restrict__ x, float* __restrict__ y, long planes, int H, int W, int k,
                                       float a, float b) {
@@ -1727,6 +1771,20 @@ int sfk_conv_c3_bwd(const void* g, const float* w, float* gx, int n, int h, int 
     if (sfk_act_f32()) run(float{}); else run(bf16{});
   }
   return sfk_check_launch("conv_c3_bwd");
+}
+
+int sfk_c3_pack(const float* x, void* xp, int n, int h, int w, sfk_stream_t s) {
+  SFK_REQUIRE(x && xp && sfk_aligned16(xp) && n >= 1 && h >= 1 && w >= 1, SFK_E_ARG, "c3_pack: bad args");
+  SFK_REQUIRE(!sfk_act_f32(), SFK_E_ARG, "c3_pack: bf16 storage only (the fp32 parity mode runs sfk_conv_c3_fwd)");
+  c3_pack_kernel<<<grid_for(static_cast<long>(n) * h * w), kBlock, 0, S_(s)>>>(x, static_cast<uint4*>(xp), n, h * w);
+  return sfk_check_launch("c3_pack");
+}
+
+int sfk_c3_unpack(const void* gp, float* gx, int n, int h, int w, sfk_stream_t s) {
+  SFK_REQUIRE(gp && gx && sfk_aligned16(gp) && n >= 1 && h >= 1 && w >= 1, SFK_E_ARG, "c3_unpack: bad args");
+  SFK_REQUIRE(!sfk_act_f32(), SFK_E_ARG, "c3_unpack: bf16 storage only");
+  c3_unpack_kernel<<<grid_for(static_cast<long>(n) * h * w), kBlock, 0, S_(s)>>>(static_cast<const uint4*>(gp), gx, n, h * w);
+  return sfk_check_launch("c3_unpack");
 }
 
 int sfk_avgpool_affine_fwd(const float* x, float* y, int n_planes, int h, int w, int k, float a, float b, sfk_stream_t s) {

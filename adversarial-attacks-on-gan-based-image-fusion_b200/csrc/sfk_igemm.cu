@@ -625,7 +625,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                 tma_load_3d(smem_b + ((hf * a.num_cblk + cb) * a.num_taps + a.groups[g].bidx[j]) * a.b_tap_bytes, &a.mapB, &bres_bar,
                             cb * a.KC, a.groups[g].brow[j] + n0, bs + hf * a.b_samples);
       }
-      int ks = 0;
+      int stage = 0;           // ring slot and its phase advance incrementally (no division by the run-time stage count per k-step)
+      uint32_t phase = 0;
       const bool prof = (a.flags & SFK_EP_PROFILE) != 0;
       long long t_wait = 0;
       const long long t_start = clock64();
@@ -657,8 +658,6 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
 #pragma unroll
           for (int g = 0; g < kMaxGroups; ++g) {
             if (g < ngroups && ok) {
-              const int stage = ks % a.stages;
-              const uint32_t phase = (ks / a.stages) & 1;
               const long long tw0 = prof ? clock64() : 0;
               ok = mbar_wait(&empty_bar[stage], phase ^ 1, a.err);
               if (prof) t_wait += clock64() - tw0;
@@ -676,7 +675,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
                                 a.groups[g].brow[j] + n0, nb);
                 }
               }
-              ++ks;
+              if (++stage == a.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
             }
           }
         }
@@ -713,10 +715,13 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const int kpt = a.num_cblk * a.passes * a.num_groups;   // ring slots per tile
       const uint64_t m2_a16 = static_cast<uint64_t>((8 * a.TWB * a.row_bytes) >> 4);
       const uint32_t m2_col = static_cast<uint32_t>(a.num_acc * a.block_n);
+      // ring slot / phase of this warp's next k-step, advanced incrementally (the other issuer's tiles are skipped kpt slots at a time)
+      int stage = (par * kpt) % a.stages;
+      uint32_t phase = static_cast<uint32_t>((par * kpt) / a.stages) & 1u;
+      const int skip = (step - 1) * kpt;
       for (int it = par; blockIdx.x + it * static_cast<int>(gridDim.x) < tiles_per_group && ok; it += step) {
-        int ks = it * kpt;
-        const int as = it % a.acc_stages;
-        const uint32_t aph = (it / a.acc_stages) & 1;
+        const int as = a.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t aph = static_cast<uint32_t>(a.acc_stages == 2 ? (it >> 1) : it) & 1u;
         const long long ta0 = prof ? clock64() : 0;
         if (!mbar_wait(&tmem_empty_bar[as], aph ^ 1, a.err)) break;
         if (prof) t_wa += clock64() - ta0;
@@ -732,10 +737,8 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           const int cb = (a.passes == 3 && cbx >= 2 * a.num_cblk) ? cbx - a.num_cblk : (cbx % a.num_cblk);   // resident B slot: lo halves follow the hi ones
           const uint32_t part = kF32 ? static_cast<uint32_t>(cbx % ksplit) * tile_cols : 0u;
           int t0 = 0;
-          for (int g = 0; g < a.num_groups && ok; ++g, ++ks) {
+          for (int g = 0; g < a.num_groups && ok; ++g) {
             const int nt = a.groups[g].ntaps;
-            const int stage = ks % a.stages;
-            const uint32_t phase = (ks / a.stages) & 1;
             // gather every descriptor of this load group BEFORE the first MMA: operands of an in-flight tcgen05.mma stay
             // pinned in their (uniform) registers, so descriptors formed one tap at a time would serialise issue and execution
             uint64_t AD[kMaxGroupTaps], BD[kMaxGroupTaps];
@@ -782,10 +785,19 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             __syncwarp();
             if (leader) umma_commit(&empty_bar[stage]);
             t0 += nt;
+            if (++stage == a.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         __syncwarp();
         if (leader) umma_commit(&tmem_full_bar[as]);
+        stage += skip;
+        while (stage >= a.stages) {
+          stage -= a.stages;
+          phase ^= 1u;
+        }
       }
       if (prof && leader) {
         atomicAdd(&g_role_cycles[2], static_cast<unsigned long long>(t_wd));
@@ -845,9 +857,10 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       }
     };
     if (tile < tiles_per_group) noise4_at(t_h * a.TH + th, t_w * a.TW + tw);
+    const bool acc2 = a.acc_stages == 2;   // (acc_stages is 1 or 2: stage / phase without a division by a run-time value)
     for (int it = 0; tile < tiles_per_group; ++it) {
-      const int as = it % a.acc_stages;
-      const uint32_t aph = (it / a.acc_stages) & 1;
+      const int as = acc2 ? (it & 1) : 0;
+      const uint32_t aph = static_cast<uint32_t>(acc2 ? (it >> 1) : it) & 1u;
       int h = t_h * a.TH + th;
       const int w = t_w * a.TW + tw;
       bool valid = (tw < a.TW) && (h < a.out_h) && (w < a.out_w);
@@ -908,12 +921,15 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         if (!(flags & SFK_EP_DSCALE) && (flags & (SFK_EP_NOISE | SFK_EP_BIAS))) {
           const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
 #pragma unroll
-          for (int i = 0; i < NC / 4; ++i) {
+          const float2 nz2 = make_float2(nz, nz);
+          for (int i = 0; i < NC / 4; ++i) {   // packed fp32 (add.f32x2): half the issue slots of this issue/latency-bound loop
             const float4 bb = (flags & SFK_EP_BIAS) ? cb_[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * i + 0] += nz + bb.x;
-            v[4 * i + 1] += nz + bb.y;
-            v[4 * i + 2] += nz + bb.z;
-            v[4 * i + 3] += nz + bb.w;
+            const float2 r0 = __fadd2_rn(make_float2(v[4 * i + 0], v[4 * i + 1]), __fadd2_rn(nz2, make_float2(bb.x, bb.y)));
+            const float2 r1 = __fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), __fadd2_rn(nz2, make_float2(bb.z, bb.w)));
+            v[4 * i + 0] = r0.x;
+            v[4 * i + 1] = r0.y;
+            v[4 * i + 2] = r1.x;
+            v[4 * i + 3] = r1.y;
           }
         } else if (flags & (SFK_EP_DSCALE | SFK_EP_NOISE | SFK_EP_BIAS)) {
           const float4* cd = reinterpret_cast<const float4*>(col_dscale + c0);
@@ -936,8 +952,13 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
           for (int i = 0; i < NC; ++i) v[i] = lrelu_fwd(v[i]);
         }
         if (flags & SFK_EP_LRELU_RAW) {
+          const float2 k02 = make_float2(0.2f, 0.2f);
 #pragma unroll
-          for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);
+          for (int i = 0; i < NC; i += 2) {
+            const float2 m = __fmul2_rn(make_float2(v[i], v[i + 1]), k02);
+            v[i] = fmaxf(v[i], m.x);
+            v[i + 1] = fmaxf(v[i + 1], m.y);
+          }
         }
         if ((flags & SFK_EP_GSDOT) && reg_gs) {
           // c0 is 0 or 32 here (block_n <= 64, NC == 32 or the 16-wide path with c0 in {0,16,32,48})

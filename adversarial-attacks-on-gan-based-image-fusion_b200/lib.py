@@ -50,7 +50,7 @@ class SfkIgemmDesc(C.Structure):
 # every symbol include/sfk.h declares (tests/test_abi.py checks the .so exports all of them)
 EXPORTS = [
     "sfk_version", "sfk_set_activation_dtype", "sfk_get_activation_dtype", "sfk_last_error_string", "sfk_igemm", "sfk_igemm_prepare", "sfk_igemm_run", "sfk_igemm_destroy", "sfk_igemm_plan_info", "sfk_set_conv_math", "sfk_get_conv_math",
-    "sfk_igemm_workspace_bytes", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd",
+    "sfk_igemm_workspace_bytes", "sfk_igemm_v1", "sfk_role_cycles", "sfk_igemm_ref", "sfk_conv_c3_fwd", "sfk_conv_c3_bwd", "sfk_c3_pack", "sfk_c3_unpack",
     "sfk_avgpool_affine_fwd", "sfk_maxpool2_fwd", "sfk_maxpool2_bwd", "sfk_gap_fwd", "sfk_gap_bwd", "sfk_mse_tap",
     "sfk_mse_f32", "sfk_image_loss_grad", "sfk_style_affine_fwd", "sfk_style_affine_bwd", "sfk_demod_fwd", "sfk_demod_bwd",
     "sfk_modulate_weights", "sfk_demod_fwd_batched", "sfk_modulate_weights_batched", "sfk_demod_bwd_batched", "sfk_blur_act_fwd", "sfk_blur_act_bwd", "sfk_act_bwd", "sfk_torgb_fwd", "sfk_torgb_bwd", "sfk_act_torgb_bwd",
@@ -334,6 +334,33 @@ def conv_c3_fwd(x, w, bias, out, relu=True):
 def conv_c3_bwd(g, w, gx):
     n, _, h, wd = gx.shape
     _chk(load().sfk_conv_c3_bwd(_p(g), _p(w), _p(gx), n, h, wd, w.shape[0], _stream()), "conv_c3_bwd")
+
+
+def c3_pack(x, xp):
+    """x (n,3,h,w) fp32 -> xp (n,h,w,16) bf16 = [hi(3) | lo(3) | hi(3) | 0 x 7], the tensor-core operand of the first conv"""
+    n, _, h, wd = x.shape
+    _chk(load().sfk_c3_pack(_p(x), _p(xp), n, h, wd, _stream()), "c3_pack")
+
+
+def c3_unpack(gp, gx):
+    """gp (n,h,w,16) bf16 (data gradient of the packed operand) -> gx (n,3,h,w) fp32 = channels [0:3] + [3:6]"""
+    n, _, h, wd = gx.shape
+    _chk(load().sfk_c3_unpack(_p(gp), _p(gx), n, h, wd, _stream()), "c3_unpack")
+
+
+def c3_pack_weights(W: torch.Tensor):
+    """W (cout,3,3,3) fp32 -> (forward weights [9*cout][16], data-gradient weights [9*16][cout]) in bf16 for the packed operand:
+    forward K-channels [W.hi | W.hi | W.lo | 0]; gradient rows [W.hi^T (3) | W.lo^T (3) | 0 x 10] per tap."""
+    cout = W.shape[0]
+    W = W.to(torch.float32)
+    hi = W.bfloat16().float()
+    lo = (W - hi).bfloat16().float()
+    wf = torch.zeros(3, 3, cout, 16, dtype=torch.float32, device=W.device)
+    hik, lok = hi.permute(2, 3, 0, 1), lo.permute(2, 3, 0, 1)          # (ky,kx,cout,3)
+    wf[..., 0:3], wf[..., 3:6], wf[..., 6:9] = hik, hik, lok
+    wb = torch.zeros(3, 3, 16, cout, dtype=torch.float32, device=W.device)
+    wb[:, :, 0:3], wb[:, :, 3:6] = hi.permute(2, 3, 1, 0), lo.permute(2, 3, 1, 0)
+    return wf.reshape(9 * cout, 16).bfloat16().contiguous(), wb.reshape(9 * 16, cout).bfloat16().contiguous()
 
 
 def avgpool_affine_fwd(x, y, k, a=1.0, b=0.0):

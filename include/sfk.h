@@ -165,6 +165,14 @@ int sfk_conv_c3_fwd(const float* x /*[N][3][H][W]*/, const float* w /*[Cout][3][
 int sfk_conv_c3_bwd(const void* g /*bf16 NHWC*/, const float* w, float* gx /*[N][3][H][W]*/,
                     int n, int h, int w_, int cout, sfk_stream_t s);
 
+/* The same first conv on the tensor cores (bf16 storage): the 3-channel fp32 image becomes a 16-channel NHWC bf16 operand
+ * [x.hi(3) | x.lo(3) | x.hi(3) | 0 x 7] (x = hi + lo, both bf16) that sfk_igemm multiplies with weights laid out
+ * [W.hi(3) | W.hi(3) | W.lo(3) | 0 x 7] per tap (fp32-class products, one K = 16 MMA per tap); the data gradient comes back
+ * from sfk_igemm as 16 bf16 channels [g.W.hi(3) | g.W.lo(3) | ...] that sfk_c3_unpack sums into gx [N][3][H][W] fp32.
+ * code/vgg.py:45 (conv1_1) and the encoder's first conv. */
+int sfk_c3_pack(const float* x /*[N][3][H][W]*/, void* xp /*bf16 [N][H][W][16]*/, int n, int h, int w, sfk_stream_t s);
+int sfk_c3_unpack(const void* gp /*bf16 [N][H][W][16]*/, float* gx /*[N][3][H][W]*/, int n, int h, int w, sfk_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * Pools.  F.avg_pool2d(img, k, k) (attack_main2.py:590-591,619-624) fused with y = a*pool(x)+b;
  * nn.MaxPool2d(2,2[,ceil_mode]) (code/vgg.py:14,18,24). */

@@ -272,6 +272,52 @@ def test_conv_c3_fwd_bwd(n, h, w, cout):
     _close(gx, gx_ref, rtol=1e-4, what="conv_c3_bwd")
 
 
+@pytest.mark.parametrize("n,h,w,cout", [(2, 20, 24, 64), (1, 33, 17, 32), (2, 64, 64, 16)])
+def test_conv_c3_tensor_core_path(n, h, w, cout):
+    """First conv on the tensor cores (sfk_c3_pack -> sfk_igemm with hi/lo-split image and weights -> sfk_c3_unpack) against
+    torch fp32: the hi/lo split must keep a 1/255-scale perturbation of the image visible (a plain bf16 copy would not)."""
+    from sfattack import lib
+    g = _gen(14)
+    x = (torch.rand(n, 3, h, w, generator=g, device=_dev()) * 2 - 1).requires_grad_(True)
+    wt = torch.randn(cout, 3, 3, 3, generator=g, device=_dev()) * 0.2
+    b = torch.randn(cout, generator=g, device=_dev()) * 0.1
+    wf, wb = lib.c3_pack_weights(wt)
+    err = torch.zeros(1, dtype=torch.int32, device=_dev())
+
+    def fwd(xin, relu):
+        xp = torch.empty(n, h, w, 16, device=_dev(), dtype=torch.bfloat16)
+        out = torch.full((n, h, w, cout), float("nan"), device=_dev(), dtype=torch.bfloat16)
+        lib.c3_pack(xin, xp)
+        d = lib.make_igemm_desc(xp, n, h, w, 16, 1, wf, 1, 9 * cout, out, h, w, cout, 1, lib.pick_block_n(cout), lib.conv3x3_taps(cout),
+                                flags=lib.EP_BIAS | (lib.EP_RELU if relu else 0), bias=b, err=err)
+        lib.igemm(d)
+        torch.cuda.synchronize()
+        assert err.item() == 0
+        return out
+
+    ref = F.conv2d(x, wt, b, padding=1)
+    _close(_nchw(fwd(x.detach(), True)), ref.detach().relu(), what="c3 tensor-core fwd")
+    # a perturbation of 1/255 per pixel: the packed operand must carry it to fp32 accuracy (checked on the pre-activation, which the
+    # bf16 OUTPUT rounds to 2^-9 -- so compare the operand itself)
+    delta = (torch.rand(n, 3, h, w, generator=g, device=_dev()) - 0.5) * (2.0 / 255)
+    xp = torch.empty(n, h, w, 16, device=_dev(), dtype=torch.bfloat16)
+    lib.c3_pack((x.detach() + delta).contiguous(), xp)
+    rec = (xp[..., 0:3].float() + xp[..., 3:6].float()).permute(0, 3, 1, 2)
+    assert (rec - (x.detach() + delta)).abs().max().item() < 2e-5
+    assert torch.equal(xp[..., 0:3], xp[..., 6:9]) and xp[..., 9:].abs().max().item() == 0
+    # data gradient
+    gpre = _rb(n, cout, h, w, g=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gpre)
+    gp = torch.full((n, h, w, 16), float("nan"), device=_dev(), dtype=torch.bfloat16)
+    d = lib.make_igemm_desc(_nhwc(gpre), n, h, w, cout, 1, wb, 1, 9 * 16, gp, h, w, 16, 1, 16, lib.conv3x3_dgrad_taps(16), err=err)
+    lib.igemm(d)
+    gx = torch.empty(n, 3, h, w, device=_dev())
+    lib.c3_unpack(gp, gx)
+    torch.cuda.synchronize()
+    assert err.item() == 0
+    _close(gx, gx_ref, rtol=BF16_RTOL, what="c3 tensor-core dgrad")     # the gradient leaves the conv kernel in bf16
+
+
 @pytest.mark.parametrize("h,w", [(16, 16), (9, 7)])
 def test_maxpool_fwd_bwd(h, w):
     from sfattack import lib
