@@ -34,16 +34,21 @@ class AttackCfg:
                                   # launches per iteration); not for adam (its bias correction is a per-iteration host scalar)
 
 
-def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: AttackCfg, start_noise: Optional[torch.Tensor] = None,
+def run_attack(eng: AttackEngine, xa, xb: Optional[torch.Tensor], cfg: AttackCfg, start_noise: Optional[torch.Tensor] = None,
                target: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, mask: Optional[torch.Tensor] = None,
                patch0: Optional[torch.Tensor] = None, compute_final: bool = True, record: Optional[list] = None,
                seed: Optional[int] = None):
-    """xa, xb: (B,3,S,S) in [0,1] on the engine's device.  Returns dict(x_adv, fused_adv, fused_ref, losses, [patch]).
+    """xa, xb: (B,3,S,S) in [0,1] on the engine's device (N-way fusion: xa = list of the engine's n_inputs tensors, xb = None;
+    x_adv then holds input k in rows [k*B:(k+1)*B]).  Returns dict(x_adv, fused_adv, fused_ref, losses, [patch]).
     Random start (interpolation.py:74-76): from `start_noise` (U(-1,1) values supplied by the caller: what the parity tests share
     with the oracle) or, when `seed` is given, drawn on the device by sfk_attack_random_start."""
     B, dev = eng.B, eng.dev
     direction = -1.0 if cfg.targeted else 1.0
-    eng.set_inputs(xa, xb)
+    NB = eng.x.shape[0]          # images in the shard: n_inputs * B (pairs: 2B)
+    if xb is None:               # N-way fusion: xa is the list of the N inputs
+        eng.set_inputs(*xa)
+    else:
+        eng.set_inputs(xa, xb)
     eng.compute_reference(target if cfg.targeted else None)
     k = eng.k_in
     gscale = 2.0 / (k * k)
@@ -53,8 +58,8 @@ def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: Attac
         # single initial patch is replicated, the copies then evolve independently (a shared, all-reduced patch is SURVEY 8f-4)
         patch = patch0.to(dev).expand_as(eng.x).clone().contiguous()
         mask = mask.to(dev).expand_as(eng.x).contiguous()
-        lo = torch.empty(2 * B, device=dev)
-        hi = torch.empty(2 * B, device=dev)
+        lo = torch.empty(NB, device=dev)
+        hi = torch.empty(NB, device=dev)
         lib.minmax_per_sample(eng.x0, lo, hi)
         # adv_x = (1-mask)*img + mask*patch, clamped to the clean range (adversarial_patch.py:106,137-138): a zero-step update
         zero_g = torch.zeros_like(eng.g_xin)
@@ -67,8 +72,8 @@ def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: Attac
         m = torch.zeros_like(eng.x)
         v = torch.zeros_like(eng.x)
     if cfg.kind == "l2":
-        norms = torch.zeros(2 * B, device=dev)
-        dn = torch.zeros(2 * B, device=dev)
+        norms = torch.zeros(NB, device=dev)
+        dn = torch.zeros(NB, device=dev)
     def iteration(it):
         loss, g = eng.forward_backward()
         if record is not None:      # diagnostics only (forces clones; never used by the benchmark)
@@ -92,7 +97,7 @@ def run_attack(eng: AttackEngine, xa: torch.Tensor, xb: torch.Tensor, cfg: Attac
     # once (after an eager first iteration has run every kernel's one-time setup) and replayed.  The Linf body only touches
     # engine-owned buffers, so its graph is cached on the engine and reused by later calls with the same step parameters; the
     # L2 / patch bodies use per-call buffers (norms, patch, mask), so they capture per call and only when the run is long.
-    use_graph = cfg.graph and record is None and cfg.steps > 2 and (cfg.kind == "linf" or (cfg.kind in ("l2", "patch") and cfg.steps >= 20))
+    use_graph = cfg.graph and getattr(eng, "graph_ok", True) and record is None and cfg.steps > 2 and (cfg.kind == "linf" or (cfg.kind in ("l2", "patch") and cfg.steps >= 20))
     cache = eng.__dict__.setdefault("_iter_graphs", {}) if cfg.kind == "linf" else {}
     key = (cfg.kind, float(cfg.alpha), float(cfg.eps), direction)
     graph = cache.get(key) if use_graph else None
@@ -127,6 +132,7 @@ def run_attack_stream(eng: AttackEngine, batches, cfg: AttackCfg, seed: int = 0,
     gather_into: optional DEVICE tensor (len(batches)*2B,3,S,S) that also receives every batch's adversarial pairs (the operand of
     the final all-gather across ranks, parallel.gather_results)."""
     assert cfg.kind in ("linf", "l2"), "run_attack_stream: linf / l2 attacks"
+    assert getattr(eng, "NI", 2) == 2, "run_attack_stream: pairs (use run_attack for N-way fusion)"
     B, dev = eng.B, eng.dev
     S = eng.S
     nb = len(batches)
@@ -214,9 +220,10 @@ def _attack_resident(eng: AttackEngine, cfg: AttackCfg, seed: int) -> torch.Tens
 
     cache = eng.__dict__.setdefault("_iter_graphs", {})
     gkey = (cfg.kind, float(cfg.alpha), float(cfg.eps), 1.0)
-    graph = cache.get(gkey) if cfg.graph else None
+    use_graph = cfg.graph and getattr(eng, "graph_ok", True)
+    graph = cache.get(gkey) if use_graph else None
     for it in range(cfg.steps):
-        if cfg.graph and (it >= 1 or graph is not None):
+        if use_graph and (it >= 1 or graph is not None):
             if graph is None:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, capture_error_mode="thread_local"):

@@ -520,11 +520,27 @@ class AttackEngine:
     """One data-parallel shard of the attack: B independent pairs resident in HBM."""
 
     def __init__(self, gspec: GenSpec, GP, espec: EncSpec, EP, vgg_sd, FP=None, fusion: str = "arithmetic", batch: int = 1,
-                 device="cuda:0", loss: Optional[LossCfg] = None, vgg_res: int = 256, vgg_width_div: int = 1):
+                 device="cuda:0", loss: Optional[LossCfg] = None, vgg_res: int = 256, vgg_width_div: int = 1,
+                 encoder_module: Optional[torch.nn.Module] = None, latent_avg: Optional[torch.Tensor] = None,
+                 n_inputs: int = 2, hierarchy: Optional[dict] = None):
+        """n_inputs: images fused into one output (2 = the pairs of BASELINE.json; 5 / 4 / 3 = the reference's ffhq / car / church
+        fusion, attack_main2.py:521-581).  fusion: "arithmetic" (mean of the N inputs' W+ codes, interpolation.py:661), "spatial"
+        (pair gate) or "hierarchy" (N-way: `hierarchy` = dict(parts=[part names in hierarchy order], source=[input index
+        per part], gates={part: dict(alpha, beta, c)}), the s_dict of generate_img (style_fusion_simple.py:84-104) blended by the
+        chain of per-part gates that stands in for base_blender.forward (:164); see StyleFusionSimple.hierarchy_for()).
+        Rows [k*B:(k+1)*B] of every per-input buffer (x, x0, xin, g_xin, codes ...) belong to input k.
+        encoder_module: any torch module `x (n,3,R,R) in [-1,1] -> codes (n, n_latent, 512)` (or (n,512)) that takes the place of the
+        encoder stand-in on the gradient path -- e.g. the reference's `net.encoder` = e4e `Encoder4Editing(50,'ir_se')`
+        (code/utils/model_utils.py:24; un-vendored upstream).  Its forward and backward run through torch autograd on
+        the engine's stream; everything downstream (fusion, synthesis, VGG, update) stays on the CUDA schedules.  `latent_avg`
+        (n_latent,512) is added to its codes as get_latents does (attack_main2.py:137-146).  EP is then only read for nothing and
+        may be None; CUDA-graph replay is off for such an engine (autograd allocates)."""
         lib.load()
         self.dev = torch.device(device)
         self.gspec, self.espec, self.fusion, self.B = gspec, espec, fusion, batch
         self.loss_cfg = loss or LossCfg()
+        self.NI = NI = int(n_inputs)
+        assert NI >= 2 and (fusion != "spatial" or NI == 2) and (fusion != "hierarchy" or hierarchy is not None)
         B, dev = batch, self.dev
         S, R = gspec.size, espec.in_res
         self.S, self.R, self.k_in = S, R, S // R
@@ -532,24 +548,50 @@ class AttackEngine:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         # encoder
-        enc_w = [(EP[f"convs.{i}.weight"], EP[f"convs.{i}.bias"]) for i in range(len(espec.widths))]
-        self.enc = ConvStack(encoder_layers(espec), enc_w, 2 * B, R, dev, self.err)
-        self.head_w = f32(EP["head.weight"])
-        self.head_b = f32(EP["head.bias"] + EP["latent_avg"].reshape(-1))     # get_latents adds latent_avg (attack_main2.py:137-146)
+        self.enc_module = encoder_module
+        self.graph_ok = encoder_module is None
+        if encoder_module is None:
+            enc_w = [(EP[f"convs.{i}.weight"], EP[f"convs.{i}.bias"]) for i in range(len(espec.widths))]
+            self.enc = ConvStack(encoder_layers(espec), enc_w, NI * B, R, dev, self.err)
+            self.head_w = f32(EP["head.weight"])
+            self.head_b = f32(EP["head.bias"] + EP["latent_avg"].reshape(-1))     # get_latents adds latent_avg (attack_main2.py:137-146)
+        else:
+            self.enc = None
+            self.enc_latent_avg = f32(latent_avg) if latent_avg is not None else None
+            for p_ in encoder_module.parameters():      # the attack differentiates w.r.t. the pixels only
+                p_.requires_grad_(False)
         cl = espec.widths[-1]
         LD = espec.n_latent * espec.style_dim
-        self.feat = _empty((2 * B, cl), dev, torch.float32)
-        self.gfeat = _empty((2 * B, cl), dev, torch.float32)
-        self.codes = _empty((2 * B, espec.n_latent, espec.style_dim), dev, torch.float32)
-        self.gcodes = _empty((2 * B, espec.n_latent, espec.style_dim), dev, torch.float32)
+        self.feat = _empty((NI * B, cl), dev, torch.float32)
+        self.gfeat = _empty((NI * B, cl), dev, torch.float32)
+        self.codes = _empty((NI * B, espec.n_latent, espec.style_dim), dev, torch.float32)
+        self.gcodes = _empty((NI * B, espec.n_latent, espec.style_dim), dev, torch.float32)
         self.w = _empty((B, espec.n_latent, espec.style_dim), dev, torch.float32)
         self.gw = _empty((B, espec.n_latent, espec.style_dim), dev, torch.float32)
         # synthesis
         self.syn = SynthesisEngine(gspec, GP, B, dev, self.err)
         if fusion == "spatial":
             self.FP = {k: f32(v) for k, v in FP.items()}
-            self.s_all = _empty((2 * B, gspec.s_dim), dev, torch.float32)
-            self.gs_all = _empty((2 * B, gspec.s_dim), dev, torch.float32)
+        if fusion in ("spatial", "hierarchy"):
+            self.s_all = _empty((NI * B, gspec.s_dim), dev, torch.float32)
+            self.gs_all = _empty((NI * B, gspec.s_dim), dev, torch.float32)
+        if fusion == "hierarchy":
+            # out = s[source of parts[0]]; every later part whose input differs from what `out` holds gates it in:
+            # out <- q*out + (1-q)*s_part, q = sigmoid(alpha*out + beta*s_part + c)  (oracle/fusion_ref.py blend()).  A part assigned
+            # to the base input is skipped only while nothing has been gated in yet (its style vector then EQUALS out).
+            parts, source = list(hierarchy["parts"]), [int(k) for k in hierarchy["source"]]
+            assert len(parts) == len(source) and all(0 <= k < NI for k in source)
+            self.h_base = source[0]
+            self.h_chain = []
+            for p_, k in zip(parts[1:], source[1:]):
+                if not self.h_chain and k == self.h_base:
+                    continue
+                gate = hierarchy["gates"][p_]
+                self.h_chain.append(dict(part=p_, src=k, alpha=f32(gate["alpha"]), beta=f32(gate["beta"]), c=f32(gate["c"])))
+            nch = len(self.h_chain)
+            self.h_mid = [_empty((B, gspec.s_dim), dev, torch.float32) for _ in range(max(nch - 1, 0))]   # outputs of gates 0..n-2
+            self.h_ga = [_empty((B, gspec.s_dim), dev, torch.float32) for _ in range(2)]
+            self.h_gb = _empty((B, gspec.s_dim), dev, torch.float32)
         # loss network
         from .params import VGG_EXECUTED
         vals = list(vgg_sd.values())
@@ -561,38 +603,69 @@ class AttackEngine:
         self.g_img = _empty((B, 3, S, S), dev, torch.float32)
         self.loss = _zeros((B,), dev)
         if self.loss_cfg.c_reg != 0.0:
-            self.vgg_reg = ConvStack(vgg_layers(vgg_width_div), vgg_w, 2 * B, R, dev, self.err)
+            self.vgg_reg = ConvStack(vgg_layers(vgg_width_div), vgg_w, NI * B, R, dev, self.err)
             self.reg_refs = [torch.empty_like(t) for t in self.vgg_reg.tap_outputs()]
-            self.reg_loss = _zeros((2 * B,), dev)
+            self.reg_loss = _zeros((NI * B,), dev)
         # attack state
-        self.x = _empty((2 * B, 3, S, S), dev, torch.float32)
-        self.x0 = _empty((2 * B, 3, S, S), dev, torch.float32)
-        self.xin = _empty((2 * B, 3, R, R), dev, torch.float32)
-        self.g_xin = _empty((2 * B, 3, R, R), dev, torch.float32)
-        self.stats = _zeros((2 * B,), dev)
+        self.x = _empty((NI * B, 3, S, S), dev, torch.float32)
+        self.x0 = _empty((NI * B, 3, S, S), dev, torch.float32)
+        self.xin = _empty((NI * B, 3, R, R), dev, torch.float32)
+        self.g_xin = _empty((NI * B, 3, R, R), dev, torch.float32)
+        self.stats = _zeros((NI * B,), dev)
 
     # ---------------------------------------------------------------------------------------
     @_on_device
-    def set_inputs(self, xa: torch.Tensor, xb: torch.Tensor):
+    def set_inputs(self, *xs: torch.Tensor):
+        """the N inputs, each (B,3,S,S) in [0,1] (a single list / tuple of them is accepted too)"""
+        if len(xs) == 1 and isinstance(xs[0], (list, tuple)):
+            xs = tuple(xs[0])
         B = self.B
-        self.x0[:B].copy_(xa)
-        self.x0[B:].copy_(xb)
+        assert len(xs) == self.NI, f"engine fuses {self.NI} inputs, got {len(xs)}"
+        for k, xk in enumerate(xs):
+            self.x0[k * B:(k + 1) * B].copy_(xk)
         self.x.copy_(self.x0)
+
+    def _rows(self, t: torch.Tensor, k: int) -> torch.Tensor:
+        return t[k * self.B:(k + 1) * self.B]
 
     def _encode(self):
         lib.avgpool_affine_fwd(self.x, self.xin, self.k_in, 2.0, -1.0)
+        if self.enc_module is not None:
+            self._xin_leaf = self.xin.detach().requires_grad_(True)
+            with torch.enable_grad():
+                codes = self.enc_module(self._xin_leaf)
+            if codes.ndim == 2:                                               # (n,512): one w for every layer (style_fusion_simple.py:139-141)
+                codes = codes.unsqueeze(1).expand(-1, self.espec.n_latent, -1)
+            self._codes_t = codes
+            c = codes.detach().to(torch.float32)
+            self.codes.copy_(c + self.enc_latent_avg[None] if self.enc_latent_avg is not None else c)
+            return
         top = self.enc.forward(self.xin)
         lib.gap_fwd(top, self.feat)
-        lib.linear_fwd(self.feat, self.head_w, self.head_b, self.codes.view(2 * self.B, -1))
+        lib.linear_fwd(self.feat, self.head_w, self.head_b, self.codes.view(self.NI * self.B, -1))
 
     def _fuse(self):
-        B = self.B
+        B, NI = self.B, self.NI
         if self.fusion == "arithmetic":
-            lib.axpby(self.codes[:B], self.codes[B:], self.w, 0.5, 0.5)       # interpolation.py:661
+            r = 1.0 / NI
+            lib.axpby(self._rows(self.codes, 0), self._rows(self.codes, 1), self.w, r, r)       # interpolation.py:661 (mean over the inputs)
+            for k in range(2, NI):
+                lib.axpby(self.w, self._rows(self.codes, k), self.w, 1.0, r)
             self.syn.styles_from_wplus(self.w)
-        else:
+        elif self.fusion == "spatial":
             self.syn.styles_from_wplus(self.codes, self.s_all)
             lib.fuse_spatial_fwd(self.s_all[:B], self.s_all[B:], self.FP["alpha"], self.FP["beta"], self.FP["c"], self.syn.s)
+        else:
+            self.syn.styles_from_wplus(self.codes, self.s_all)
+            cur = self._rows(self.s_all, self.h_base)
+            n = len(self.h_chain)
+            for j, gte in enumerate(self.h_chain):
+                dst = self.syn.s if j == n - 1 else self.h_mid[j]
+                gte["in"] = cur
+                lib.fuse_spatial_fwd(cur, self._rows(self.s_all, gte["src"]), gte["alpha"], gte["beta"], gte["c"], dst)
+                cur = dst
+            if n == 0:
+                self.syn.s.copy_(cur)
 
     @_on_device
     def fused_forward(self) -> torch.Tensor:
@@ -611,8 +684,8 @@ class AttackEngine:
         B = self.B
         keep = self.x.clone()
         if target is not None:
-            self.x[:B].copy_(target[0])
-            self.x[B:].copy_(target[1])
+            for k in range(self.NI):
+                self._rows(self.x, k).copy_(target[k])
         else:
             self.x.copy_(self.x0)
         img = self.fused_forward()
@@ -644,26 +717,47 @@ class AttackEngine:
         # synthesis backward -> style gradient
         gs = self.syn.backward(self.g_img)
         # fusion backward -> latent gradients of both inputs
+        NI = self.NI
         if self.fusion == "arithmetic":
             self.syn.wplus_grad_from_styles(gs, self.gw)
-            lib.axpby(self.gw, None, self.gcodes[:B], 0.5)
-            lib.axpby(self.gw, None, self.gcodes[B:], 0.5)
-        else:
+            for k in range(NI):
+                lib.axpby(self.gw, None, self._rows(self.gcodes, k), 1.0 / NI)
+        elif self.fusion == "spatial":
             lib.fuse_spatial_bwd(self.s_all[:B], self.s_all[B:], self.FP["alpha"], self.FP["beta"], self.FP["c"], gs,
                                  self.gs_all[:B], self.gs_all[B:])
             self.syn.wplus_grad_from_styles(self.gs_all, self.gcodes)
+        else:
+            # the gate chain backwards: the gradient of each gate's second operand accumulates on its input's style vector, the
+            # gradient of the first operand walks on down the chain and ends on the base input
+            self.gs_all.zero_()
+            g = gs
+            for j in range(len(self.h_chain) - 1, -1, -1):
+                gte = self.h_chain[j]
+                ga = self.h_ga[j % 2]
+                lib.fuse_spatial_bwd(gte["in"], self._rows(self.s_all, gte["src"]), gte["alpha"], gte["beta"], gte["c"], g, ga, self.h_gb)
+                dst = self._rows(self.gs_all, gte["src"])
+                lib.axpby(dst, self.h_gb, dst, 1.0, 1.0)
+                g = ga
+            dst = self._rows(self.gs_all, self.h_base)
+            lib.axpby(dst, g, dst, 1.0, 1.0)
+            self.syn.wplus_grad_from_styles(self.gs_all, self.gcodes)
         # encoder backward
-        lib.linear_bwd(self.gcodes.view(2 * B, -1), self.head_w, self.gfeat)
-        lib.gap_bwd(self.enc.out[-1], self.gfeat, self.enc.g[-1])
-        g_xin = self.enc.backward(top_grad_ready=True)
+        if self.enc_module is not None:
+            (g_xin,) = torch.autograd.grad(self._codes_t, self._xin_leaf, self.gcodes.to(self._codes_t.dtype))
+            g_xin = g_xin.to(torch.float32).contiguous()
+            self._codes_t = None
+        else:
+            lib.linear_bwd(self.gcodes.view(NI * B, -1), self.head_w, self.gfeat)
+            lib.gap_bwd(self.enc.out[-1], self.gfeat, self.enc.g[-1])
+            g_xin = self.enc.backward(top_grad_ready=True)
         if cfg.c_reg != 0.0:
             # perceptual regulariser on the adversarial inputs themselves (config 5): L -= c_reg * sum_taps MSE
             self.reg_loss.zero_()
             self.vgg_reg.forward(self.xin)
             g_reg = self.vgg_reg.backward(self.reg_refs, -cfg.c_reg, self.reg_loss)
             lib.axpby(g_xin, g_reg, self.g_xin, 1.0, 1.0)
-            lib.axpby(self.reg_loss[:B], self.reg_loss[B:], self.reg_loss[:B], 1.0, 1.0)
-            lib.axpby(self.loss, self.reg_loss[:B], self.loss, 1.0, 1.0)
+            for k in range(NI):
+                lib.axpby(self.loss, self._rows(self.reg_loss, k), self.loss, 1.0, 1.0)
         else:
             self.g_xin.copy_(g_xin)
         return self.loss, self.g_xin

@@ -22,6 +22,37 @@ _PARTS = {   # get_all_active_parts() of the three hierarchies (code/style_fusio
 }
 
 
+def part_sources(parts: List[str], base: int, hair=None, face=None, background=None, all=None, mouth=None, eyes=None, wheels=None,
+                 car=None, bg_top=None, bg_bottom=None) -> List[int]:
+    """The s_dict of generate_img (code/style_fusion_simple.py:84-104) with input indices in place of style tensors: every part
+    starts on `base`, then the keyword roles overwrite their part lists in the reference's order (later swaps win)."""
+    src = {p_: base for p_ in parts}
+    for value, keys in ((hair, ["bg_hair_clothes", "hair"]), (face, ["face", "eyes", "skin_mouth", "mouth", "skin", "shirt"]),
+                        (background, ["background", "background_top", "background_bottom", "bg"]), (all, ["all"]),
+                        (mouth, ["skin_mouth", "face"]), (eyes, ["eyes", "face"]), (wheels, ["wheels"]),
+                        (car, ["car", "body", "wheels", "car_body"]), (bg_top, ["background_top"]), (bg_bottom, ["background_bottom"])):
+        if value is not None:
+            for k in keys:
+                if k in src:
+                    src[k] = value
+    return [src[p_] for p_ in parts]
+
+
+def fusion_hierarchy(dataset_name: str, parts: List[str], gates: Dict[str, dict]) -> dict:
+    """Role assignment of `fusion()` (code/attack/attack_main2.py:521-581) as the attack engine's `hierarchy` argument: ffhq inputs
+    [mouth, background, hair, eyes, global] (:526), car [wheel, bg_top, bg_bottom, body] (:547), church [bg_top, bg_bottom, body]
+    (:566); the LAST input is the base; names are matched by substring as upstream."""
+    if "ffhq" in dataset_name:
+        source, n = part_sources(parts, 4, hair=2, eyes=3, background=1, mouth=0), 5
+    elif "car" in dataset_name:
+        source, n = part_sources(parts, 3, wheels=0, bg_top=1, bg_bottom=2), 4
+    elif "church" in dataset_name:
+        source, n = part_sources(parts, 2, bg_top=0, bg_bottom=1), 3
+    else:
+        raise ValueError(f"unknown dataset {dataset_name!r} (expected a name containing ffhq / car / church)")
+    return dict(parts=list(parts), source=source, gates=gates, n_inputs=n)
+
+
 class _Node:
     """One node of the hierarchy (stand-in for a `stylefusion.sf_hierarchy` node): its FusionNet is the per-dimension
     gate q = sigmoid(alpha*s_a + beta*s_b + c), s = q*s_a + (1-q)*s_b that blends this part's StyleSpace vector into the running
@@ -140,6 +171,18 @@ class StyleFusionSimple:
         swap(bg_top, ["background_top"])
         swap(bg_bottom, ["background_bottom"])
         return self.s_dict_to_image(s_dict)
+
+    # ---- the same part assignment with input INDICES instead of style tensors: what the attack engine's N-way gradient path needs
+    def part_sources(self, base: int, **roles) -> List[int]:
+        """generate_img's s_dict (:84-104) as a list: for every active part, the index of the input whose style vector it holds."""
+        return part_sources(self.sf_hierarchy.nodes["all"].get_all_active_parts(), base, **roles)
+
+    def fusion_hierarchy(self, dataset_name: str) -> dict:
+        """`AttackEngine(..., fusion="hierarchy", n_inputs=N, hierarchy=...)` argument for the role assignment of `fusion()`
+        (code/attack/attack_main2.py:521-581); the gates are this model's FusionNet stand-ins."""
+        parts = self.sf_hierarchy.nodes["all"].get_all_active_parts()
+        gates = {p_: self.sf_hierarchy.nodes[p_].fusion_net.p for p_ in parts if p_ != "all"}
+        return fusion_hierarchy(dataset_name, parts, gates)
 
     def seed_to_z(self, seed):                                                                             # :110-113
         torch.manual_seed(seed[0])

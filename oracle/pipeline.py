@@ -83,10 +83,14 @@ class OraclePipeline:
     """Everything the hot loop evaluates, as plain autograd-able torch code."""
 
     def __init__(self, gspec: GenSpec, GP, espec: EncSpec, EP, vgg_sd, FP=None, fusion: str = "arithmetic",
-                 vgg_res: int = 256):
+                 vgg_res: int = 256, encoder_module=None, latent_avg=None):
         self.gspec, self.GP, self.espec, self.EP, self.vgg_sd, self.FP = gspec, GP, espec, EP, vgg_sd, FP
         self.fusion = fusion
         self.vgg_res = vgg_res
+        # N-way hierarchy fusion (SURVEY 8f-3): hier = dict(parts=[...], source=[input index per part], gates={part: {alpha,beta,c}})
+        self.hier = None
+        # any torch module in the encoder's place (`net.encoder` of the reference, code/utils/model_utils.py:24) + latent_avg
+        self.encoder_module, self.latent_avg = encoder_module, latent_avg
 
     # pixels in [0,1] -> [-1,1], box-pool to the encoder resolution (attack_main2.py:590-591,619)
     def pool_in(self, x01: torch.Tensor) -> torch.Tensor:
@@ -95,18 +99,28 @@ class OraclePipeline:
         return F.avg_pool2d(x, k, k) if k > 1 else x
 
     def latents(self, x01):
+        if self.encoder_module is not None:                     # get_latents, code/attack/attack_main2.py:137-146
+            codes = self.encoder_module(self.pool_in(x01))
+            if codes.ndim == 2:
+                codes = codes.unsqueeze(1).expand(-1, self.espec.n_latent, -1)
+            return codes + self.latent_avg[None] if self.latent_avg is not None else codes
         return get_latents(self.EP, self.espec, self.pool_in(x01))
 
-    def styles(self, w_a, w_b):
-        if self.fusion == "arithmetic":
-            return sg.styles_from_wplus(self.GP, self.gspec, fuse_arithmetic(w_a, w_b))
-        s_a = cat_styles(sg.styles_from_wplus(self.GP, self.gspec, w_a))
-        s_b = cat_styles(sg.styles_from_wplus(self.GP, self.gspec, w_b))
-        return split_styles(self.gspec, fuse_spatial(self.FP, s_a, s_b))
+    def styles(self, *ws):
+        if self.fusion == "arithmetic":      # mean of the N inputs' W+ codes (interpolation.py:661)
+            return sg.styles_from_wplus(self.GP, self.gspec, sum(ws) / float(len(ws)))
+        ss = [cat_styles(sg.styles_from_wplus(self.GP, self.gspec, w)) for w in ws]
+        if self.fusion == "hierarchy":
+            # generate_img's s_dict (code/style_fusion_simple.py:84-104: every part holds the style vector of the input assigned to
+            # it) -> base_blender.forward(s_dict) (:164), restated as the chain of per-part gates of oracle/fusion_ref.py
+            from .fusion_ref import blend
+            h = self.hier
+            return split_styles(self.gspec, blend(h["parts"], h["gates"], {p: ss[k] for p, k in zip(h["parts"], h["source"])}))
+        return split_styles(self.gspec, fuse_spatial(self.FP, ss[0], ss[1]))
 
-    def fused(self, xa01, xb01):
-        """fused image (B,3,S,S), roughly [-1,1]"""
-        return sg.synthesis_from_styles(self.GP, self.gspec, self.styles(self.latents(xa01), self.latents(xb01)))
+    def fused(self, *xs01):
+        """fused image (B,3,S,S), roughly [-1,1], of the N inputs (each (B,3,S,S) in [0,1])"""
+        return sg.synthesis_from_styles(self.GP, self.gspec, self.styles(*[self.latents(x) for x in xs01]))
 
     def pool_vgg(self, img):
         k = img.shape[-1] // self.vgg_res
@@ -118,6 +132,24 @@ class OraclePipeline:
     def reference_of(self, img) -> Tuple[torch.Tensor, tuple]:
         with torch.no_grad():
             return img.detach(), tuple(f.detach() for f in self.features(img))
+
+    def loss_n(self, xs01, ref_img, ref_feats, cfg: LossCfg, reg_refs=None):
+        """N-input form of loss(): per-sample loss (B,) and the fused image."""
+        img = self.fused(*xs01)
+        L = cfg.c_pix * per_sample_mse(img, ref_img)
+        if cfg.c_feat != 0.0:
+            for f, r in zip(self.features(img), ref_feats):
+                L = L + cfg.c_feat * per_sample_mse(f, r)
+        if cfg.c_reg != 0.0:
+            for x, refs in zip(xs01, reg_refs):
+                for f, r in zip(vgg_forward(self.vgg_sd, self.pool_in(x)), refs):
+                    L = L - cfg.c_reg * per_sample_mse(f, r)
+        return L, img
+
+    def input_grads_n(self, xs01, ref_img, ref_feats, cfg: LossCfg, reg_refs=None):
+        xs = [x.detach().clone().requires_grad_(True) for x in xs01]
+        L, img = self.loss_n(xs, ref_img, ref_feats, cfg, reg_refs=reg_refs)
+        return L.detach(), img.detach(), list(torch.autograd.grad(L.sum(), xs))
 
     def loss(self, xa01, xb01, ref_img, ref_feats, cfg: LossCfg, xa_clean=None, xb_clean=None, reg_refs=None):
         """per-sample loss (B,) and the fused image."""
@@ -208,15 +240,18 @@ def run_attack(pipe: OraclePipeline, xa, xb, cfg: AttackCfg, start_noise=None, t
     untargeted: reference = clean fusion, ascend.   targeted: reference = fusion of (target,target), descend.
     start_noise (2,B,3,S,S) in [-1,1] scales to U(-eps,eps) (pre-generated so both sides share bits)."""
     direction = -1.0 if cfg.targeted else 1.0
+    # N-way form (SURVEY 8f-3): xa is a list of the N inputs and xb is None; start_noise is then (N,B,3,S,S)
+    inputs = list(xa) if xb is None else [xa, xb]
+    NI, B = len(inputs), inputs[0].shape[0]
+    split = lambda T: [T[k * B:(k + 1) * B] for k in range(NI)]
     with torch.no_grad():
-        ref_src = pipe.fused(target[0], target[1]) if cfg.targeted else pipe.fused(xa, xb)
+        ref_src = pipe.fused(*target) if cfg.targeted else pipe.fused(*inputs)
     ref_img, ref_feats = pipe.reference_of(ref_src)
     reg_refs = None
     if cfg.loss.c_reg != 0.0:
         with torch.no_grad():
-            reg_refs = (tuple(vgg_forward(pipe.vgg_sd, pipe.pool_in(xa))), tuple(vgg_forward(pipe.vgg_sd, pipe.pool_in(xb))))
-    X0 = torch.cat([xa, xb], 0)
-    B = xa.shape[0]
+            reg_refs = tuple(tuple(vgg_forward(pipe.vgg_sd, pipe.pool_in(x))) for x in inputs)
+    X0 = torch.cat(inputs, 0)
     if cfg.kind == "patch":
         patch = patch0.clone()
         lo = X0.flatten(1).min(1)[0].view(-1, 1, 1, 1)
@@ -229,8 +264,8 @@ def run_attack(pipe: OraclePipeline, xa, xb, cfg: AttackCfg, start_noise=None, t
     m = torch.zeros_like(X); v = torch.zeros_like(X)
     losses = []
     for it in range(cfg.steps):
-        L, img, ga, gb = pipe.input_grads(X[:B], X[B:], ref_img, ref_feats, cfg.loss, reg_refs=reg_refs)
-        g = torch.cat([ga, gb], 0)
+        L, img, gl = pipe.input_grads_n(split(X), ref_img, ref_feats, cfg.loss, reg_refs=reg_refs)
+        g = torch.cat(gl, 0)
         losses.append(L)
         if record is not None:
             record.append(dict(loss=L.clone(), grad=g.clone(), img=img.clone(), x=X.clone()))
@@ -246,7 +281,7 @@ def run_attack(pipe: OraclePipeline, xa, xb, cfg: AttackCfg, start_noise=None, t
         else:
             raise ValueError(cfg.kind)
     with torch.no_grad():
-        final = pipe.fused(X[:B], X[B:])
+        final = pipe.fused(*split(X))
     out = dict(x_adv=X, fused_adv=final, fused_ref=ref_img, losses=torch.stack(losses, 0) if losses else None)
     if cfg.kind == "patch":
         out["patch"] = patch

@@ -202,6 +202,87 @@ def test_attack_gradient_and_pgd_vs_oracle(fusion):
     assert (out["losses"][-1] >= out["losses"][0]).all()
 
 
+class _IRSEToy(torch.nn.Module):
+    """A small encoder with the layer types of the reference's e4e encoder, `Encoder4Editing(50, 'ir_se')`
+    (code/utils/model_utils.py:24; un-vendored): strided convs, BatchNorm (eval), PReLU, a squeeze-excitation gate, a residual
+    shortcut and a linear map to the W+ codes.  Stands for `net.encoder` as an arbitrary torch module."""
+
+    def __init__(self, n_latent, style_dim, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        nn = torch.nn
+        self.stem = nn.Sequential(nn.Conv2d(3, 16, 3, 1, 1, bias=False), nn.BatchNorm2d(16), nn.PReLU(16))
+        self.res = nn.Sequential(nn.BatchNorm2d(16), nn.Conv2d(16, 32, 3, 1, 1, bias=False), nn.PReLU(32),
+                                 nn.Conv2d(32, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32))
+        self.short = nn.Sequential(nn.Conv2d(16, 32, 1, 2, bias=False), nn.BatchNorm2d(32))
+        self.se = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(32, 8, 1, bias=False), nn.ReLU(), nn.Conv2d(8, 32, 1, bias=False),
+                                nn.Sigmoid())
+        self.head = nn.Linear(32 * 16, n_latent * style_dim)
+        self.head.weight.data.mul_(12.0)    # (keeps the attack's signal above the bf16 noise floor of the fused-image difference)
+        self.n_latent, self.style_dim = n_latent, style_dim
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        self.eval()
+
+    def forward(self, x):
+        x = self.stem(x)
+        r = self.res(x)
+        x = r * self.se(r) + self.short(x)
+        x = torch.nn.functional.adaptive_avg_pool2d(x, 4).flatten(1)
+        return self.head(x).view(x.shape[0], self.n_latent, self.style_dim)
+
+
+@pytest.mark.parametrize("fp32_mode_on", [False, True])
+def test_torch_module_encoder_on_the_gradient_path(fp32_mode_on):
+    """`net.encoder` as an arbitrary torch module (the real e4e encoder plugs in here): its forward / backward run
+    through autograd, fusion / synthesis / VGG / update on the CUDA schedules; gradient and a 3-step PGD against the oracle that
+    holds the same module (in fp32 on the CPU)."""
+    from oracle.pipeline import AttackCfg as OCfg, LossCfg as OLoss, OraclePipeline, run_attack as oracle_run
+    from sfattack import lib
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    spec, GP, es, EP, vsd, FP, xa, xb = _small_setup(size=32, fusion="spatial")
+    B = xa.shape[0]
+    enc_cpu = _IRSEToy(spec.n_latent, spec.style_dim, seed=3)
+    lat_avg = EP["latent_avg"]
+    pipe = OraclePipeline(spec, GP, es, EP, vsd, FP, fusion="spatial", vgg_res=32, encoder_module=enc_cpu, latent_avg=lat_avg)
+    enc_gpu = _IRSEToy(spec.n_latent, spec.style_dim, seed=3)
+    enc_gpu.load_state_dict(enc_cpu.state_dict())
+    enc_gpu = enc_gpu.to(DEV)
+    if fp32_mode_on:
+        lib.set_activation_dtype(torch.float32)
+    try:
+        eng = AttackEngine(spec, GP, es, None, vsd, FP, fusion="spatial", batch=B, device=DEV, loss=LossCfg(1.0, 1.0), vgg_res=32,
+                           vgg_width_div=4, encoder_module=enc_gpu, latent_avg=lat_avg)
+        g = torch.Generator().manual_seed(11)
+        noise = torch.rand(2, B, 3, 32, 32, generator=g) * 2 - 1
+        X0 = torch.cat([xa, xb])
+        Xs = torch.clamp(X0 + (8 / 255) * noise.reshape(X0.shape), 0, 1)
+        with torch.no_grad():
+            ref_img, ref_feats = pipe.reference_of(pipe.fused(xa, xb))
+        L_ref, _, ga, gb = pipe.input_grads(Xs[:B], Xs[B:], ref_img, ref_feats, OLoss(1.0, 1.0))
+        g_ref = torch.cat([ga, gb])
+        eng.set_inputs(xa.to(DEV), xb.to(DEV))
+        eng.compute_reference()
+        eng.x.copy_(Xs.to(DEV))
+        loss = eng.forward_backward()[0].clone()      # (engine-owned buffer: the PGD below overwrites it)
+        eng.check()
+        c = _cos(eng.full_res_grad(), g_ref)
+        steps = 3
+        out_ref = oracle_run(pipe, xa, xb, OCfg(kind="linf", steps=steps, loss=OLoss(1.0, 1.0)), start_noise=noise)
+        out = run_attack(eng, xa.to(DEV), xb.to(DEV), AttackCfg(kind="linf", steps=steps, graph=True), start_noise=noise)   # graph is ignored
+        same = ((out["x_adv"].cpu() - out_ref["x_adv"]).abs() < 1e-3).float().mean().item()
+    finally:
+        lib.set_activation_dtype(torch.bfloat16)
+    if fp32_mode_on:
+        assert _relerr(eng.ref_img, ref_img) < 1e-4 and _relerr(loss, L_ref) < 2e-3 and c > 0.9995 and same > 0.97, (c, same)
+    else:
+        assert _relerr(eng.ref_img, ref_img) < 2e-2 and _relerr(loss, L_ref) < 0.3 and c > 0.93 and same > 0.5, (c, same, _relerr(loss, L_ref))
+    assert not eng.graph_ok
+
+
 @pytest.mark.parametrize("kind", ["l2", "patch", "adam"])
 def test_other_update_rules_vs_oracle(kind):
     from oracle.pipeline import AttackCfg as OCfg, LossCfg as OLoss, OraclePipeline, run_attack as oracle_run
