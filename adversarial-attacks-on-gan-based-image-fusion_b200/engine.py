@@ -429,6 +429,8 @@ class SynthesisEngine:
         # every layer's demodulation and per-sample weights in two launches; demodulation rides on the weights wherever the
         # conv epilogue would apply it (the blur kernel of the unfused up-layers applies it itself, after the FIR)
         lib.demod_fwd_batched(s, self.q_cat, self.d_cat, self.style_tab, self.max_cout)
+        # (writing the later layers' weights on a side stream while the 4x4 .. 16x16 convs run was measured: 7.81 vs 7.78 ms -- the
+        #  weight stream competes with those L2-bound launches for the same bandwidth; one launch on the main stream stays)
         lib.modulate_weights_batched(self.wb_cat, s, self.wm_cat, self.d_cat, self.style_tab)
         for e in self.L:
             l = e["l"]

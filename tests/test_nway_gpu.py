@@ -151,3 +151,56 @@ def test_church_fusion_hierarchy_matches_generate_img_roles():
     finally:
         lib.set_activation_dtype(torch.bfloat16)
     assert _rel(img2, want) > 2e-3      # (random-init gates mix about half-half: roles differ by ~1e-2, two orders above the match)
+
+
+def test_ffhq_5way_hierarchy_at_1024_vs_oracle():
+    """The reference's ffhq fusion at its real geometry: five 1024x1024 inputs [mouth, background, hair, eyes, global]
+    (attack_main2.py:526), StyleGAN2-1024, hierarchy gate chain -- clean fusion, first gradient and one PGD step against the oracle
+    (fp32 on the same GPU, TF32 off) in the fp32 parity mode (north_star's 1e-3 tolerance), and the bf16 product path on the same
+    inputs held to the bf16 bounds of tests/test_fullsize_gpu.py."""
+    from oracle.pipeline import AttackCfg as OCfg, LossCfg as OLoss, OraclePipeline, run_attack as oracle_run
+    from sfattack import lib
+    from sfattack.attack_loop import AttackCfg, run_attack
+    from sfattack.engine import AttackEngine, LossCfg
+    from sfattack.params import EncSpec, gen_spec, make_encoder_params, make_generator_params, make_vgg_state_dict
+    S, n_in = 1024, 5
+    spec = gen_spec(S)
+    GP, es = make_generator_params(spec, 0), EncSpec(n_latent=spec.n_latent)
+    EP, vsd = make_encoder_params(es, 1), make_vgg_state_dict(2)
+    hier = _hier("ffhq", spec.s_dim)
+    to = lambda d: {k: v.to(DEV) for k, v in d.items()}
+    g = torch.Generator().manual_seed(71)
+    xs = [F.avg_pool2d(torch.rand(1, 3, S + 4, S + 4, generator=g), 5, 1) for _ in range(n_in)]
+    noise = torch.rand(n_in, 1, 3, S, S, generator=g) * 2 - 1
+    eps, alpha = 8 / 255, 2 / 255
+    pipe = OraclePipeline(spec, to(GP), es, to(EP), to(vsd), None, fusion="hierarchy")
+    pipe.hier = dict(hier, gates={p: to(v) for p, v in hier["gates"].items()})
+    rec = []
+    want = oracle_run(pipe, [x.to(DEV) for x in xs], None, OCfg(kind="linf", steps=1, eps=eps, alpha=alpha, loss=OLoss(1.0, 1.0)),
+                      start_noise=noise.to(DEV), record=rec)
+    torch.cuda.empty_cache()
+    scale = want["fused_ref"].abs().max().item()
+    for mode in ("fp32", "bf16"):
+        lib.set_activation_dtype(torch.float32 if mode == "fp32" else torch.bfloat16)
+        try:
+            eng = AttackEngine(spec, GP, es, EP, vsd, None, fusion="hierarchy", batch=1, device=DEV, loss=LossCfg(1.0, 1.0), n_inputs=n_in,
+                               hierarchy=hier)
+            rec_g = []
+            got = run_attack(eng, [x.to(DEV) for x in xs], None, AttackCfg(kind="linf", steps=1, eps=eps, alpha=alpha), start_noise=noise,
+                             record=rec_g)
+        finally:
+            lib.set_activation_dtype(torch.bfloat16)
+        ref_err = (got["fused_ref"] - want["fused_ref"]).abs().max().item()
+        g_ref, g_got = rec[0]["grad"], rec_g[0]["grad"]
+        c = _cos(g_got, g_ref)
+        per_in = [_cos(g_got[k:k + 1], g_ref[k:k + 1]) for k in range(n_in)]
+        band = g_ref.abs() > (1e-3 if mode == "fp32" else 5e-2) * g_ref.abs().mean()
+        step1 = ((got["x_adv"] - want["x_adv"]).abs() < 1e-3)[band].float().mean().item()
+        print(f"[ffhq 5-way 1024 {mode}] range +-{scale:.2f}: clean fusion max-abs err {ref_err:.2e}, grad cos {c:.6f} per input "
+              f"{[round(v, 4) for v in per_in]}, x_adv after the step within 1e-3 outside the tie band: {step1:.5f}")
+        del eng
+        torch.cuda.empty_cache()
+        if mode == "fp32":
+            assert ref_err < 1e-3 * max(1.0, scale) and c > 0.9995 and min(per_in) > 0.999 and step1 > 0.999
+        else:
+            assert ref_err < 0.015 * scale and c > 0.72 and step1 > 0.75

@@ -5,7 +5,7 @@ import collections, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "adversarial-attacks-on-gan-based-image-fusion_b200", "csrc")
-KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "LDG", "STG", "LDS", "STS", "FFMA", "FFMA2", "REDG", "SHFL"]
+KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "LDG", "STG", "LDS", "STS", "FFMA", "FFMA2", "FADD2", "FMUL2", "REDG", "SHFL"]
 
 
 def demangle(names):
