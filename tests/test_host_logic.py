@@ -104,3 +104,45 @@ def test_sharding_and_final_gather_two_ranks_gloo():
         p.join(60)
     assert res[0][1:3] == (0, 4) and res[1][1:3] == (4, 7)
     assert res[0][3] == res[1][3] == [float(i) for i in range(7)]
+
+
+@pytest.mark.parametrize("name,n_in", [("ffhq", 5), ("car", 4), ("church", 3)])
+def test_fusion_hierarchy_roles_match_generate_img_and_the_engine_chain(name, n_in):
+    """Host logic of the N-way gradient path: `fusion_hierarchy` (input INDEX per part) against the oracle's generate_img, which
+    swaps style TENSORS per part as the reference does (code/style_fusion_simple.py:84-104, roles of fusion() at
+    code/attack/attack_main2.py:526-566); and the engine's static gate chain (skip a base-assigned part only while nothing has
+    been gated in) against the oracle's value-based blend.  Tiny CPU generator; styles are passed as latents_type='s'."""
+    from oracle import stylegan2 as sg
+    from oracle.fusion_ref import PARTS, OracleFusion, blend, gate
+    from sfattack.params import gen_spec, make_fusion_params, make_generator_params
+    from sfattack.style_fusion_simple import _PARTS, fusion_hierarchy
+    assert _PARTS[name] == PARTS[name]
+    spec = gen_spec(16, style_dim=32, n_mlp=2, channels={4: 16, 8: 16, 16: 8})
+    GP = make_generator_params(spec, seed=0)
+    gates = {p: make_fusion_params(spec.s_dim, 30 + i) for i, p in enumerate(PARTS[name]) if p != "all"}
+    od = OracleFusion(name, sg.OracleGenerator(spec, GP), gates, mean_latent=torch.zeros(1, 32))
+    g = torch.Generator().manual_seed(1)
+    s = [torch.randn(1, spec.s_dim, generator=g) for _ in range(n_in)]
+    if name == "ffhq":      # [mouth, background, hair, eyes, global]
+        want, _ = od.generate_img(s[4], latents_type="s", hair=s[2], eyes=s[3], background=s[1], mouth=s[0])
+    elif name == "car":     # [wheel, bg_top, bg_bottom, body]
+        want, _ = od.generate_img(s[3], latents_type="s", wheels=s[0], bg_top=s[1], bg_bottom=s[2])
+    else:                   # [bg_top, bg_bottom, body]
+        want, _ = od.generate_img(s[2], latents_type="s", bg_top=s[0], bg_bottom=s[1])
+    h = fusion_hierarchy(name + "_encode", _PARTS[name], gates)
+    assert h["n_inputs"] == n_in and h["source"][0] == n_in - 1
+    got, _ = od.s_to_image(blend(h["parts"], gates, {p: s[k] for p, k in zip(h["parts"], h["source"])}))
+    torch.testing.assert_close(got, want)
+    # the engine's chain (AttackEngine.__init__, fusion="hierarchy")
+    base, chain = h["source"][0], []
+    for p, k in zip(h["parts"][1:], h["source"][1:]):
+        if not chain and k == base:
+            continue
+        chain.append((p, k))
+    out = s[base]
+    for p, k in chain:
+        out = gate(gates[p], out, s[k])
+    torch.testing.assert_close(od.s_to_image(out)[0], want)
+    assert len({k for _, k in chain} | {base}) == n_in        # every input takes part
+    with pytest.raises(ValueError):
+        fusion_hierarchy("bedroom", _PARTS[name], gates)
