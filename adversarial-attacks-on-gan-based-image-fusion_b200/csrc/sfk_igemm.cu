@@ -490,6 +490,7 @@ struct __align__(64) Igemm2Args {
   int f_wm[SFK_MAX_TAPS];
   int acc_blk[4];
   int merged;   // any f_wm != 1
+  int early;    // the epilogue releases the accumulator stage as soon as its last chunk sits in registers (before the arithmetic and stores)
 };
 
 // role-level cycle accounting (only when SFK_EP_PROFILE is set): [0] producer waiting for a free slot, [1] producer total,
@@ -889,7 +890,7 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
       const int ksplit = kF32 ? a.ksplit : 1;
       uint32_t acc_col = static_cast<uint32_t>(as * ksplit) * tile_cols;   // first TMEM column of the tile (half)
       // NC = 16 or 32 accumulator columns per step (32 whenever block_n allows: twice the independent work per TMEM round trip)
-      auto do_cols = [&](auto nc_tag, int acc, int c0, long pix) {
+      auto do_cols = [&](auto nc_tag, int acc, int c0, long pix, bool last_chunk) {
         constexpr int NC = decltype(nc_tag)::value;
         float v[NC], x[NC];
         long off = pix * a.out_c + n0 + c0;
@@ -918,10 +919,15 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
             for (int i = 0; i < NC; ++i) v[i] += u[i];
           }
         }
+        if (last_chunk && a.early) {   // the accumulator is in registers: hand the TMEM stage back before the arithmetic and the stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
         if (!(flags & SFK_EP_DSCALE) && (flags & (SFK_EP_NOISE | SFK_EP_BIAS))) {
           const float4* cb_ = reinterpret_cast<const float4*>(col_bias + c0);
-#pragma unroll
           const float2 nz2 = make_float2(nz, nz);
+#pragma unroll
           for (int i = 0; i < NC / 4; ++i) {   // packed fp32 (add.f32x2): half the issue slots of this issue/latency-bound loop
             const float4 bb = (flags & SFK_EP_BIAS) ? cb_[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 r0 = __fadd2_rn(make_float2(v[4 * i + 0], v[4 * i + 1]), __fadd2_rn(nz2, make_float2(bb.x, bb.y)));
@@ -1068,16 +1074,19 @@ __global__ void __launch_bounds__(kThreads, 2) igemm_tc2_kernel(const __grid_con
         }
         for (int acc = 0; acc < a.num_acc; ++acc) {
           const long pix = ((static_cast<long>(n) * a.num_acc + acc) * a.out_h + h) * a.out_w + w;
+          const bool last_acc = half == m2n - 1 && acc == a.num_acc - 1;
           if ((a.block_n & 31) == 0 && (!v_d2s || ((a.out_c >> 2) & 31) == 0)) {
-            for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix);
+            for (int c0 = 0; c0 < a.block_n; c0 += 32) do_cols(std::integral_constant<int, 32>{}, acc, c0, pix, last_acc && c0 + 32 >= a.block_n);
           } else {
-            for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix);
+            for (int c0 = 0; c0 < a.block_n; c0 += 16) do_cols(std::integral_constant<int, 16>{}, acc, c0, pix, last_acc && c0 + 16 >= a.block_n);
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (one arrival per warp)
+      if (!a.early) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage drained (one arrival per warp)
+      }
     }
     if (v_ts && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
     if (reg_gs) {
@@ -1803,6 +1812,8 @@ int build_plan(const sfk_igemm_desc* d, IgemmPlan* P) {
     D.plane = hg[g].plane; D.dx_min = hg[g].dx_min; D.dy_min = hg[g].dy_min; D.map = hg[g].map; D.bytes = hg[g].bytes; D.ntaps = hg[g].ntaps;
     for (int j = 0; j < kMaxGroupTaps; ++j) { D.brow[j] = hg[g].brow[j]; D.bidx[j] = hg[g].bidx[j]; }
   }
+  static const int early_env = env_int("SFK_EARLY_RELEASE", 1);
+  k.early = early_env ? 1 : 0;
   static_assert(sizeof(Igemm2Args) <= 4096, "kernel argument block must stay in the 4 KB constant bank window");
   P->smem = static_cast<size_t>(stages) * stage_bytes + resident + staging + 1024;
   P->grid = dim3(static_cast<unsigned>(ctas_per_group), static_cast<unsigned>(groups_total));
