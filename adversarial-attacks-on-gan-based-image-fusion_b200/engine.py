@@ -535,8 +535,8 @@ class AttackEngine:
         encoder stand-in on the gradient path -- e.g. the reference's `net.encoder` = e4e `Encoder4Editing(50,'ir_se')`
         (code/utils/model_utils.py:24; un-vendored upstream).  Its forward and backward run through torch autograd on
         the engine's stream; everything downstream (fusion, synthesis, VGG, update) stays on the CUDA schedules.  `latent_avg`
-        (n_latent,512) is added to its codes as get_latents does (attack_main2.py:137-146).  EP is then only read for nothing and
-        may be None; CUDA-graph replay is off for such an engine (autograd allocates)."""
+        (n_latent,512) is added to its codes as get_latents does (attack_main2.py:137-146).  EP (the stand-in's weights) is not
+        read then and may be None; CUDA-graph replay is off for such an engine (autograd allocates)."""
         lib.load()
         self.dev = torch.device(device)
         self.gspec, self.espec, self.fusion, self.B = gspec, espec, fusion, batch

@@ -13,6 +13,11 @@ What is pinned / unpinned:
   * Adam-on-pixels: code/attack/attack_main2.py:606,614-653 (torch.optim.Adam defaults).
   * L2 variant, encoder stand-in and pair fusion: NOT in the reference (SURVEY F2-F4, D1, A.4);
     builder-defined here -> PARITY UNPINNED for those pieces.
+  * N-way fusion (`fusion="hierarchy"`, OraclePipeline.hier): the part assignment is the reference's
+    (generate_img's swap lists, code/style_fusion_simple.py:84-104; roles of fusion(),
+    code/attack/attack_main2.py:526-566); the blender itself is the gate-chain stand-in of
+    oracle/fusion_ref.py (un-vendored FusionNets) -> PARITY UNPINNED for the gates.
+  * `encoder_module`: any torch module in `net.encoder`'s place (code/utils/model_utils.py:24).
 """
 from __future__ import annotations
 
