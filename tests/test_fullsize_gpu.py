@@ -131,7 +131,7 @@ def test_1024_gradient_and_pgd2_vs_oracle(mode, fusion):
         # (seeds 61-64, SFK_TEST_SEED) with the first conv on the CUDA cores / on the tensor cores, two kernels of equal accuracy
         # (tools/diag_c3b.py, diag_c3c.py: both within 0.4 % of one bf16 ulp of the fp64 conv): gradient cosine 0.94/0.88, 0.80/0.78,
         # 0.80/0.83, 0.87/0.81; sign agreement 0.79-0.90; pixels within 1e-3 after two steps 0.54-0.65; outcome MSE -35 %..+12 %
-        # of the oracle's (gpurun_out/s4e_seeds.log).  The bounds below hold that whole range; what bf16 storage is HELD to is the
+        # of the oracle's (profiles/logs_r2/s4e_seeds.log).  The bounds below hold that whole range; what bf16 storage is HELD to is the
         # success criterion of test_identical_attack_success_outcomes_on_16_fixed_seed_pairs -- north_star's 1e-3 is the fp32 mode's.
         assert ref_err < 0.015 * scale and loss_abs < (0.01 * scale) ** 2 and cos > 0.72 and agree > 0.75 and within > 0.5
         assert abs(d_got - d_ref) <= 0.4 * d_ref
