@@ -146,3 +146,39 @@ def test_fusion_hierarchy_roles_match_generate_img_and_the_engine_chain(name, n_
     assert len({k for _, k in chain} | {base}) == n_in        # every input takes part
     with pytest.raises(ValueError):
         fusion_hierarchy("bedroom", _PARTS[name], gates)
+
+
+def test_run_artifacts_in_the_reference_formats(tmp_path):
+    """parameters.txt lines (attack_main2.py:975-988), the `.npz`-named torch pickles in benign/ and adversarial/ (:1098-1111) and the
+    results header / row order (interpolation.py:1256-1258)."""
+    import argparse
+    from sfattack import artifacts as A
+    root = A.new_run_folder(str(tmp_path / "run"))
+    assert A.new_run_folder(root) == root
+    args = argparse.Namespace(dataset_name="ffhq_encode", epochs=1, max_count=50, patch_size=0.1, train_size=2000, patch_type="square",
+                              lr=0.01, use_generate_img=False)
+    pf = A.write_parameters(root, "white_box", args, 1024, 100)
+    lines = open(pf).read().splitlines()
+    assert lines == ["adversarial attack white_box", "dataset ffhq_encode", "dataset size 1024", "epochs 1", "max_count 50",
+                     "patch_size 0.1", "train_size 2000", "patch_type square", "white-box max_iter 100", "white-box lr 0.01",
+                     "use_generate_img False"]
+    A.write_parameters(root, "patch", args, 1024, 100)                         # the reference opens the file with 'a'
+    assert len(open(pf).read().splitlines()) == 22
+    rec = A.RunRecorder(root)
+    x = torch.rand(5, 3, 8, 8)
+    rec.add(all_inputs=x, all_adv_inputs=x + 0.01)
+    rec.add(all_inputs=x * 0.5, all_adv_inputs=x * 0.5 + 0.01, all_rec_loss=torch.rand(5))
+    with pytest.raises(KeyError):
+        rec.add(bogus=x)
+    paths = rec.save()
+    assert sorted(os.path.relpath(p, root) for p in paths) == ["adversarial/all_adv_inputs.npz", "benign/all_inputs.npz",
+                                                              "benign/all_rec_loss.npz"]
+    back = torch.load(os.path.join(root, "benign", "all_inputs.npz"))
+    assert back.shape == (10, 3, 8, 8) and torch.equal(back[:5], x)
+    cols = A.result_columns(A.DATASET_N["car"])
+    assert len(cols) == 4 + 6 * 5 and cols[:4] == ["noise"] * 4 and cols[4:9] == ["cri_spati"] * 5 and cols[-5:] == ["ssmi_arith"] * 5
+    d = {i: float(i) for i in range(5)}
+    row = A.result_row([0.1, 0.2, 0.3, 0.4], d, d, d, d, d, d)
+    assert len(row) == len(cols) and row[4:9] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    with pytest.raises(ValueError):
+        A.result_row([0.1], d, d, d, d, d, d)
