@@ -182,3 +182,32 @@ def test_run_artifacts_in_the_reference_formats(tmp_path):
     assert len(row) == len(cols) and row[4:9] == [0.0, 1.0, 2.0, 3.0, 4.0]
     with pytest.raises(ValueError):
         A.result_row([0.1], d, d, d, d, d, d)
+
+
+def test_first_conv_hi_lo_operand_layout_on_cpu():
+    """The packed operand of the first conv (sfk_c3_pack) and its weight layouts (lib.c3_pack_weights), emulated on the CPU with the
+    tap lists the kernel gets: forward = x.hi*W.hi + x.lo*W.hi + x.hi*W.lo within 2^-16 of the fp64 conv (a plain bf16 copy of x
+    would be 2^-9), data gradient = channels [0:3] + [3:6] of the packed gradient."""
+    from sfattack import lib
+    g = torch.Generator().manual_seed(3)
+    N, H, W_, Cout = 2, 7, 9, 16
+    x = torch.rand(N, 3, H, W_, generator=g) * 2 - 1
+    w = torch.randn(Cout, 3, 3, 3, generator=g) * 0.3
+    wf, wb = lib.c3_pack_weights(w)
+    assert wf.shape == (9 * Cout, 16) and wb.shape == (9 * 16, Cout) and wf.dtype == torch.bfloat16
+    hi = x.bfloat16().float()
+    lo = (x - hi).bfloat16().float()
+    xp = torch.zeros(N, H, W_, 16)
+    xp[..., 0:3], xp[..., 3:6], xp[..., 6:9] = hi.permute(0, 2, 3, 1), lo.permute(0, 2, 3, 1), hi.permute(0, 2, 3, 1)
+    got = emulate_igemm(xp.double()[:, None], wf.double(), lib.conv3x3_taps(Cout), (H, W_), 1, Cout)[:, 0].permute(0, 3, 1, 2)
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 2 ** -15 * scale
+    plain = F.conv2d(hi.double(), w.bfloat16().double(), padding=1)           # what a bf16 copy of image and weights would give
+    assert (plain - ref).abs().max().item() > 20 * (got - ref).abs().max().item()
+    gz = torch.randn(N, Cout, H, W_, generator=g).bfloat16().double()
+    gp = emulate_igemm(gz.permute(0, 2, 3, 1)[:, None], wb.double(), lib.conv3x3_dgrad_taps(16), (H, W_), 1, 16)[:, 0]
+    gx = (gp[..., 0:3] + gp[..., 3:6]).permute(0, 3, 1, 2)
+    gref = F.conv_transpose2d(gz, w.double(), padding=1)
+    assert (gx - gref).abs().max().item() < 2 ** -15 * gref.abs().max().item()
+    assert gp[..., 6:].abs().max().item() == 0
