@@ -104,7 +104,14 @@ def _recon_engine(Model, vgg, batch, device, loss: ReconLossCfg) -> ReconAttackE
     key = (id(dec), _version(dec), id(enc), _version(enc), id(vgg), _version(vgg), batch, str(torch.device(device)),
            tuple(vars(loss).values()), lib.mode_key())
     eng = _ENGINES.get(key)
-    if eng is None:
+    if eng is None and isinstance(enc, torch.nn.Module):
+        # `Model.encoder` is a real torch encoder (the reference's e4e network, code/utils/model_utils.py:24): it stays a torch
+        # module on the gradient path; the reference feeds it the image pooled to 256x256 (attack_main2.py:590-591,619)
+        from ..params import EncSpec
+        es = EncSpec(n_latent=dec.spec.n_latent, style_dim=dec.spec.style_dim, in_res=min(256, dec.spec.size))
+        eng = ReconAttackEngine(dec.spec, dec.params, es, None, vgg.sd, batch=batch, device=str(device), loss=loss,
+                                vgg_res=es.in_res, vgg_width_div=vgg.width_div, encoder_module=enc)
+    elif eng is None:
         eng = ReconAttackEngine(dec.spec, dec.params, enc.spec, enc.params, vgg.sd, batch=batch, device=str(device), loss=loss,
                                 vgg_res=enc.spec.in_res, vgg_width_div=vgg.width_div)
         eng._owners = (dec, enc, vgg)        # the ids in the key stay valid as long as the engine lives

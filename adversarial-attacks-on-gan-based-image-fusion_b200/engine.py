@@ -798,7 +798,11 @@ class ReconAttackEngine:
     Images are in the reference's [-1,1] range."""
 
     def __init__(self, gspec: GenSpec, GP, espec: EncSpec, EP, vgg_sd, batch: int = 1, device="cuda:0",
-                 loss: Optional[ReconLossCfg] = None, vgg_res: int = 256, vgg_width_div: int = 1):
+                 loss: Optional[ReconLossCfg] = None, vgg_res: int = 256, vgg_width_div: int = 1,
+                 encoder_module: Optional[torch.nn.Module] = None):
+        """encoder_module: `Model.encoder` as any torch module (x (n,3,R,R) in [-1,1] -> codes (n, n_latent, 512) or (n,512)); its
+        forward / backward then run through autograd, the rest of the loop on the CUDA schedules (espec supplies n_latent,
+        style_dim and in_res; EP may be None; no CUDA-graph replay)."""
         lib.load()
         self.dev = torch.device(device)
         self.cfg = loss or ReconLossCfg()
@@ -808,9 +812,16 @@ class ReconAttackEngine:
         B, dev, S, R = batch, self.dev, self.S, self.R
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
-        enc_w = [(EP[f"convs.{i}.weight"], EP[f"convs.{i}.bias"]) for i in range(len(espec.widths))]
-        self.enc = ConvStack(encoder_layers(espec), enc_w, B, R, dev, self.err)
-        self.head_w, self.head_b = f32(EP["head.weight"]), f32(EP["head.bias"])     # optimize_vgg calls encoder() directly: no latent_avg
+        self.enc_module, self.espec = encoder_module, espec
+        self.graph_ok = encoder_module is None
+        if encoder_module is None:
+            enc_w = [(EP[f"convs.{i}.weight"], EP[f"convs.{i}.bias"]) for i in range(len(espec.widths))]
+            self.enc = ConvStack(encoder_layers(espec), enc_w, B, R, dev, self.err)
+            self.head_w, self.head_b = f32(EP["head.weight"]), f32(EP["head.bias"])     # optimize_vgg calls encoder() directly: no latent_avg
+        else:
+            self.enc = None
+            for p_ in encoder_module.parameters():
+                p_.requires_grad_(False)
         L, D, cl = espec.n_latent, espec.style_dim, espec.widths[-1]
         self.LD = L * D
         self.feat, self.gfeat = _empty((B, cl), dev, torch.float32), _empty((B, cl), dev, torch.float32)
@@ -833,6 +844,15 @@ class ReconAttackEngine:
 
     def _encode(self, x):
         lib.avgpool_affine_fwd(x, self.xin, self.k_in, 1.0, 0.0)
+        if self.enc_module is not None:
+            self._xin_leaf = self.xin.detach().requires_grad_(True)
+            with torch.enable_grad():
+                codes = self.enc_module(self._xin_leaf)
+            if codes.ndim == 2:
+                codes = codes.unsqueeze(1).expand(-1, self.espec.n_latent, -1)
+            self._codes_t = codes
+            self.codes.copy_(codes.detach().to(torch.float32))
+            return
         lib.gap_fwd(self.enc.forward(self.xin), self.feat)
         lib.linear_fwd(self.feat, self.head_w, self.head_b, self.codes.view(self.B, -1))
 
@@ -881,9 +901,14 @@ class ReconAttackEngine:
         gs = self.syn.backward(self.g_rec)
         self.syn.wplus_grad_from_styles(gs, self.gw)
         lib.axpby(self.gcodes, self.gw, self.gcodes, 1.0, 1.0)
-        lib.linear_bwd(self.gcodes.view(B, -1), self.head_w, self.gfeat)
-        lib.gap_bwd(self.enc.out[-1], self.gfeat, self.enc.g[-1])
-        g_enc = self.enc.backward(top_grad_ready=True)
+        if self.enc_module is not None:
+            (g_enc,) = torch.autograd.grad(self._codes_t, self._xin_leaf, self.gcodes.to(self._codes_t.dtype))
+            g_enc = g_enc.to(torch.float32).contiguous()
+            self._codes_t = None
+        else:
+            lib.linear_bwd(self.gcodes.view(B, -1), self.head_w, self.gfeat)
+            lib.gap_bwd(self.enc.out[-1], self.gfeat, self.enc.g[-1])
+            g_enc = self.enc.backward(top_grad_ready=True)
         if c.w_lpips_img != 0.0:
             self.vgg_img.forward(self.xin)
             g_v = self.vgg_img.backward(self.org_feats, c.w_lpips_img, self.loss)

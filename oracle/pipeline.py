@@ -317,11 +317,17 @@ class ReconLossCfg:
 
 
 def optimize_vgg_oracle(gspec, GP, espec, EP, vgg_sd, img, img_target, cfg: ReconLossCfg, n_iters: int, lr: float,
-                        record=None):
+                        record=None, encoder_module=None):
     """Restatement of the reference's live loop (attack_main2.py:584-671): Adam on the pixels of `img` ([-1,1]) against the
     encoder->decoder reconstruction; per-sample means (the reference runs batch 1).  No file I/O."""
     k = gspec.size // espec.in_res
     pool = (lambda t: F.avg_pool2d(t, k, k)) if k > 1 else (lambda t: t)
+    if encoder_module is not None:           # `Model.encoder` as any torch module (the reference's e4e encoder, model_utils.py:24)
+        def encoder_forward(_EP, _spec, t):  # noqa: F811  (shadows the stand-in for this call)
+            c = encoder_module(t)
+            return c.unsqueeze(1).expand(-1, espec.n_latent, -1) if c.ndim == 2 else c
+    else:
+        encoder_forward = globals()["encoder_forward"]
     img_org = img.clone().detach()
     with torch.no_grad():                                                    # :597-603
         latent_target = encoder_forward(EP, espec, pool(img_target))

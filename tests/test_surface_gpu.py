@@ -429,3 +429,70 @@ def test_engine_cache_follows_weights_and_library_mode():
     e3 = _recon_engine(net, vgg, 1, DEV, cfg)
     assert e3 is not e1
     assert len(_ENGINES) <= 4
+
+
+class _ToyE4E(torch.nn.Module):
+    """`net.encoder` as a real torch module with the layer types of the reference's e4e encoder (`Encoder4Editing(50,'ir_se')`,
+    code/utils/model_utils.py:24, un-vendored): strided convs, eval-mode BatchNorm, PReLU, an SE gate, a residual shortcut."""
+
+    def __init__(self, n_latent, style_dim, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        nn = torch.nn
+        self.stem = nn.Sequential(nn.Conv2d(3, 16, 3, 1, 1, bias=False), nn.BatchNorm2d(16), nn.PReLU(16))
+        self.res = nn.Sequential(nn.BatchNorm2d(16), nn.Conv2d(16, 32, 3, 1, 1, bias=False), nn.PReLU(32),
+                                 nn.Conv2d(32, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32))
+        self.short = nn.Sequential(nn.Conv2d(16, 32, 1, 2, bias=False), nn.BatchNorm2d(32))
+        self.se = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(32, 8, 1, bias=False), nn.ReLU(), nn.Conv2d(8, 32, 1, bias=False),
+                                nn.Sigmoid())
+        self.head = nn.Linear(32 * 16, n_latent * style_dim)
+        self.head.weight.data.mul_(4.0)
+        self.n_latent, self.style_dim = n_latent, style_dim
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        self.eval()
+
+    def forward(self, x):
+        x = self.stem(x)
+        r = self.res(x)
+        x = r * self.se(r) + self.short(x)
+        return self.head(F.adaptive_avg_pool2d(x, 4).flatten(1)).view(x.shape[0], self.n_latent, self.style_dim)
+
+
+def test_optimize_vgg_with_a_torch_module_encoder(fp32_mode, tmp_path):
+    """The reference's live loop (attack_main2.py:584-671) with `Model.encoder` a real torch module: optimize_vgg
+    keeps it on the gradient path through autograd; first loss / gradient and a 5-step Adam trajectory against the oracle holding
+    the same module on the CPU."""
+    from oracle.pipeline import ReconLossCfg as OCfg, optimize_vgg_oracle
+    from sfattack.attack.attack_main2 import LOSS_MENUS, _recon_engine, optimize_vgg
+    from sfattack.params import EncSpec, make_vgg_state_dict
+    from sfattack.vgg import vgg16
+    net = _small_net()
+    dec = net.decoder
+    enc_cpu = _ToyE4E(dec.spec.n_latent, dec.spec.style_dim, seed=7)
+    enc_gpu = _ToyE4E(dec.spec.n_latent, dec.spec.style_dim, seed=7)
+    enc_gpu.load_state_dict(enc_cpu.state_dict())
+    net.encoder = enc_gpu.to(DEV)
+    vsd = make_vgg_state_dict(5, width_div=4)
+    vgg = vgg16(vsd, DEV)
+    g = torch.Generator().manual_seed(2)
+    img, tgt = _smooth(g, 2, 3, 32, 32), _smooth(g, 2, 3, 32, 32)
+    cfg = LOSS_MENUS["interpolation"]
+    es = EncSpec(n_latent=dec.spec.n_latent, style_dim=dec.spec.style_dim, in_res=32)
+    args = argparse.Namespace(lr=5e-3, save_img=False)
+    rec = []
+    want = optimize_vgg_oracle(dec.spec, dec.params, es, None, vsd, img, tgt, OCfg(**vars(cfg)), 5, args.lr, record=rec,
+                               encoder_module=enc_cpu)
+    got = optimize_vgg(0, net, vgg, img.to(DEV), tgt.to(DEV), str(tmp_path), DEV, "x", args, n_iters=5, loss=cfg)
+    assert _rel(got.cpu() - img, want - img) < 5e-2, _rel(got.cpu() - img, want - img)
+    eng = _recon_engine(net, vgg, 2, DEV, cfg)
+    assert eng.enc_module is net.encoder and not eng.graph_ok
+    eng.set_inputs(img.to(DEV), tgt.to(DEV))
+    loss, _, _ = eng.forward_backward()
+    eng.check()
+    assert _rel(loss, rec[0]["loss"]) < 1e-3
+    gf = eng.full_res_grad().cpu()
+    cos = float((gf.flatten() @ rec[0]["grad"].flatten()) / (gf.norm() * rec[0]["grad"].norm()))
+    assert cos > 0.9999, cos
